@@ -1,0 +1,228 @@
+"""Device backend of a dense Elastic Table: block slabs in HBM, shared by all GPUs.
+
+Every block is a slab [rows_per_block, row_stride] in the OWNER GPU's HBM, allocated from a
+PeerArena whose segments are CUDA-IPC mapped by all executors.  The replicated ownership array
+of the reference (OwnershipCache.java) becomes `block_ptrs`: an int64[num_blocks] tensor in every
+GPU's memory holding, for each block, the virtual address of the slab *as mapped in that
+process*.  Kernels (ops/csrc/table_ops.cu, mlr_ops.cu ...) resolve key -> (block, slot) -> address
+and load / reduce straight into the owner's memory over NVLink.
+
+Table semantics kept from the reference:
+  * block -> owner map, initial placement round-robin `block % num_executors` (BlockManager.java:76-88)
+  * hashed / ordered partitioning (partitioner.py)
+  * update function applied at the owner (fused into the PUSH kernel)
+  * lazy initValue becomes eager, key-deterministic initialisation at table creation
+  * block migration = bulk slab copy on a side stream + pointer flip on every GPU
+    (MigrationExecutor.java:338-414), checkpoint = per-block files (checkpoint.py)
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..parallel.peer import PeerArena, PeerGroup
+from .config import TableConfiguration
+from .partitioner import PART_HASHED, PART_ORDERED
+from .update_function import DEV_ADAGRAD, make_update_function
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class DeviceTable:
+    """SPMD handle: every rank of `group` constructs it collectively with the same conf."""
+
+    def __init__(self, conf: TableConfiguration, arena: PeerArena, group: Optional[PeerGroup] = None,
+                 block_owners: Optional[Sequence[int]] = None, init: bool = True) -> None:
+        from ..ops import native
+        assert conf.dense, "device tables are dense slab tables"
+        self._n = native()
+        self.conf = conf
+        self.arena = arena
+        self.group = group or arena.group
+        self.rank, self.world = self.group.rank, self.group.world
+        self.device = torch.device("cuda", arena.device)
+        self.update_fn = make_update_function(conf.update_function)
+        self.torch_dtype = torch.float32 if conf.dtype == "float32" else torch.int32
+        self.num_blocks = conf.num_total_blocks
+        self.rows_per_block = max(1, -(-conf.capacity // self.num_blocks))
+        width = conf.row_dim * (2 if self.update_fn.device_fn == DEV_ADAGRAD else 1)
+        self.row_dim = conf.row_dim
+        self.row_stride = _round_up(width, 32)
+        if self.update_fn.device_fn == DEV_ADAGRAD:
+            self.row_stride = 2 * _round_up(conf.row_dim, 32)   # kernel expects h at stride/2
+        self.mode = PART_ORDERED if conf.is_ordered else PART_HASHED
+        self.block_bytes = self.rows_per_block * self.row_stride * 4
+        self.owners: List[int] = list(block_owners) if block_owners is not None else \
+            [b % self.world for b in range(self.num_blocks)]
+        # local slabs
+        self._local_ptr: Dict[int, int] = {}
+        self._loc: Dict[int, Tuple[int, int, int]] = {}   # block -> (rank, seg, offset) for ALL blocks
+        for b in range(self.num_blocks):
+            if self.owners[b] == self.rank:
+                p, si, off = arena.alloc(self.block_bytes)
+                self._local_ptr[b] = p
+                self._loc[b] = (self.rank, si, off)
+        # pointer table lives in the arena too (so that a migrating peer can flip it remotely)
+        self._ptr_tbl_ptr, tsi, toff = arena.alloc(self.num_blocks * 8)
+        self.block_ptrs = arena.tensor(self._ptr_tbl_ptr, [self.num_blocks], torch.int64)
+        self._ptr_tbl_loc = (self.rank, tsi, toff)
+        self._exchange()
+        if init:
+            self.init_local_blocks()
+        self.group.barrier()
+
+    # ---- handle exchange & pointer table ----
+    def _exchange(self) -> None:
+        mine = {"rank": self.rank,
+                "blocks": {b: loc for b, loc in self._loc.items() if loc[0] == self.rank},
+                "handles": {si: self.arena.segment_handle(si) for si in range(self.arena.num_segments())},
+                "ptr_tbl": self._ptr_tbl_loc}
+        allinfo = self.group.all_gather_object(mine)
+        self._peer_tbl_ptrs: List[int] = [0] * self.world
+        ptrs = np.zeros(self.num_blocks, dtype=np.int64)
+        for info in allinfo:
+            r = info["rank"]
+            for si, h in info["handles"].items():
+                self.arena.map_peer(r, si, h)
+            for b, (rr, si, off) in info["blocks"].items():
+                self._loc[b] = (rr, si, off)
+                ptrs[b] = self.arena.resolve(rr, si, off)
+            _, tsi, toff = info["ptr_tbl"]
+            self._peer_tbl_ptrs[r] = self.arena.resolve(r, tsi, toff)
+        assert (ptrs != 0).all(), "some blocks have no owner slab"
+        self.block_ptrs.copy_(torch.from_numpy(ptrs))
+        self._peer_tbl_ptrs_dev = torch.tensor(self._peer_tbl_ptrs, dtype=torch.int64, device=self.device)
+
+    def _key_base_stride(self, b: int) -> Tuple[int, int]:
+        return (b * self.rows_per_block, 1) if self.mode == PART_ORDERED else (b, self.num_blocks)
+
+    def init_local_blocks(self) -> None:
+        spec = self.update_fn.init_spec()
+        for b, p in self._local_ptr.items():
+            kb, ks = self._key_base_stride(b)
+            if self.torch_dtype == torch.int32 or spec["kind"] == 0:
+                self.local_block(b).zero_()
+            else:
+                self._n.init_slab(p, self.rows_per_block, self.row_stride, self.row_dim, spec["kind"],
+                                  spec["a"], spec["b"], spec["seed"], kb, ks)
+                if self.update_fn.device_fn == DEV_ADAGRAD:
+                    self.local_block(b)[:, self.row_stride // 2:].zero_()
+
+    # ---- views ----
+    def view(self) -> Tuple[torch.Tensor, int, int, int, int]:
+        """(block_ptrs, rows_per_block, row_stride, row_dim, mode): the kernel-side TableView."""
+        return self.block_ptrs, self.rows_per_block, self.row_stride, self.row_dim, self.mode
+
+    def local_block_ids(self) -> List[int]:
+        return sorted(self._local_ptr)
+
+    def local_block(self, b: int) -> torch.Tensor:
+        return self.arena.tensor(self._local_ptr[b], [self.rows_per_block, self.row_stride], self.torch_dtype)
+
+    def keys_of_block(self, b: int) -> np.ndarray:
+        if self.mode == PART_ORDERED:
+            lo = b * self.rows_per_block
+            return np.arange(lo, min(self.conf.capacity, lo + self.rows_per_block), dtype=np.int64)
+        return np.arange(b, self.conf.capacity, self.num_blocks, dtype=np.int64)
+
+    def nbytes_local(self) -> int:
+        return len(self._local_ptr) * self.block_bytes
+
+    # ---- data plane ----
+    def pull(self, keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """K1: gather rows by key from whichever GPU owns them."""
+        from ..ops import count_launch
+        if out is None:
+            out = torch.empty((keys.numel(), self.row_dim), dtype=self.torch_dtype, device=self.device)
+        self._n.table_pull(*self.view(), keys, out)
+        count_launch()
+        return out
+
+    def push(self, keys: torch.Tensor, deltas: torch.Tensor) -> None:
+        """K2 fused with the table's update function, executed in the owner's HBM."""
+        from ..ops import count_launch
+        fn = self.update_fn.device_fn
+        assert fn is not None, f"update function {self.update_fn.name} has no device implementation"
+        p = self.update_fn.device_params()
+        self._n.table_push(*self.view(), keys, deltas, fn, p["step"], p["lo"], p["hi"], p["eps"])
+        count_launch()
+
+    def push_sparse_i32(self, keys: torch.Tensor, topics: torch.Tensor, deltas: torch.Tensor) -> None:
+        """K2+K5: LDA sparse (row, topic, delta) triples with clamp>=0 and nnz bookkeeping."""
+        from ..ops import count_launch
+        self._n.table_push_sparse_i32(*self.view(), keys, topics, deltas, self.row_dim - 1)
+        count_launch()
+
+    def put_rows(self, keys: torch.Tensor, values: torch.Tensor) -> None:
+        from ..ops import count_launch
+        self._n.table_push(*self.view(), keys, values.contiguous(), 3, 0.0, 0.0, 0.0, 0.0)
+        count_launch()
+
+    def scale_local(self, factor: float) -> None:
+        """Owner-side decay of the local shard (L2 term of MLR applied at the owner)."""
+        for b in self._local_ptr:
+            self.local_block(b).mul_(factor)
+
+    # ---- elasticity: block migration (collective over the group) ----
+    def migrate_block(self, block: int, dst_rank: int, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Move `block` to `dst_rank`: slab copy by the receiver on a side stream, then the
+        pointer flip on every GPU.  Callers quiesce accessors of THIS table at a mini-batch
+        boundary (other jobs keep running; the copy overlaps their compute)."""
+        from ..ops import count_launch
+        src_rank = self.owners[block]
+        if src_rank == dst_rank:
+            return
+        new_loc = None
+        if self.rank == dst_rank:
+            p, si, off = self.arena.alloc(self.block_bytes)
+            new_loc = (self.rank, si, off, self.arena.segment_handle(si))
+        infos = self.group.all_gather_object(new_loc)
+        rr, si, off, handle = infos[dst_rank]
+        if self.rank == dst_rank:
+            src_va = int(self.block_ptrs[block].item())
+            s = stream or torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._n.migrate_copy(src_va, p, self.block_bytes)
+                count_launch()
+            s.synchronize()
+            self._local_ptr[block] = p
+        self.group.barrier()          # data has landed at the receiver
+        self.arena.map_peer(rr, si, handle)
+        new_va = self.arena.resolve(rr, si, off)
+        self.block_ptrs[block] = new_va   # ownership flip (local table of this GPU)
+        self._loc[block] = (rr, si, off)
+        self.owners[block] = dst_rank
+        torch.cuda.synchronize(self.device)
+        self.group.barrier()          # nobody references the old slab any more
+        if self.rank == src_rank:
+            self.arena.free(self._local_ptr.pop(block))
+
+    # ---- host import / export (checkpoint, tests) ----
+    def export_block(self, b: int) -> Tuple[np.ndarray, np.ndarray]:
+        keys = self.keys_of_block(b)
+        rows = self.local_block(b)[: len(keys), : self.row_dim].cpu().numpy()
+        return keys, rows
+
+    def import_block(self, b: int, keys: np.ndarray, rows: np.ndarray) -> None:
+        if len(keys) == 0:
+            return
+        keys = np.asarray(keys, dtype=np.int64)
+        slots = (keys % self.rows_per_block) if self.mode == PART_ORDERED else (keys // self.num_blocks)
+        blk = self.local_block(b)
+        blk[torch.from_numpy(slots).to(self.device), : rows.shape[1]] = torch.from_numpy(np.ascontiguousarray(rows)).to(self.device)
+
+    def to_dense(self) -> torch.Tensor:
+        """Gather the whole table [capacity, row_dim] (tests / evaluation of small models)."""
+        keys = torch.arange(self.conf.capacity, dtype=torch.int64, device=self.device)
+        return self.pull(keys)
+
+    def close(self) -> None:
+        for p in self._local_ptr.values():
+            self.arena.free(p)
+        self._local_ptr.clear()
+        self.arena.free(self._ptr_tbl_ptr)

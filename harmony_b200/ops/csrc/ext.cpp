@@ -1,0 +1,63 @@
+// pybind11 bindings of the harmony_b200 native runtime (sm_100a kernels + peer arena).
+#include <torch/extension.h>
+#include <string>
+#include <vector>
+
+namespace hb {
+// arena.cpp
+int64_t arena_create(int64_t device, int64_t bytes);
+int64_t arena_alloc(int64_t id, int64_t bytes);
+void arena_free(int64_t id, int64_t ptr);
+std::vector<int64_t> arena_stats(int64_t id);
+void arena_destroy(int64_t id);
+py::bytes ipc_export(int64_t ptr);
+int64_t ipc_open(std::string handle_bytes, int64_t device);
+void ipc_close(int64_t ptr);
+bool enable_peer_access(int64_t device, int64_t peer);
+at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, std::vector<int64_t> strides,
+                           int64_t dtype_code, int64_t device);
+// table_ops.cu
+void table_pull(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                at::Tensor keys, at::Tensor out);
+void table_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                at::Tensor keys, at::Tensor deltas, int64_t fn, double step, double lo, double hi, double eps);
+void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K);
+void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_dim, int64_t kind, double a,
+               double b, int64_t seed, int64_t row_key_base, int64_t key_stride);
+void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes);
+void flip_owner(at::Tensor ptr_tables, int64_t block, at::Tensor new_ptrs);
+void clock_publish(at::Tensor clock_ptrs, int64_t rank, int64_t value);
+void clock_wait(at::Tensor my_clocks, int64_t min_value, int64_t timeout_cycles, at::Tensor err_flag);
+// mlr_ops.cu
+void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                 int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, at::Tensor labels,
+                 double step, c10::optional<at::Tensor> D, at::Tensor stats);
+void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                       int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
+                       at::Tensor xval, at::Tensor D);
+}  // namespace hb
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "harmony_b200 native runtime (sm_100a)";
+  m.def("arena_create", &hb::arena_create);
+  m.def("arena_alloc", &hb::arena_alloc);
+  m.def("arena_free", &hb::arena_free);
+  m.def("arena_stats", &hb::arena_stats);
+  m.def("arena_destroy", &hb::arena_destroy);
+  m.def("ipc_export", &hb::ipc_export);
+  m.def("ipc_open", &hb::ipc_open);
+  m.def("ipc_close", &hb::ipc_close);
+  m.def("enable_peer_access", &hb::enable_peer_access);
+  m.def("tensor_from_ptr", &hb::tensor_from_ptr);
+  m.def("table_pull", &hb::table_pull);
+  m.def("table_push", &hb::table_push);
+  m.def("table_push_sparse_i32", &hb::table_push_sparse_i32);
+  m.def("init_slab", &hb::init_slab);
+  m.def("migrate_copy", &hb::migrate_copy);
+  m.def("flip_owner", &hb::flip_owner);
+  m.def("clock_publish", &hb::clock_publish);
+  m.def("clock_wait", &hb::clock_wait);
+  m.def("mlr_forward", &hb::mlr_forward);
+  m.def("mlr_backward_push", &hb::mlr_backward_push);
+}

@@ -1,0 +1,363 @@
+// Generic Elastic-Table data plane kernels (K1 PULL, K2 PUSH fused with K3/K4/K5 update
+// functions, K10 block migration, table initialisers, device clocks).
+//
+// Reference parity (behaviour, not code):
+//   PULL  = Table.multiGetOrInit  -> services/et/.../evaluator/impl/TableImpl.java:366-408
+//   PUSH  = Table.multiUpdate     -> TableImpl.java:460-501 + BlockImpl.update (BlockImpl.java:65-76)
+//   update functions              -> MLRETModelUpdateFunction.java:51-62 (ADD),
+//                                    NMFETModelUpdateFunction.java:43-52 (SGD + clamp),
+//                                    LDAETModelUpdateFunction.java:38-64 (sparse int add, clamp>=0, nnz)
+//   migration                     -> MigrationExecutor.java:338-414 (chunked block copy)
+// The B200 design replaces per-block Avro messages with ONE kernel whose loads / reductions
+// land directly in the owner GPU's HBM through peer mappings (NVLink 5 / NVSwitch).
+#include "hb_common.cuh"
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+namespace hb {
+
+enum UpdateFn : int {
+  UPD_ADD = 0,          // w += d                                   (MLR / AddVector / Lasso)
+  UPD_SGD_CLAMP = 1,    // w = clamp(w - step*d, lo, hi)           (NMF)
+  UPD_ADAGRAD = 2,      // h += d^2 ; w -= step*d/sqrt(h+eps)      (north-star option)
+  UPD_ASSIGN = 3,       // w = d                                   (put)
+};
+
+struct UpdateParams {
+  float step, lo, hi, eps;
+};
+
+// ------------------------------------------------------------------------------------------
+// PULL: out[i, :] = table[keys[i], :]      (one warp per row, 128-bit loads)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pull_rows_kernel(TableView t, const long long* __restrict__ keys,
+                                                        int n, float* __restrict__ out, int out_stride,
+                                                        int vec_ok) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int vec = t.row_stride >> 2;  // float4 per row (stride is a multiple of 32 floats)
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    const float* src = row_ptr<float>(t, keys[i]);
+    float* dst = out + (size_t)i * out_stride;
+#pragma unroll 4
+    for (int v = lane; v < vec; v += 32) {
+      float4 x = ld_stream_f4(src + 4 * v);
+      if (vec_ok && 4 * v + 3 < out_stride) {
+        *reinterpret_cast<float4*>(dst + 4 * v) = x;
+      } else {
+        float xs[4] = {x.x, x.y, x.z, x.w};
+        for (int e = 0; e < 4; ++e) if (4 * v + e < out_stride) dst[4 * v + e] = xs[e];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// PUSH fused with the update function, applied in the owner's HBM.
+//   ADD        : 128-bit red.add (no return value, fully fire-and-forget)
+//   SGD_CLAMP  : atom.add returning the old value; the rare out-of-range result is projected
+//                back with a CAS loop, so the row is never left outside [lo, hi]
+//   ADAGRAD    : table row = [w(0..D) | h(0..D)] : h via atom.add (returns old), w via red.add
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void clamp_fixup(float* p, float lo, float hi) {
+  unsigned* up = reinterpret_cast<unsigned*>(p);
+  unsigned cur = *reinterpret_cast<volatile unsigned*>(up);
+  for (int it = 0; it < 64; ++it) {
+    float f = __uint_as_float(cur);
+    float c = fminf(fmaxf(f, lo), hi);
+    if (c == f) break;
+    unsigned prev = atom_cas_b32_sys(up, cur, __float_as_uint(c));
+    if (prev == cur) break;
+    cur = prev;
+  }
+}
+
+__global__ void __launch_bounds__(256) push_rows_kernel(TableView t, const long long* __restrict__ keys, int n,
+                                                        const float* __restrict__ deltas, int d_stride,
+                                                        int fn, UpdateParams up, int vec_ok) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int D = t.row_dim;
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    float* dst = row_ptr<float>(t, keys[i]);
+    const float* src = deltas + (size_t)i * d_stride;
+    if (fn == UPD_ADD) {
+      const int vec = vec_ok ? (D >> 2) : 0;
+      for (int v = lane; v < vec; v += 32) {
+        float4 x = *reinterpret_cast<const float4*>(src + 4 * v);
+        red_add_f4_sys(dst + 4 * v, x);
+      }
+      for (int e = (vec << 2) + lane; e < D; e += 32) red_add_f32_sys(dst + e, src[e]);
+    } else if (fn == UPD_SGD_CLAMP) {
+      for (int e = lane; e < D; e += 32) {
+        float d = -up.step * src[e];
+        float old = atom_add_f32_sys(dst + e, d);
+        float nv = old + d;
+        if (nv < up.lo || nv > up.hi) clamp_fixup(dst + e, up.lo, up.hi);
+      }
+    } else if (fn == UPD_ADAGRAD) {
+      // second half of the (2*D wide) row holds the accumulated squared gradients
+      float* h = dst + (t.row_stride >> 1);
+      for (int e = lane; e < D; e += 32) {
+        float g = src[e];
+        float hold = atom_add_f32_sys(h + e, g * g);
+        red_add_f32_sys(dst + e, -up.step * g * rsqrtf(hold + g * g + up.eps));
+      }
+    } else {  // ASSIGN
+      for (int e = lane; e < D; e += 32) dst[e] = src[e];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Integer tables (LDA): pull rows; push sparse (row, topic, delta) triples.
+// Row layout int[K+1], last element = number of non-zero topics.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pull_rows_i32_kernel(TableView t, const long long* __restrict__ keys,
+                                                            int n, int* __restrict__ out, int out_stride) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int vec = t.row_stride >> 2;
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    const int* src = row_ptr<int>(t, keys[i]);
+    int* dst = out + (size_t)i * out_stride;
+    for (int v = lane; v < vec; v += 32) {
+      int4 x = ld_stream_i4(src + 4 * v);
+      int xs[4] = {x.x, x.y, x.z, x.w};
+      for (int e = 0; e < 4; ++e) if (4 * v + e < out_stride) dst[4 * v + e] = xs[e];
+    }
+  }
+}
+
+// One thread per (key, topic, delta) triple. atom.add returns the old count so that the
+// clamp-at-zero and the nnz bookkeeping of the reference update function are preserved:
+// a decrement below zero is compensated by adding the deficit back.
+__global__ void __launch_bounds__(256) push_sparse_i32_kernel(TableView t, const long long* __restrict__ keys,
+                                                              const int* __restrict__ topics,
+                                                              const int* __restrict__ deltas, int n, int K) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int d = deltas[i];
+  if (d == 0) return;
+  int* row = row_ptr<int>(t, keys[i]);
+  int old = atom_add_s32_sys(row + topics[i], d);
+  int nv = old + d;
+  if (nv < 0) {  // clamp >= 0 : give the deficit back
+    atom_add_s32_sys(row + topics[i], -nv);
+    nv = 0;
+  }
+  if (old <= 0 && nv > 0) atom_add_s32_sys(row + K, 1);
+  else if (old > 0 && nv == 0) atom_add_s32_sys(row + K, -1);
+}
+
+// ------------------------------------------------------------------------------------------
+// Initialisers: eager initValue for every row of a block slab (lazy init in the reference).
+// ------------------------------------------------------------------------------------------
+enum InitKind : int { INIT_ZERO = 0, INIT_GAUSSIAN = 1, INIT_UNIFORM = 2, INIT_CONST = 3 };
+
+__global__ void init_slab_kernel(float* slab, long long rows, int row_stride, int row_dim, int kind,
+                                 float a, float b, unsigned long long seed, long long row_key_base,
+                                 long long key_stride) {
+  long long total = rows * row_stride;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx / row_stride;
+    int c = (int)(idx - r * row_stride);
+    float v = 0.f;
+    if (c < row_dim) {
+      // counter derived from the GLOBAL key so that init is independent of block placement
+      unsigned long long ctr = (unsigned long long)(row_key_base + r * key_stride) * (unsigned long long)row_dim + c;
+      if (kind == INIT_GAUSSIAN) v = a + b * rng_normal(seed, ctr);        // mean a, std b
+      else if (kind == INIT_UNIFORM) v = a + (b - a) * rng_uniform(seed, ctr);
+      else if (kind == INIT_CONST) v = a;
+    }
+    slab[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Block migration (K10): bulk copy of a block slab from (peer) src to (local or peer) dst.
+// 128-bit grid-stride copy with 4 loads in flight per thread; run on a side stream.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) migrate_copy_kernel(const int4* __restrict__ src, int4* __restrict__ dst,
+                                                           long long n_vec) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    int4 a = ld_stream_i4(reinterpret_cast<const int*>(src + i));
+    int4 b = ld_stream_i4(reinterpret_cast<const int*>(src + i + stride));
+    int4 c = ld_stream_i4(reinterpret_cast<const int*>(src + i + 2 * stride));
+    int4 d = ld_stream_i4(reinterpret_cast<const int*>(src + i + 3 * stride));
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < n_vec; i += stride) dst[i] = ld_stream_i4(reinterpret_cast<const int*>(src + i));
+}
+
+// Ownership flip: write the new base pointer of `block` into every GPU's pointer table
+// (ptr_tables[g] is the VA of GPU g's table as mapped here) and publish with a system fence.
+__global__ void flip_owner_kernel(const long long* __restrict__ ptr_tables, int n_tables, int block,
+                                  const long long* __restrict__ new_ptrs) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_tables) {
+    long long* tbl = reinterpret_cast<long long*>(ptr_tables[g]);
+    tbl[block] = new_ptrs[g];
+    __threadfence_system();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Device clocks: SSP / barrier without host round trips.  clock_ptrs[g] = VA of GPU g's
+// int[world] clock array.  publish: write my clock into slot `rank` of every GPU.
+// wait: spin (bounded) until every slot of MY array >= min_clock.
+// ------------------------------------------------------------------------------------------
+__global__ void clock_publish_kernel(const long long* __restrict__ clock_ptrs, int world, int rank, int value) {
+  int g = threadIdx.x;
+  if (g < world) {
+    __threadfence_system();  // all prior pushes of this GPU are visible before the clock moves
+    int* arr = reinterpret_cast<int*>(clock_ptrs[g]);
+    st_release_sys_s32(arr + rank, value);
+  }
+}
+
+__global__ void clock_wait_kernel(const int* __restrict__ my_clocks, int world, int min_value,
+                                  long long timeout_cycles, int* __restrict__ err_flag) {
+  int g = threadIdx.x;
+  if (g < world) {
+    long long t0 = clock64();
+    while (ld_acquire_sys_s32(my_clocks + g) < min_value) {
+      if (clock64() - t0 > timeout_cycles) { atomicExch(err_flag, 1 + g); break; }
+      __nanosleep(64);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host wrappers
+// ------------------------------------------------------------------------------------------
+static TableView make_view(const at::Tensor& block_ptrs, int64_t rows_per_block, int64_t row_stride,
+                           int64_t row_dim, int64_t mode) {
+  TORCH_CHECK(block_ptrs.is_cuda() && block_ptrs.scalar_type() == at::kLong, "block_ptrs must be cuda int64");
+  TableView v;
+  v.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
+  v.num_blocks = (int)block_ptrs.numel();
+  v.rows_per_block = (int)rows_per_block;
+  v.row_stride = (int)row_stride;
+  v.row_dim = (int)row_dim;
+  v.mode = (int)mode;
+  return v;
+}
+
+static int grid_for_rows(int64_t n, int warps_per_cta) {
+  int64_t g = (n + warps_per_cta - 1) / warps_per_cta;
+  int64_t cap = 148 * 16;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
+}
+
+void table_pull(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                at::Tensor keys, at::Tensor out) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && keys.is_cuda());
+  TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == n && out.stride(1) == 1);
+  if (out.scalar_type() == at::kFloat) {
+    pull_rows_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
+        v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, out.data_ptr<float>(),
+        (int)out.stride(0),
+        (int)((out.stride(0) % 4 == 0) && (reinterpret_cast<uintptr_t>(out.data_ptr<float>()) % 16 == 0)));
+  } else {
+    TORCH_CHECK(out.scalar_type() == at::kInt);
+    pull_rows_i32_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
+        v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, out.data_ptr<int>(),
+        (int)out.stride(0));
+  }
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void table_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                at::Tensor keys, at::Tensor deltas, int64_t fn, double step, double lo, double hi, double eps) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && keys.is_cuda());
+  TORCH_CHECK(deltas.is_cuda() && deltas.scalar_type() == at::kFloat && deltas.dim() == 2 && deltas.size(0) == n);
+  TORCH_CHECK(deltas.stride(1) == 1, "deltas rows must be contiguous");
+  const int vec_ok = (deltas.stride(0) % 4 == 0) && (reinterpret_cast<uintptr_t>(deltas.data_ptr<float>()) % 16 == 0);
+  UpdateParams up{(float)step, (float)lo, (float)hi, (float)eps};
+  push_rows_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
+      v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, deltas.data_ptr<float>(),
+      (int)deltas.stride(0), (int)fn, up, vec_ok);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && topics.scalar_type() == at::kInt && deltas.scalar_type() == at::kInt);
+  push_sparse_i32_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
+      v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), topics.data_ptr<int>(),
+      deltas.data_ptr<int>(), (int)n, (int)K);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_dim, int64_t kind, double a,
+               double b, int64_t seed, int64_t row_key_base, int64_t key_stride) {
+  auto stream = at::cuda::getCurrentCUDAStream();
+  long long total = rows * row_stride;
+  if (total == 0) return;
+  int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  init_slab_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(slab_ptr), rows, (int)row_stride,
+                                             (int)row_dim, (int)kind, (float)a, (float)b,
+                                             (unsigned long long)seed, row_key_base, key_stride);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes) {
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TORCH_CHECK(nbytes % 16 == 0 && src_ptr % 16 == 0 && dst_ptr % 16 == 0, "migration needs 16B alignment");
+  long long n_vec = nbytes / 16;
+  if (n_vec == 0) return;
+  int grid = (int)std::min<long long>((n_vec + 2047) / 2048, 148 * 4);
+  migrate_copy_kernel<<<grid, 512, 0, stream>>>(reinterpret_cast<const int4*>(src_ptr),
+                                                reinterpret_cast<int4*>(dst_ptr), n_vec);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void flip_owner(at::Tensor ptr_tables, int64_t block, at::Tensor new_ptrs) {
+  c10::cuda::CUDAGuard guard(ptr_tables.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  int n = (int)ptr_tables.numel();
+  flip_owner_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const long long*>(ptr_tables.data_ptr<int64_t>()), n,
+                                          (int)block,
+                                          reinterpret_cast<const long long*>(new_ptrs.data_ptr<int64_t>()));
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void clock_publish(at::Tensor clock_ptrs, int64_t rank, int64_t value) {
+  c10::cuda::CUDAGuard guard(clock_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  int world = (int)clock_ptrs.numel();
+  clock_publish_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const long long*>(clock_ptrs.data_ptr<int64_t>()),
+                                             world, (int)rank, (int)value);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void clock_wait(at::Tensor my_clocks, int64_t min_value, int64_t timeout_cycles, at::Tensor err_flag) {
+  c10::cuda::CUDAGuard guard(my_clocks.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  int world = (int)my_clocks.numel();
+  clock_wait_kernel<<<1, 32, 0, stream>>>(my_clocks.data_ptr<int>(), world, (int)min_value,
+                                          (long long)timeout_cycles, err_flag.data_ptr<int>());
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+}  // namespace hb

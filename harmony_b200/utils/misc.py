@@ -1,0 +1,93 @@
+"""Small helpers (reference: utils/{LongRangeUtils,Tuple3,MemoryUtils,HostnameResolver}.java)."""
+from __future__ import annotations
+
+import os
+import socket
+from dataclasses import dataclass
+from typing import Generic, List, Sequence, Tuple, TypeVar
+
+A = TypeVar("A")
+B = TypeVar("B")
+C = TypeVar("C")
+
+
+@dataclass(frozen=True)
+class Tuple3(Generic[A, B, C]):
+    first: A
+    second: B
+    third: C
+
+
+def generate_dense_long_ranges(keys: Sequence[int]) -> List[Tuple[int, int]]:
+    """Sorted keys -> minimal list of closed [lo, hi] ranges (LongRangeUtils.generateDenseLongRanges)."""
+    out: List[Tuple[int, int]] = []
+    for k in sorted(set(int(x) for x in keys)):
+        if out and out[-1][1] + 1 == k:
+            out[-1] = (out[-1][0], k)
+        else:
+            out.append((k, k))
+    return out
+
+
+def get_num_units(ranges: Sequence[Tuple[int, int]]) -> int:
+    return sum(hi - lo + 1 for lo, hi in ranges)
+
+
+def used_memory_mb() -> float:
+    try:
+        import psutil
+        return psutil.Process(os.getpid()).memory_info().rss / (1 << 20)
+    except Exception:  # noqa: BLE001
+        return 0.0
+
+
+def device_memory_mb() -> float:
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.memory_allocated() / (1 << 20)
+    except Exception:  # noqa: BLE001
+        pass
+    return 0.0
+
+
+def resolve_hostname() -> str:
+    try:
+        return socket.gethostname()
+    except Exception:  # noqa: BLE001
+        return "localhost"
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    """MurmurHash3 x86_32 (the hash used by the hashed block partitioner)."""
+    c1, c2 = 0xcc9e2d51, 0x1b873593
+    h = seed & 0xffffffff
+    n = len(data)
+    rounded = n & ~3
+    for i in range(0, rounded, 4):
+        k = int.from_bytes(data[i:i + 4], "little")
+        k = (k * c1) & 0xffffffff
+        k = ((k << 15) | (k >> 17)) & 0xffffffff
+        k = (k * c2) & 0xffffffff
+        h ^= k
+        h = ((h << 13) | (h >> 19)) & 0xffffffff
+        h = (h * 5 + 0xe6546b64) & 0xffffffff
+    k = 0
+    tail = n & 3
+    if tail == 3:
+        k ^= data[rounded + 2] << 16
+    if tail >= 2:
+        k ^= data[rounded + 1] << 8
+    if tail >= 1:
+        k ^= data[rounded]
+        k = (k * c1) & 0xffffffff
+        k = ((k << 15) | (k >> 17)) & 0xffffffff
+        k = (k * c2) & 0xffffffff
+        h ^= k
+    h ^= n
+    h ^= h >> 16
+    h = (h * 0x85ebca6b) & 0xffffffff
+    h ^= h >> 13
+    h = (h * 0xc2b2ae35) & 0xffffffff
+    h ^= h >> 16
+    return h

@@ -1,0 +1,124 @@
+"""Numerics of the sm_100a kernels against plain PyTorch fp32 references (single GPU)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def arena():
+    from harmony_b200.parallel.peer import PeerArena, PeerGroup
+    a = PeerArena(0, PeerGroup(), segment_bytes=256 << 20)
+    yield a
+    a.close()
+
+
+def _table(arena, capacity, row_dim, nblocks, ordered, fn, dtype="float32"):
+    from harmony_b200.et.config import TableConfiguration
+    from harmony_b200.et.device_table import DeviceTable
+    conf = TableConfiguration(table_id=f"t{np.random.randint(1 << 30)}", dense=True, capacity=capacity,
+                              row_dim=row_dim, dtype=dtype, num_total_blocks=nblocks, is_ordered=ordered,
+                              update_function=fn, backend="device")
+    return DeviceTable(conf, arena)
+
+
+@pytest.mark.parametrize("ordered", [True, False])
+@pytest.mark.parametrize("row_dim", [10, 64, 1000])
+def test_pull_push_add(arena, ordered, row_dim):
+    cap = 5000
+    t = _table(arena, cap, row_dim, 16, ordered, {"name": "add", "params": {"init": "gaussian", "std": 0.01, "seed": 3}})
+    W0 = t.to_dense().clone()
+    assert W0.shape == (cap, row_dim)
+    assert abs(float(W0.std()) - 0.01) < 0.002 and abs(float(W0.mean())) < 1e-3
+    g = torch.Generator(device="cuda").manual_seed(1)
+    keys = torch.randint(0, cap, (3000,), device="cuda", generator=g)
+    deltas = torch.randn((3000, row_dim), device="cuda", generator=g)
+    t.push(keys, deltas)
+    ref = W0.clone().index_add_(0, keys, deltas)
+    torch.testing.assert_close(t.to_dense(), ref, rtol=1e-4, atol=1e-4)
+    out = t.pull(keys[:100])
+    torch.testing.assert_close(out, ref[keys[:100]], rtol=1e-4, atol=1e-4)
+    t.close()
+
+
+def test_push_sgd_clamp(arena):
+    cap, d = 1000, 32
+    t = _table(arena, cap, d, 8, True, {"name": "sgd_clamp", "params": {"step": 0.5, "lo": 0.0, "hi": 1.0,
+                                                                         "init": "uniform", "init_lo": 0.0, "init_hi": 1.0}})
+    W0 = t.to_dense().clone()
+    keys = torch.randperm(cap, device="cuda")[:500]
+    g = torch.randn((500, d), device="cuda")
+    t.push(keys, g)
+    ref = W0.clone()
+    ref[keys] = (W0[keys] - 0.5 * g).clamp(0.0, 1.0)
+    torch.testing.assert_close(t.to_dense(), ref, rtol=1e-5, atol=1e-5)
+    t.close()
+
+
+def test_push_adagrad(arena):
+    cap, d = 512, 48
+    t = _table(arena, cap, d, 4, False, {"name": "adagrad", "params": {"step": 0.1, "eps": 1e-8}})
+    keys = torch.randperm(cap, device="cuda")[:200]
+    g = torch.randn((200, d), device="cuda")
+    t.push(keys, g)
+    ref = torch.zeros((cap, d), device="cuda")
+    ref[keys] = -0.1 * g / torch.sqrt(g * g + 1e-8)
+    torch.testing.assert_close(t.to_dense(), ref, rtol=1e-3, atol=1e-4)
+    t.close()
+
+
+def test_lda_sparse_push(arena):
+    V, K = 300, 20
+    t = _table(arena, V + 1, K + 1, 8, False, None, dtype="int32")
+    t.update_fn  # void
+    keys = torch.tensor([5, 5, 7, 7, 300], device="cuda")
+    topics = torch.tensor([1, 2, 3, 3, 0], dtype=torch.int32, device="cuda")
+    deltas = torch.tensor([2, 1, 4, -1, 9], dtype=torch.int32, device="cuda")
+    t.push_sparse_i32(keys, topics, deltas)
+    M = t.to_dense()
+    assert M[5, 1] == 2 and M[5, 2] == 1 and M[5, K] == 2
+    assert M[7, 3] == 3 and M[7, K] == 1 and M[300, 0] == 9 and M[300, K] == 1
+    # decrement below zero clamps at zero and fixes the nnz counter
+    t.push_sparse_i32(torch.tensor([5], device="cuda"), torch.tensor([2], dtype=torch.int32, device="cuda"),
+                      torch.tensor([-5], dtype=torch.int32, device="cuda"))
+    M = t.to_dense()
+    assert M[5, 2] == 0 and M[5, K] == 1
+    t.close()
+
+
+@pytest.mark.parametrize("classes,features", [(10, 784), (1000, 20000), (1500, 5000)])
+def test_mlr_step_matches_reference(arena, classes, features):
+    from harmony_b200.models.mlr import MLRDeviceModel, mlr_reference_step, synthetic_batch
+    t = _table(arena, features, classes, 32, True, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 7}})
+    model = MLRDeviceModel(t, classes, step_size=0.01)
+    batch = synthetic_batch(257, features, classes, 13, seed=5).to("cuda")
+    W0 = t.to_dense().clone()
+    model.stats.zero_()
+    model.step(batch)
+    Wref, loss_ref, acc_ref = mlr_reference_step(W0, batch, classes, 0.01)
+    torch.testing.assert_close(t.to_dense(), Wref, rtol=2e-3, atol=2e-5)
+    s = model.stats.cpu()
+    assert abs(float(s[0]) - loss_ref) / max(1.0, abs(loss_ref)) < 2e-3
+    assert abs(float(s[1]) / 257 - acc_ref) < 0.02
+    t.close()
+
+
+def test_migrate_block_single_rank_copy(arena):
+    """migration copy kernel: bulk slab copy is exact."""
+    from harmony_b200.ops import native
+    n = native()
+    src = torch.randn(1 << 20, device="cuda")
+    dst = torch.zeros_like(src)
+    n.migrate_copy(src.data_ptr(), dst.data_ptr(), src.numel() * 4)
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst)
+
+
+def test_device_clock_single(arena):
+    from harmony_b200.parallel.device_clock import DeviceClock
+    c = DeviceClock(arena)
+    c.tick(); c.wait(); c.barrier()
+    torch.cuda.synchronize()
+    c.check()
+    assert int(c.clocks[0]) == 2
