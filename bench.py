@@ -217,19 +217,37 @@ def main():
         clock.check()
     loss_dev = float(model.stats[0]) / max(1, args.steps * B)
 
+    # ---------------- per-phase device timing (outside the headline region) ----------------
+    phase = None
+    if args.impl == "harmony":
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_pull = t_push = 0.0
+        reps = min(args.steps, 10)
+        for i in range(reps):
+            b = dev_batches[i % len(dev_batches)]
+            barrier_sync()
+            evs[0].record(); model.forward(b, True); evs[1].record(); model.backward_push(b); evs[2].record()
+            torch.cuda.synchronize(dev)
+            t_pull += evs[0].elapsed_time(evs[1]); t_push += evs[1].elapsed_time(evs[2])
+        phase = {"pull_fwd_ms": max_over_ranks(t_pull / reps), "bwd_push_ms": max_over_ranks(t_push / reps)}
+
     # ---------------- end-to-end: pinned host -> H2D every step, loss D2H every step ----------------
     e2e = None
     if not args.no_e2e:
-        staging = [hb.to(dev) for hb in host_batches[:2]]   # double-buffered device staging
-        copy_stream = torch.cuda.Stream(device=dev)
+        from harmony_b200.models.mlr import MLRBatch
+        maxn = [max(t.numel() for t in ts) for ts in zip(*[hb.tensors() for hb in host_batches])]
+        staging = [[torch.empty(n, dtype=t.dtype, device=dev) for n, t in zip(maxn, host_batches[0].tensors())]
+                   for _ in range(2)]                       # double-buffered device staging
 
         def e2e_step(i):
             hbt = host_batches[i % len(host_batches)]
-            buf = staging[i % 2]
-            for dst, src in zip(buf.tensors(), hbt.tensors()):
-                dst.copy_(src, non_blocking=True)           # H2D of this step's inputs (pinned)
+            views = []
+            for dst, src in zip(staging[i % 2], hbt.tensors()):
+                v = dst[: src.numel()]
+                v.copy_(src, non_blocking=True)             # H2D of this step's inputs (pinned)
+                views.append(v)
             model.stats.zero_()
-            step(buf)
+            step(MLRBatch(*views))
             return float(model.stats.cpu()[0])              # D2H of the step's loss (syncs)
         for i in range(max(3, args.warmup)):
             e2e_step(i)
@@ -261,8 +279,12 @@ def main():
                                    % ((nnz + uniq) * row_bytes / 1e9),
                        "sgd": "step_size %.1e, decay_rate 0.9 / decay_period 5 epochs (applied per epoch)" % args.step_size},
             "clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(loss_dev, 5),
-            "pull_GBps_per_gpu": round(nnz * row_bytes / (ms / args.steps / 1e3) / 1e9, 1),
-            "push_GBps_per_gpu": round(uniq * row_bytes / (ms / args.steps / 1e3) / 1e9, 1),
+            "phases": None if phase is None else {
+                "pull_fwd_ms": round(phase["pull_fwd_ms"], 4), "bwd_push_ms": round(phase["bwd_push_ms"], 4),
+                "pull_GBps_per_gpu": round(nnz * row_bytes / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
+                "push_GBps_per_gpu": round(uniq * row_bytes / (phase["bwd_push_ms"] / 1e3) / 1e9, 1),
+                "pull_nvlink_GBps_per_gpu": round(nnz * row_bytes * remote_frac / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
+                "push_nvlink_GBps_per_gpu": round(uniq * row_bytes * remote_frac / (phase["bwd_push_ms"] / 1e3) / 1e9, 1)},
             "nvlink_bytes_per_step_per_gpu": int((nnz + uniq) * row_bytes * remote_frac),
         }
         if e2e is not None:

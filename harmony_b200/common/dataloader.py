@@ -1,0 +1,212 @@
+"""File-split data loading + bulk loaders + parsers.
+
+Reference: common/.../dataloader/HdfsSplitManager.java:46-80 (N exact splits of an input path),
+ExactNumSplitFileInputFormat.java, HdfsSplitFetcher.java:44-95 / HdfsDataSet.java:46-65 (record
+iterator of one split), services/et/.../evaluator/impl/NoneKeyBulkDataLoader.java:57-87 +
+LocalKeyGenerator.java:55-113 (assign Long keys out of the key ranges of the LOCAL blocks of an
+ordered table, then multiPut), ExistKeyBulkDataLoader.java:53-73, DefaultDataParser.
+
+Local files only (`file://` prefixes accepted); HDFS is replaced by the local FS of the box.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import asdict, dataclass
+from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ..et.exceptions import KeyGenerationError
+
+
+def strip_scheme(path: str) -> str:
+    for pre in ("file://", "hdfs://"):
+        if path.startswith(pre):
+            return path[len(pre):]
+    return path
+
+
+@dataclass
+class SplitInfo:
+    path: str
+    start: int
+    length: int
+
+    def to_dict(self) -> Dict[str, Any]:
+        return asdict(self)
+
+    @staticmethod
+    def from_dict(d: Dict[str, Any]) -> "SplitInfo":
+        return SplitInfo(d["path"], d["start"], d["length"])
+
+
+def _files_of(path: str) -> List[str]:
+    path = strip_scheme(path)
+    if os.path.isdir(path):
+        return sorted(os.path.join(path, n) for n in os.listdir(path) if not n.startswith((".", "_")))
+    return [path]
+
+
+def get_splits(path: str, num_splits: int) -> List[SplitInfo]:
+    """Exactly `num_splits` byte-range splits over the file(s) (some may be empty)."""
+    files = _files_of(path)
+    sizes = [os.path.getsize(f) for f in files]
+    total = sum(sizes)
+    num_splits = max(1, num_splits)
+    target = max(1, -(-total // num_splits))
+    splits: List[SplitInfo] = []
+    for f, sz in zip(files, sizes):
+        off = 0
+        while off < sz:
+            ln = min(target, sz - off)
+            splits.append(SplitInfo(f, off, ln))
+            off += ln
+    # merge / pad to the exact number
+    while len(splits) > num_splits:
+        # merge the two smallest adjacent splits of the same file
+        best = None
+        for i in range(len(splits) - 1):
+            a, b = splits[i], splits[i + 1]
+            if a.path == b.path and a.start + a.length == b.start:
+                c = a.length + b.length
+                if best is None or c < best[0]:
+                    best = (c, i)
+        if best is None:
+            break
+        i = best[1]
+        a, b = splits[i], splits[i + 1]
+        splits[i:i + 2] = [SplitInfo(a.path, a.start, a.length + b.length)]
+    while len(splits) < num_splits:
+        splits.append(SplitInfo(files[0], sizes[0], 0))
+    return splits
+
+
+def read_split(split: SplitInfo) -> Iterator[str]:
+    """Lines whose FIRST byte lies inside [start, start+length) (Hadoop line-record semantics)."""
+    if split.length == 0:
+        return
+    with open(strip_scheme(split.path), "rb") as f:
+        end = split.start + split.length
+        if split.start > 0:
+            f.seek(split.start - 1)
+            f.readline()          # skip the partial (or exactly-ended) previous line
+        pos = f.tell()
+        while pos < end:
+            line = f.readline()
+            if not line:
+                break
+            pos = f.tell()
+            yield line.decode("utf-8", errors="replace").rstrip("\r\n")
+
+
+# ------------------------------------------------------------------------------------------
+# parsers  (value parsers return `value`; key-value parsers return `(key, value)`)
+# ------------------------------------------------------------------------------------------
+class DataParser:
+    has_key = False
+
+    def __init__(self, **params: Any) -> None:
+        self.params = params
+
+    def parse(self, lines: Iterable[str]) -> List[Any]:
+        out = []
+        for line in lines:
+            s = line.strip()
+            if not s or s.startswith("#"):
+                continue
+            v = self.parse_line(s)
+            if v is not None:
+                out.append(v)
+        return out
+
+    def parse_line(self, line: str) -> Any:
+        return line
+
+
+class DefaultDataParser(DataParser):
+    pass
+
+
+_PARSERS: Dict[str, Callable[..., DataParser]] = {"default": DefaultDataParser}
+
+
+def register_parser(name: str, cls: Callable[..., DataParser]) -> None:
+    _PARSERS[name] = cls
+
+
+def make_parser(spec: Any) -> DataParser:
+    if isinstance(spec, DataParser):
+        return spec
+    if spec is None:
+        return DefaultDataParser()
+    if isinstance(spec, str):
+        _ensure_app_parsers()
+        return _PARSERS[spec]()
+    _ensure_app_parsers()
+    return _PARSERS[spec["name"]](**spec.get("params", {}))
+
+
+def _ensure_app_parsers() -> None:
+    # app parsers register themselves on import
+    import importlib
+    for mod in ("harmony_b200.mlapps.mlr", "harmony_b200.mlapps.nmf", "harmony_b200.mlapps.lda",
+                "harmony_b200.mlapps.lasso", "harmony_b200.mlapps.gbt", "harmony_b200.pregel.graph"):
+        try:
+            importlib.import_module(mod)
+        except ImportError:
+            pass
+
+
+# ------------------------------------------------------------------------------------------
+# key generation + bulk loaders
+# ------------------------------------------------------------------------------------------
+class LocalKeyGenerator:
+    """Hands out unused Long keys from the key ranges of the blocks owned by this executor."""
+
+    def __init__(self, comps) -> None:
+        self._comps = comps
+        self._next: Dict[int, int] = {}
+
+    def get_keys(self, n: int) -> List[int]:
+        part = self._comps.partitioner
+        blocks = self._comps.ownership.get_current_local_block_ids()
+        if not blocks:
+            raise KeyGenerationError("this executor owns no block of the table")
+        if not hasattr(part, "key_range"):
+            raise KeyGenerationError("key generation needs an ordered table")
+        keys: List[int] = []
+        # spread evenly over local blocks so every block (== mini-batch) gets data
+        per = -(-n // len(blocks))
+        for b in blocks:
+            lo, hi = part.key_range(b)
+            cur = self._next.get(b, lo)
+            take = min(per, n - len(keys), hi - cur + 1)
+            if take > 0:
+                keys.extend(range(cur, cur + take))
+                self._next[b] = cur + take
+            if len(keys) >= n:
+                break
+        if len(keys) < n:
+            raise KeyGenerationError(f"local key space exhausted: need {n}, got {len(keys)}")
+        return keys
+
+
+def run_bulk_load(executor, table_id: str, file_splits: Sequence[Dict[str, Any]]) -> int:
+    comps = executor.tables.get_components(table_id)
+    table = comps.table
+    parser = make_parser(comps.conf.data_parser)
+    total = 0
+    keygen = LocalKeyGenerator(comps)
+    for sd in file_splits:
+        records = parser.parse(read_split(SplitInfo.from_dict(sd)))
+        if not records:
+            continue
+        if comps.conf.bulk_loader == "exist_key" or parser.has_key:
+            keys = [r[0] for r in records]
+            vals = [r[1] for r in records]
+        else:
+            keys = keygen.get_keys(len(records))
+            vals = records
+        table.multi_put(keys, vals).get(timeout=300)
+        total += len(records)
+    return total

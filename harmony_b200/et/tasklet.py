@@ -1,0 +1,173 @@
+"""Tasklets, the tasklet runtime and the per-executor task-unit scheduler.
+
+Reference: evaluator/api/Tasklet.java:23-35 (run/close), evaluator/impl/TaskletRuntime.java:69-130
+(thread pool of `num_tasklets`, start/stop by driver messages, Running/Done/Failed reports,
+per-tasklet custom message handler), evaluator/impl/LocalTaskUnitScheduler.java:36-145
+(resource slots: 1 CPU, 2 NET, VOID = no wait; waitSchedule = Wait to the driver, block until the
+driver's Ready -- all executors of the job reached the same unit -- then queue for a local slot).
+
+On a GPU executor the COMP unit is the SM-bound phase and NET the NVLink-bound pull/push phase of
+a job; the slots arbitrate co-located jobs so that job A's COMP overlaps job B's PULL/PUSH.
+"""
+from __future__ import annotations
+
+import importlib
+import logging
+import threading
+import traceback
+from dataclasses import dataclass
+from typing import Any, Callable, Dict, Optional
+
+from ..utils.concurrent import new_fixed_thread_pool
+from .config import TaskletConfiguration
+
+LOG = logging.getLogger(__name__)
+
+CPU, NET, VOID = "CPU", "NET", "VOID"
+SLOTS = {CPU: 1, NET: 2}
+
+
+@dataclass(frozen=True)
+class TaskUnitInfo:
+    job_id: str
+    unit_name: str        # e.g. PULL / COMP / PUSH / SYNC
+    resource: str         # CPU | NET | VOID
+    seq: int = 0
+
+
+class Tasklet:
+    """User code executed on an executor. Subclasses override run() (and optionally close())."""
+
+    def __init__(self, context: "TaskletContext") -> None:
+        self.context = context
+
+    def run(self) -> Any:
+        raise NotImplementedError
+
+    def close(self) -> None:
+        pass
+
+    def on_msg(self, payload: Any) -> None:   # TaskletCustomMsgHandler
+        pass
+
+
+class TaskletContext:
+    def __init__(self, executor, conf: TaskletConfiguration) -> None:
+        self.executor = executor
+        self.tasklet_id = conf.tasklet_id
+        self.params: Dict[str, Any] = dict(conf.user_params)
+        self.table_accessor = executor.table_accessor
+        self.task_units = executor.task_unit_scheduler
+        self.metric_collector = executor.metric_collector
+
+    def send_to_driver(self, payload: Any) -> None:
+        """TaskletCustomMsgSender.send (evaluator/impl/TaskletCustomMsgSender.java:53-70)."""
+        self.executor.send_to_driver({"type": "TaskletCustom", "tasklet_id": self.tasklet_id,
+                                      "executor_id": self.executor.executor_id, "payload": payload})
+
+
+def load_class(path: str):
+    mod, _, name = path.partition(":")
+    return getattr(importlib.import_module(mod), name)
+
+
+class TaskletRuntime:
+    def __init__(self, executor, num_tasklets: int) -> None:
+        self._ex = executor
+        self._pool = new_fixed_thread_pool(max(1, num_tasklets), f"{executor.executor_id}-tasklet")
+        self._tasklets: Dict[str, Tasklet] = {}
+        self._lock = threading.Lock()
+
+    def start_tasklet(self, conf: TaskletConfiguration) -> None:
+        ctx = TaskletContext(self._ex, conf)
+        cls = load_class(conf.tasklet_class)
+        tasklet = cls(ctx)
+        with self._lock:
+            if conf.tasklet_id in self._tasklets:
+                raise RuntimeError(f"tasklet {conf.tasklet_id} already running")
+            self._tasklets[conf.tasklet_id] = tasklet
+        self._pool.submit(self._run, conf.tasklet_id, tasklet)
+
+    def _status(self, tasklet_id: str, status: str, result: Any = None, error: Optional[str] = None) -> None:
+        self._ex.send_to_driver({"type": "TaskletStatus", "tasklet_id": tasklet_id,
+                                 "executor_id": self._ex.executor_id, "status": status, "result": result,
+                                 "error": error})
+
+    def _run(self, tasklet_id: str, tasklet: Tasklet) -> None:
+        self._status(tasklet_id, "Running")
+        try:
+            result = tasklet.run()
+            self._status(tasklet_id, "Done", result=result)
+        except BaseException as e:  # noqa: BLE001
+            LOG.error("tasklet %s failed:\n%s", tasklet_id, traceback.format_exc())
+            self._status(tasklet_id, "Failed", error=f"{type(e).__name__}: {e}")
+        finally:
+            with self._lock:
+                self._tasklets.pop(tasklet_id, None)
+
+    def stop_tasklet(self, tasklet_id: str) -> None:
+        with self._lock:
+            t = self._tasklets.get(tasklet_id)
+        if t is not None:
+            t.close()
+
+    def on_custom_msg(self, tasklet_id: str, payload: Any) -> None:
+        with self._lock:
+            t = self._tasklets.get(tasklet_id)
+        if t is not None:
+            t.on_msg(payload)
+        else:
+            LOG.warning("custom message for unknown tasklet %s", tasklet_id)
+
+    def running(self):
+        with self._lock:
+            return list(self._tasklets)
+
+    def close(self) -> None:
+        with self._lock:
+            ts = list(self._tasklets.values())
+        for t in ts:
+            try:
+                t.close()
+            except Exception:  # noqa: BLE001
+                pass
+        self._pool.shutdown(wait=False)
+
+
+class LocalTaskUnitScheduler:
+    """Per-executor slots + the global per-job unit barrier hosted by the driver."""
+
+    def __init__(self, executor) -> None:
+        self._ex = executor
+        self._sems = {r: threading.Semaphore(n) for r, n in SLOTS.items()}
+        self._ready: Dict[Any, threading.Event] = {}
+        self._lock = threading.Lock()
+        self.enabled = True
+
+    def _key(self, tasklet_id: str, u: TaskUnitInfo):
+        return (tasklet_id, u.job_id, u.unit_name, u.seq)
+
+    def wait_schedule(self, tasklet_id: str, unit: TaskUnitInfo) -> None:
+        if not self.enabled or unit.resource == VOID:
+            return
+        key = self._key(tasklet_id, unit)
+        ev = threading.Event()
+        with self._lock:
+            self._ready[key] = ev
+        self._ex.send_to_driver({"type": "TaskUnitWait", "tasklet_id": tasklet_id,
+                                 "executor_id": self._ex.executor_id, "job_id": unit.job_id,
+                                 "unit_name": unit.unit_name, "seq": unit.seq})
+        ev.wait()
+        self._sems[unit.resource].acquire()
+
+    def on_ready(self, m: Dict[str, Any]) -> None:
+        key = (m["tasklet_id"], m["job_id"], m["unit_name"], m["seq"])
+        with self._lock:
+            ev = self._ready.pop(key, None)
+        if ev is not None:
+            ev.set()
+
+    def on_task_unit_finished(self, tasklet_id: str, unit: TaskUnitInfo) -> None:
+        if not self.enabled or unit.resource == VOID:
+            return
+        self._sems[unit.resource].release()

@@ -59,6 +59,34 @@ __device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// ---- L2 residency hints -------------------------------------------------------------------
+// Small, re-read buffers (the [B, C] error matrix of MLR) are tagged evict_last so the streaming
+// row traffic (GBs per step) does not push them out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld_hint_f4(const float* p, uint64_t pol) {
+  float4 r;
+  asm("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+      : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st_hint_f4(float* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f4_sys_hint(float* p, const float4& v, uint64_t pol) {
+  asm volatile("red.relaxed.sys.global.add.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 // 128-bit fire-and-forget float reduction (sm_90+). System scope so that it is valid on a
 // peer-mapped address: this is the PUSH primitive (reduce-write into the owner's HBM).
 __device__ __forceinline__ void red_add_f4_sys(float* p, const float4& v) {

@@ -26,6 +26,10 @@ namespace hb {
 static constexpr int MLR_THREADS = 256;
 static constexpr float MLR_ZERO_THRESHOLD = 1e-7f;
 
+__device__ __forceinline__ float4 ld_row_hint_f4(const float* r, int c0, int width, uint64_t pol) {
+  return (c0 < width) ? ld_hint_f4(r + c0, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Guarded 128-bit row load: threads beyond the (padded) row width contribute zeros.
 __device__ __forceinline__ float4 ld_row_f4(const float* r, int c0, int width) {
   return (c0 < width) ? ld_stream_f4(r + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -41,6 +45,7 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_fwd_kernel(
   __shared__ float s_red[32];
   const int tid = threadIdx.x;
   float cta_loss = 0.f, cta_correct = 0.f;
+  const uint64_t pol_keep = l2_policy_evict_last();
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     float4 acc[VEC];
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_fwd_kernel(
         d[e] = (c < C) ? -step * p : 0.f;
       }
       if (WRITE_D && c0 < d_stride)
-        st_stream_f4(D + (size_t)b * d_stride + c0, make_float4(d[0], d[1], d[2], d[3]));
+        st_hint_f4(D + (size_t)b * d_stride + c0, make_float4(d[0], d[1], d[2], d[3]), pol_keep);
     }
     cta_loss += my_loss;      // exactly one thread of the CTA owns column y
     cta_correct += my_hit;
@@ -148,6 +153,8 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
     const int* __restrict__ samp, const float* __restrict__ xval, int U, const float* __restrict__ D,
     int d_stride) {
   const int tid = threadIdx.x;
+  const uint64_t pol_keep = l2_policy_evict_last();    // D is re-read ~nnz/B times: keep it in L2
+  const uint64_t pol_stream = l2_policy_evict_first(); // model rows are touched once per step
   for (int u = blockIdx.x; u < U; u += gridDim.x) {
     const int beg = feat_ptr[u], end = feat_ptr[u + 1];
     float* dst = row_ptr<float>(W, (long long)uniq_feat[u]);
@@ -163,7 +170,7 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
         const float* drow = D + (size_t)samp[j + q] * d_stride;
         x[q] = xval[j + q];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) d[q][k] = ld_row_f4(drow, 4 * (tid + k * MLR_THREADS), d_stride);
+        for (int k = 0; k < VEC; ++k) d[q][k] = ld_row_hint_f4(drow, 4 * (tid + k * MLR_THREADS), d_stride, pol_keep);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
       const float x = xval[j];
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        float4 d = ld_row_f4(drow, 4 * (tid + k * MLR_THREADS), d_stride);
+        float4 d = ld_row_hint_f4(drow, 4 * (tid + k * MLR_THREADS), d_stride, pol_keep);
         acc[k].x = fmaf(x, d.x, acc[k].x); acc[k].y = fmaf(x, d.y, acc[k].y);
         acc[k].z = fmaf(x, d.z, acc[k].z); acc[k].w = fmaf(x, d.w, acc[k].w);
       }
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int c0 = 4 * (tid + k * MLR_THREADS);
-      if (c0 < W.row_stride) red_add_f4_sys(dst + c0, acc[k]);   // PUSH + `w += delta`
+      if (c0 < W.row_stride) red_add_f4_sys_hint(dst + c0, acc[k], pol_stream);   // PUSH + `w += delta`
     }
   }
 }
