@@ -1,0 +1,128 @@
+"""Dolphin launchers.
+
+`DolphinJobLauncher.submit_job`  -- submit to a running job server (submit_<app>.sh;
+                                    reference dolphin/jobserver/DolphinJobLauncher.java:75-215).
+`ETDolphinLauncher.launch`       -- stand-alone job with its own driver (run_<app>.sh;
+                                    reference dolphin/core/client/ETDolphinLauncher.java:111-378 +
+                                    core/driver/DolphinDriver.java:97-346): separate worker / server
+                                    executors (or co-located with -num_servers 0), workers subscribe
+                                    to the model table, optional optimizer orchestration and
+                                    offline model evaluation.
+"""
+from __future__ import annotations
+
+import logging
+import sys
+import threading
+import time
+from typing import Any, Dict, List, Optional, Sequence
+
+from ..et import ExecutorConfiguration, LocalTransport
+from ..et.driver import ETMaster, InProcessLauncher
+from ..jobserver.client import CommandSender, DEFAULT_PORT
+from ..utils.flags import Configuration
+from . import params as P
+from .conf import ETDolphinConfiguration
+from .jobserver import build_tables_confs
+from .master import DolphinMaster, ETDolphinMetricReceiver
+
+LOG = logging.getLogger(__name__)
+
+
+def parse_job_conf(app: ETDolphinConfiguration, argv: Sequence[str]) -> Configuration:
+    reg = P.dolphin_registry(app.parameters, P.EXAMPLES if app.app_id.startswith("Add") else [])
+    conf, _ = reg.parse(list(argv), allow_unknown=False)
+    return conf
+
+
+class DolphinJobLauncher:
+    @staticmethod
+    def submit_job(app_path: str, app: ETDolphinConfiguration, argv: Sequence[str],
+                   port: Optional[int] = None) -> str:
+        conf = parse_job_conf(app, argv).with_values(
+            job_entity_builder="harmony_b200.dolphin.jobserver:DolphinJobEntityBuilder", app=app_path)
+        reply = CommandSender(port or int(conf.get("port", DEFAULT_PORT))).send_job_submit_command(conf.serialize())
+        return reply
+
+
+class LauncherResult:
+    def __init__(self, ok: bool, results: Any, messages: List[str], master: Optional[DolphinMaster]) -> None:
+        self.ok, self.results, self.messages, self.dolphin_master = ok, results, messages, master
+
+    @property
+    def status(self) -> str:
+        return "COMPLETED" if self.ok else "FAILED"
+
+
+class ETDolphinLauncher:
+    @staticmethod
+    def launch(app: ETDolphinConfiguration, argv: Sequence[str],
+               extra_conf: Optional[Dict[str, Any]] = None) -> LauncherResult:
+        conf = parse_job_conf(app, argv)
+        if extra_conf:
+            conf = conf.merge(extra_conf)
+        num_workers = int(conf.get("num_dolphin_workers", 1))
+        num_servers = int(conf.get("num_servers", 1))
+        colocated = num_servers == 0
+        transport = LocalTransport()
+        master = ETMaster(transport, InProcessLauncher(), chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
+                          chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
+        messages: List[str] = []
+        receiver = ETDolphinMetricReceiver()
+        master.metrics.receivers.append(receiver)
+        ok, results, dm = False, None, None
+        try:
+            ec = ExecutorConfiguration(num_tasklets=4, chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
+                                       chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
+            workers = master.add_executors(num_workers, ec).get(timeout=120)
+            servers = workers if colocated else master.add_executors(num_servers, ec).get(timeout=120)
+            server_tc, worker_tc, local_tc = build_tables_confs(app, conf, 0)
+            master.create_table(server_tc, servers).get(timeout=600)
+            model_table = master.get_table(server_tc.table_id)
+            if not colocated:
+                model_table.subscribe(workers).get(timeout=120)
+            if local_tc is not None:
+                master.create_table(local_tc, workers).get(timeout=600)
+            master.create_table(worker_tc, workers).get(timeout=3600)
+            params = dict(conf)
+            params.update({"trainer_class": app.trainer_class, "device_trainer_class": app.device_trainer_class,
+                           "model_table_id": server_tc.table_id, "input_table_id": worker_tc.table_id,
+                           "local_model_table_id": local_tc.table_id if local_tc else None,
+                           "data_parser": app.input_parser, "app_id": app.app_id, "task_units_enabled": False})
+            job_id = f"{app.app_id}-0"
+            dm = DolphinMaster(master, job_id, params, report=lambda s: (messages.append(s), LOG.info(s)))
+            receiver.register(job_id, dm.metric_manager)
+            master.custom_handlers["TaskletCustom"] = lambda m: dm.on_worker_msg(m["payload"])
+            orchestrator = None
+            opt_name = conf.get("optimizer", "")
+            if opt_name and not opt_name.endswith("EmptyPlanOptimizer"):
+                from .optimizer import ETOptimizationOrchestrator
+                orchestrator = ETOptimizationOrchestrator(master, dm, conf, server_tc.table_id, worker_tc.table_id,
+                                                          servers, workers, local_tc.table_id if local_tc else None)
+                orchestrator.start()
+            try:
+                results = dm.start(servers if not colocated else [], workers) if not colocated \
+                    else dm.start([], workers)
+            finally:
+                if orchestrator is not None:
+                    orchestrator.stop()
+            ok = True
+        except BaseException:  # noqa: BLE001
+            LOG.exception("stand-alone job failed")
+        finally:
+            master.close()
+            transport.close()
+        return LauncherResult(ok, results, messages, dm)
+
+
+def main_submit(app_path: str, app: ETDolphinConfiguration, argv: Sequence[str]) -> int:
+    reply = DolphinJobLauncher.submit_job(app_path, app, argv)
+    print(reply)
+    return 0 if reply.startswith("true") else 1
+
+
+def main_run(app: ETDolphinConfiguration, argv: Sequence[str]) -> int:
+    logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s %(name)s | %(message)s")
+    res = ETDolphinLauncher.launch(app, argv)
+    print(f"LauncherStatus: {res.status}")
+    return 0 if res.ok else 1

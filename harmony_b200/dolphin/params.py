@@ -1,0 +1,100 @@
+"""Dolphin / job-server / app flags with the reference's short names (CLI compatibility surface).
+
+Reference: jobserver/.../dolphin/DolphinParameters.java:26-263, common/.../param/Parameters.java:25-119,
+jobserver/.../jobserver/Parameters.java:25-94, optimizer/parameters/*.java, dashboard/parameters/*.java,
+per-app *Parameters.java.  Flags that are meaningless on a GPU box
+(-heap_slack, -driver_memory, ...) are accepted and ignored.
+"""
+from __future__ import annotations
+
+from ..utils.flags import Param, ParamRegistry
+
+P = Param
+# ---- common client / driver (CM/param/Parameters.java) ----
+COMMON = [
+    P("driver_memory", int, 256, "ignored", "client"), P("eval_size", int, 128, "ignored", "client"),
+    P("num_eval_cores", int, 1, "ignored", "client"), P("input", str, None, "input data path", "worker"),
+    P("local", bool, True, "run on this box", "client"), P("split", int, 1, "number of input splits", "client"),
+    P("timeout", int, 100000, "client timeout (ms)", "client"),
+    P("max_num_eval_local", int, 2, "max local executors", "client"),
+    P("heap_slack", float, 0.0, "ignored (JVM heap slack)", "client"),
+    P("opt_benefit_threshold", float, 0.0, "min relative benefit to apply a plan", "optimizer"),
+    P("hyper_thread_enabled", bool, False, "halve trainer threads", "worker"),
+    P("default_bandwidth", float, 1.074e9, "bits/s assumed per host (NVLink when on GPUs)", "optimizer"),
+    P("default_core_num", int, 1, "cores assumed per host", "optimizer"),
+    P("host_to_bandwidth_file_path", str, "", "host -> bandwidth file", "optimizer"),
+    P("host_to_core_file_path", str, "", "host -> #cores file", "optimizer"),
+]
+# ---- job server (JS/jobserver/Parameters.java) ----
+JOBSERVER = [
+    P("port", int, 7008, "job-server command port", "client"),
+    P("chkp_commit_path", str, "/tmp/chkp/commit", "checkpoint commit dir", "driver"),
+    P("chkp_temp_path", str, "/tmp/chkp", "checkpoint temp dir", "driver"),
+    P("num_executors", int, 1, "executors in the resource pool", "driver"),
+    P("executor_mem_size", int, 128, "ignored", "driver"), P("executor_num_cores", int, 1, "ignored", "driver"),
+    P("executor_num_tasklets", int, 4, "tasklet threads per executor", "driver"),
+    P("handler_queue_size", int, 1024, "", "driver"), P("sender_queue_size", int, 1024, "", "driver"),
+    P("handler_num_threads", int, 2, "", "driver"), P("sender_num_threads", int, 2, "", "driver"),
+    P("scheduler", str, "edu.snu.cay.jobserver.driver.SchedulerImpl", "JobScheduler implementation", "driver"),
+    P("kill", bool, False, "stop_jobserver: kill running jobs", "client"),
+    P("backend", str, "auto", "auto | host | device (table/compute backend)", "driver"),
+    P("executor_mode", str, "inproc", "inproc | process (one OS process per executor/GPU)", "driver"),
+]
+# ---- Dolphin (DolphinParameters.java) ----
+DOLPHIN = [
+    P("max_num_epochs", int, 1, "", "master"), P("num_mini_batches", int, 10, "mini-batches per epoch (global)", "master"),
+    P("clock_slack", int, 0, "SSP staleness bound", "master"),
+    P("server_metric_flush_period_ms", int, 0, "", "master"),
+    P("offline_model_eval", bool, False, "checkpoint the model every epoch, evaluate after training", "master"),
+    P("model_eval", bool, False, "evaluate a checkpointed model instead of training", "master"),
+    P("num_server_blocks", int, 1024, "", "server"), P("load_model", bool, False, "", "server"),
+    P("model_path", str, "", "", "server"), P("local_model_path", str, "", "", "server"),
+    P("num_trainer_threads", int, 0, "0 = auto", "worker"), P("num_worker_blocks", int, 1024, "", "worker"),
+    P("test_data_path", str, "", "", "worker"), P("input_chkp_path", str, "", "", "worker"),
+    P("model_cache_enabled", bool, False, "", "worker"),
+    P("num_dolphin_workers", int, 1, "", "launcher"), P("num_servers", int, 1, "0 = co-located", "launcher"),
+    P("dolphin_worker_mem_size", int, 128, "ignored", "launcher"), P("server_mem_size", int, 128, "ignored", "launcher"),
+    P("num_dolphin_worker_cores", int, 1, "ignored", "launcher"), P("num_server_cores", int, 1, "ignored", "launcher"),
+    P("num_server_handler_threads", int, 2, "", "launcher"), P("num_server_sender_threads", int, 2, "", "launcher"),
+    P("num_worker_handler_threads", int, 2, "", "launcher"), P("num_worker_sender_threads", int, 2, "", "launcher"),
+    P("server_handler_queue_size", int, 500000, "", "launcher"), P("server_sender_queue_size", int, 500000, "", "launcher"),
+    P("worker_handler_queue_size", int, 500000, "", "launcher"), P("worker_sender_queue_size", int, 500000, "", "launcher"),
+    P("features", int, 0, "", "user"), P("lambda", float, 0.0, "L2 regularisation", "user"),
+    P("decay_rate", float, 0.9, "", "user"), P("decay_period", int, 5, "", "user"),
+    P("step_size", float, 0.0, "", "user"), P("model_gaussian", float, 0.001, "", "user"),
+    P("features_per_partition", int, 0, "", "user"),
+]
+OPTIMIZER = [
+    P("optimizer", str, "edu.snu.cay.dolphin.optimizer.impl.EmptyPlanOptimizer", "Optimizer implementation", "optimizer"),
+    P("et_plan_executor", str, "edu.snu.cay.services.et.plan.impl.PlanExecutorImpl", "", "optimizer"),
+    P("optimization_interval_ms", int, 10000, "", "optimizer"), P("delay_after_optimization_ms", int, 10000, "", "optimizer"),
+    P("num_initial_batch_metrics_to_skip", int, 3, "", "optimizer"),
+    P("min_num_required_batch_metrics", int, 3, "", "optimizer"),
+    P("moving_avg_window_size", int, 0, "", "optimizer"), P("metric_weight_factor", float, 0.0, "", "optimizer"),
+    P("num_extra_resources", int, 0, "", "optimizer"), P("extra_resources_period_sec", int, 0, "", "optimizer"),
+    P("dashboard_enabled", bool, False, "", "dashboard"), P("dashboard_port", int, 9005, "", "dashboard"),
+]
+MLR = [P("classes", int, 0, "number of classes", "user")]
+NMF = [P("rank", int, 0, "", "user"), P("max_val", float, 1e6, "", "user"), P("init_max", float, 1.0, "", "user"),
+       P("init_min", float, 0.0, "", "user"), P("print_mat", bool, False, "", "user")]
+LDA = [P("alpha", float, 0.001, "", "user"), P("beta", float, 0.01, "", "user"), P("num_topics", int, 100, "", "user"),
+       P("num_vocabs", int, 0, "", "user")]
+GBT = [P("gamma", float, 0.0, "", "user"), P("max_depth_of_tree", int, 7, "", "user"),
+       P("leaf_min_size", int, 4, "", "user"), P("metadata_path", str, "", "", "user"), P("num_keys", int, 0, "", "user")]
+EXAMPLES = [P("delta", int, 1, "", "user"), P("num_keys", int, 0, "", "user"), P("compute_time_ms", int, 300, "", "user"),
+            P("num_training_data", int, 0, "", "user"), P("num_test_data", int, 0, "", "user"),
+            P("vector_size", int, 1, "", "user"), P("start_key", int, 0, "", "user")]
+PREGEL = [P("num_pregel_workers", int, 1, "", "launcher"), P("pregel_worker_mem_size", int, 128, "ignored", "launcher"),
+          P("pregel_worker_num_cores", int, 1, "ignored", "launcher"), P("num_worker_threads", int, 0, "", "worker"),
+          P("source", int, 0, "SSSP source vertex", "user")]
+
+
+def registry(*groups) -> ParamRegistry:
+    reg = ParamRegistry()
+    for g in groups:
+        reg.register_all(g)
+    return reg
+
+
+def dolphin_registry(*app_groups) -> ParamRegistry:
+    return registry(COMMON, JOBSERVER, DOLPHIN, OPTIMIZER, *app_groups)

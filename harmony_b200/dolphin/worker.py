@@ -1,0 +1,434 @@
+"""Worker side of Dolphin: Trainer SPI, model accessor, training data provider, barriers and the
+training loop.
+
+Reference (jobserver/src/main/java/edu/snu/cay/dolphin/core/worker/):
+  Trainer.java:44-92, ModelAccessor.java:29-83, ETModelAccessor.java:60-159 (push = updateNoReply /
+  multiUpdate().get(), pull = getOrInit / multiGetOrInit().get(), pull/push timers),
+  CachedModelAccessor.java:37-199, TrainingDataProvider.java:26-51, ETTrainingDataProvider.java:54-108
+  (one local input block == one mini-batch, shuffled per epoch), WorkerGlobalBarrier.java:49-127,
+  MiniBatchBarrier.java:47-64, WorkerTasklet.java:96-261 (SYNC -> PULL(net) -> COMP(cpu) -> PUSH(net)
+  each wrapped in a task unit; Batch/Epoch metrics), ProgressReporter, ModelEvaluator.java:69-147,
+  core/server/ServerTasklet.java:43-55.
+"""
+from __future__ import annotations
+
+import logging
+import random
+import threading
+import time
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+from ..et.tasklet import CPU, NET, VOID, TaskUnitInfo, Tasklet, load_class
+from ..utils import trace
+from .metrics import BatchMetrics, EpochMetrics
+
+LOG = logging.getLogger(__name__)
+
+
+# ------------------------------------------------------------------------------------------
+# SPI
+# ------------------------------------------------------------------------------------------
+class Trainer:
+    """A machine-learning algorithm plugged into the PS training loop."""
+
+    def init_global_settings(self) -> None:
+        pass
+
+    def set_mini_batch_data(self, mini_batch: Sequence[Tuple[Any, Any]]) -> None:
+        raise NotImplementedError
+
+    def pull_model(self) -> None:
+        raise NotImplementedError
+
+    def local_compute(self) -> None:
+        raise NotImplementedError
+
+    def push_update(self) -> None:
+        raise NotImplementedError
+
+    def on_epoch_finished(self, epoch_idx: int) -> None:
+        pass
+
+    def evaluate_model(self, input_data: Sequence[Tuple[Any, Any]], test_data: Sequence[Any]) -> Dict[str, float]:
+        return {}
+
+    def cleanup(self) -> None:
+        pass
+
+
+class ModelAccessor:
+    def push(self, key, delta) -> None: raise NotImplementedError
+    def push_many(self, keys, deltas) -> None: raise NotImplementedError
+    def pull(self, key): raise NotImplementedError
+    def pull_many(self, keys): raise NotImplementedError
+    def get_and_reset_metrics(self) -> Dict[str, float]: return {}
+
+
+class ETModelAccessor(ModelAccessor):
+    """push(k, d) = updateNoReply; push_many = multiUpdate().get() (blocking, reply required);
+    pull(k) = getOrInit; pull_many = multiGetOrInit().get(); wall-clock timers for both."""
+
+    def __init__(self, table) -> None:
+        self.table = table
+        self._pull = trace.Tracer()
+        self._push = trace.Tracer()
+
+    def push(self, key, delta) -> None:
+        self._push.start_timer()
+        self.table.update_no_reply(key, delta)
+        self._push.record_time(1)
+
+    def push_many(self, keys, deltas) -> None:
+        self._push.start_timer()
+        self.table.multi_update(keys, deltas).get(timeout=600)
+        self._push.record_time(len(keys))
+
+    def pull(self, key):
+        self._pull.start_timer()
+        v = self.table.get_or_init(key).get(timeout=600)
+        self._pull.record_time(1)
+        return v
+
+    def pull_many(self, keys):
+        self._pull.start_timer()
+        v = self.table.multi_get_or_init(keys).get(timeout=600)
+        self._pull.record_time(len(keys))
+        return v
+
+    def get_and_reset_metrics(self) -> Dict[str, float]:
+        out = {"pull_time_sec": self._pull.total_elapsed_time(), "push_time_sec": self._push.total_elapsed_time()}
+        self._pull.reset_trace()
+        self._push.reset_trace()
+        return out
+
+
+class CachedModelAccessor(ETModelAccessor):
+    """Worker-side model cache refreshed every `refresh_sec`, write-through local apply
+    (stand-alone `-model_cache_enabled`).  Unlike the reference (whose refresh task builds an
+    empty key list) the refresh really re-pulls the cached keys."""
+
+    def __init__(self, table, update_fn, refresh_sec: float = 10.0) -> None:
+        super().__init__(table)
+        self._fn = update_fn
+        self._cache: Dict[Any, Any] = {}
+        self._lock = threading.Lock()
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._refresh_loop, args=(refresh_sec,), daemon=True)
+        self._thread.start()
+
+    def _refresh_loop(self, period: float) -> None:
+        while not self._stop.wait(period):
+            with self._lock:
+                keys = list(self._cache)
+            if keys:
+                vals = self.table.multi_get_or_init(keys).get(timeout=600)
+                with self._lock:
+                    for k, v in zip(keys, vals):
+                        self._cache[k] = v
+
+    def pull(self, key):
+        with self._lock:
+            if key in self._cache:
+                return self._cache[key]
+        v = super().pull(key)
+        with self._lock:
+            self._cache[key] = v
+        return v
+
+    def pull_many(self, keys):
+        return [self.pull(k) for k in keys]
+
+    def push(self, key, delta) -> None:
+        super().push(key, delta)
+        with self._lock:
+            if key in self._cache:
+                self._cache[key] = self._fn.update_value(key, self._cache[key], delta)
+
+    def push_many(self, keys, deltas) -> None:
+        for k, d in zip(keys, deltas):
+            self.push(k, d)
+
+    def close(self) -> None:
+        self._stop.set()
+
+
+class TrainingDataProvider:
+    def prepare_data_for_epoch(self) -> None: raise NotImplementedError
+    def get_next_batch_data(self) -> List[Tuple[Any, Any]]: raise NotImplementedError
+    def get_epoch_data(self) -> List[Tuple[Any, Any]]: raise NotImplementedError
+    def get_num_batches_per_epoch(self) -> int: raise NotImplementedError
+
+
+class ETTrainingDataProvider(TrainingDataProvider):
+    """One local block of the input table is one mini-batch; blocks are shuffled every epoch and
+    the provider tolerates blocks that migrate away in the middle of an epoch."""
+
+    def __init__(self, input_table) -> None:
+        self._table = input_table
+        self._blocks: List[int] = []
+
+    def _tablet(self):
+        return self._table.get_local_tablet()
+
+    def prepare_data_for_epoch(self) -> None:
+        self._blocks = list(self._tablet().get_block_ids())
+        random.shuffle(self._blocks)
+
+    def get_num_batches_per_epoch(self) -> int:
+        return len(self._tablet().get_block_ids())
+
+    def get_next_batch_data(self) -> List[Tuple[Any, Any]]:
+        while self._blocks:
+            b = self._blocks.pop()
+            data = self._tablet().get_data_in_block(b)
+            if data:
+                return data
+        return []
+
+    def get_epoch_data(self) -> List[Tuple[Any, Any]]:
+        return list(self._tablet().get_data_iterator())
+
+
+# ------------------------------------------------------------------------------------------
+# barriers / messaging
+# ------------------------------------------------------------------------------------------
+class WorkerSideMsgSender:
+    def __init__(self, context, job_id: str) -> None:
+        self._ctx = context
+        self.job_id = job_id
+        self.worker_id = context.executor.executor_id
+
+    def _send(self, body: Dict[str, Any]) -> None:
+        self._ctx.send_to_driver({"job_id": self.job_id, "dolphin": body})
+
+    def send_progress_msg(self, progress: int) -> None:
+        self._send({"type": "ProgressMsg", "executor_id": self.worker_id, "progress": progress})
+
+    def send_sync_msg(self, state: str) -> None:
+        self._send({"type": "SyncMsg", "executor_id": self.worker_id, "state": state})
+
+    def send_mini_batch_sync_msg(self) -> None:
+        self._send({"type": "MiniBatchSyncMsg", "worker_id": self.worker_id})
+
+    def send_model_eval_ask_msg(self) -> None:
+        self._send({"type": "ModelEvalAskMsg", "executor_id": self.worker_id})
+
+
+class WorkerGlobalBarrier:
+    """Local FSM INIT -> RUN -> CLEANUP; await() = SyncMsg(state) then block until ReleaseMsg."""
+
+    def __init__(self, sender: WorkerSideMsgSender) -> None:
+        self._sender = sender
+        self.state = "INIT"
+        self._released = threading.Semaphore(0)
+
+    def await_(self) -> None:
+        self._sender.send_sync_msg(self.state)
+        self._released.acquire()
+        self.state = {"INIT": "RUN", "RUN": "CLEANUP"}.get(self.state, self.state)
+
+    def on_release_msg(self) -> None:
+        self._released.release()
+
+
+class MiniBatchBarrier:
+    """await() returns True when the master says the global mini-batch budget is exhausted."""
+
+    def __init__(self, sender: WorkerSideMsgSender) -> None:
+        self._sender = sender
+        self._ev = threading.Semaphore(0)
+        self._stop = False
+
+    def await_(self) -> bool:
+        self._sender.send_mini_batch_sync_msg()
+        self._ev.acquire()
+        return self._stop
+
+    def on_control_msg(self, stop: bool) -> None:
+        self._stop = stop
+        self._ev.release()
+
+
+class ModelEvalBarrier:
+    def __init__(self, sender: WorkerSideMsgSender) -> None:
+        self._sender = sender
+        self._ev = threading.Semaphore(0)
+        self._do_next = False
+
+    def ask(self) -> bool:
+        self._sender.send_model_eval_ask_msg()
+        self._ev.acquire()
+        return self._do_next
+
+    def on_answer(self, do_next: bool) -> None:
+        self._do_next = do_next
+        self._ev.release()
+
+
+# ------------------------------------------------------------------------------------------
+# tasklets
+# ------------------------------------------------------------------------------------------
+def build_trainer(context, params: Dict[str, Any], model_table, local_model_table, input_table):
+    cls = load_class(params["trainer_class"])
+    accessor_cls = CachedModelAccessor if params.get("model_cache_enabled") else ETModelAccessor
+    if accessor_cls is CachedModelAccessor:
+        accessor = CachedModelAccessor(model_table, model_table.components.update_fn)
+    else:
+        accessor = ETModelAccessor(model_table)
+    return cls(params=params, model_accessor=accessor, model_table=model_table,
+               local_model_table=local_model_table, input_table=input_table, context=context), accessor
+
+
+class WorkerTasklet(Tasklet):
+    """THE training loop."""
+
+    def __init__(self, context) -> None:
+        super().__init__(context)
+        p = context.params
+        self.job_id = p["job_id"]
+        self.sender = WorkerSideMsgSender(context, self.job_id)
+        self.global_barrier = WorkerGlobalBarrier(self.sender)
+        self.mini_batch_barrier = MiniBatchBarrier(self.sender)
+        self._abort = threading.Event()
+        acc = context.table_accessor
+        self.model_table = acc.get_table(p["model_table_id"])
+        self.input_table = acc.get_table(p["input_table_id"])
+        self.local_model_table = acc.get_table(p["local_model_table_id"]) if p.get("local_model_table_id") else None
+        self.trainer, self.accessor = build_trainer(context, p, self.model_table, self.local_model_table,
+                                                    self.input_table)
+        self.data_provider = ETTrainingDataProvider(self.input_table)
+        self.max_epochs = int(p.get("max_num_epochs", 1))
+        self.use_task_units = bool(p.get("task_units_enabled", True))
+
+    # master -> worker messages
+    def on_msg(self, payload: Any) -> None:
+        t = payload["type"]
+        if t == "ReleaseMsg":
+            self.global_barrier.on_release_msg()
+        elif t == "MiniBatchControlMsg":
+            self.mini_batch_barrier.on_control_msg(payload["stop"])
+
+    def _unit(self, name: str, resource: str, seq: int, fn) -> float:
+        info = TaskUnitInfo(self.job_id, name, resource, seq)
+        sched = self.context.task_units
+        if self.use_task_units:
+            sched.wait_schedule(self.context.tasklet_id, info)
+        t0 = time.perf_counter()
+        try:
+            with trace.span(name, job=self.job_id):
+                fn()
+        finally:
+            if self.use_task_units:
+                sched.on_task_unit_finished(self.context.tasklet_id, info)
+        return time.perf_counter() - t0
+
+    def run(self) -> Any:
+        ex_id = self.context.executor.executor_id
+        self.trainer.init_global_settings()
+        self.global_barrier.await_()                       # INIT barrier
+        seq = 0
+        stop = False
+        total_batches = 0
+        epoch = 0
+        while not stop and not self._abort.is_set():
+            epoch_t0 = time.perf_counter()
+            self.data_provider.prepare_data_for_epoch()
+            n_batches, n_inst = 0, 0
+            while True:
+                batch = self.data_provider.get_next_batch_data()
+                if not batch:
+                    break
+                if self.mini_batch_barrier.await_():       # SYNC (void unit): SSP clock + stop flag
+                    stop = True
+                    break
+                self.trainer.set_mini_batch_data(batch)
+                self.accessor.get_and_reset_metrics()
+                t0 = time.perf_counter()
+                self._unit("PULL", NET, seq, self.trainer.pull_model)
+                comp = self._unit("COMP", CPU, seq, self.trainer.local_compute)
+                self._unit("PUSH", NET, seq, self.trainer.push_update)
+                seq += 1
+                bt = time.perf_counter() - t0
+                am = self.accessor.get_and_reset_metrics()
+                self.sender.send_progress_msg(total_batches)
+                total_batches += 1
+                n_batches += 1
+                n_inst += len(batch)
+                bm = BatchMetrics(self.job_id, ex_id, epoch, n_batches - 1, len(batch), bt,
+                                  am.get("pull_time_sec", 0.0), max(0.0, bt - am.get("pull_time_sec", 0.0)
+                                                                    - am.get("push_time_sec", 0.0)),
+                                  am.get("push_time_sec", 0.0), len(batch) / bt if bt > 0 else 0.0)
+                self.context.metric_collector.add_custom_metric(bm.to_dict())
+                self.context.metric_collector.flush()
+            if n_batches == 0 and not stop:
+                # this worker holds no data (all blocks migrated away): just keep syncing
+                if self.mini_batch_barrier.await_():
+                    stop = True
+                else:
+                    time.sleep(0.01)
+            if not stop:
+                self.trainer.on_epoch_finished(epoch)
+            em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0)
+            self.context.metric_collector.add_custom_metric(em.to_dict())
+            self.context.metric_collector.flush()
+            epoch += 1
+        self.global_barrier.await_()                       # RUN -> CLEANUP barrier
+        self.trainer.cleanup()
+        return {"num_batches": total_batches, "num_epochs": epoch}
+
+    def close(self) -> None:
+        self._abort.set()
+        self.mini_batch_barrier.on_control_msg(True)
+
+
+class ServerTasklet(Tasklet):
+    """Servers are passive shard owners: the tasklet idles until closed."""
+
+    def __init__(self, context) -> None:
+        super().__init__(context)
+        self._latch = threading.Event()
+
+    def run(self) -> Any:
+        self._latch.wait()
+        return None
+
+    def close(self) -> None:
+        self._latch.set()
+
+
+class ModelEvaluationTasklet(Tasklet):
+    """Offline model evaluation: for every restored checkpoint the master answers `do_next`."""
+
+    def __init__(self, context) -> None:
+        super().__init__(context)
+        p = context.params
+        self.job_id = p["job_id"]
+        self.sender = WorkerSideMsgSender(context, self.job_id)
+        self.barrier = ModelEvalBarrier(self.sender)
+        self.params = p
+
+    def on_msg(self, payload: Any) -> None:
+        if payload["type"] == "ModelEvalAnsMsg":
+            self.barrier.on_answer(payload["do_next"])
+
+    def run(self) -> Any:
+        from ..common.dataloader import get_splits, make_parser, read_split
+        acc = self.context.table_accessor
+        p = self.params
+        results = []
+        test_data: List[Any] = []
+        if p.get("test_data_path"):
+            parser = make_parser(p.get("data_parser"))
+            for s in get_splits(p["test_data_path"], 1):
+                test_data.extend(parser.parse(read_split(s)))
+        while self.barrier.ask():
+            model_table = acc.get_table(p["model_table_id"])
+            input_table = acc.get_table(p["input_table_id"])
+            local_table = acc.get_table(p["local_model_table_id"]) if p.get("local_model_table_id") else None
+            trainer, _ = build_trainer(self.context, p, model_table, local_table, input_table)
+            data = list(input_table.get_local_tablet().get_data_iterator())
+            m = trainer.evaluate_model(data, test_data)
+            LOG.info("[%s] model evaluation: %s", self.job_id, m)
+            results.append(m)
+            trainer.cleanup()
+        return results

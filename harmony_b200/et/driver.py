@@ -397,7 +397,7 @@ class ChkpManagerMaster:
         if c is not None:
             # blocks still in an executor's temp dir are loaded by that executor when alive
             for e, blocks in c["temp_blocks"].items():
-                tgt = e if e in self._m.executors else assoc[0]
+                tgt = e if e in assoc else assoc[hash(e) % len(assoc)]
                 plan.setdefault(tgt, {"blocks": [], "committed": False})["blocks"].extend(blocks)
             committed = sorted(c["committed"])
         else:

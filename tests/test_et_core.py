@@ -1,0 +1,234 @@
+"""Elastic Table on the host backend: op semantics, ownership, migration, checkpoint, fallback.
+
+Mirrors the reference's RemoteAccessOpHandlerTest / OwnershipCacheTest / BlockManagerTest /
+MigrationManagerTest / FallbackManagerTest and the ET example integration tests.
+"""
+import tempfile
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from harmony_b200.et import ExecutorConfiguration, TableConfiguration, local_cluster
+from harmony_b200.et.driver import BlockManager
+from harmony_b200.et.ownership import OwnershipCache
+
+
+@pytest.fixture()
+def cluster():
+    tmp = tempfile.mkdtemp(prefix="hbchk")
+    conf = ExecutorConfiguration(chkp_temp_path=tmp + "/temp", chkp_commit_path=tmp + "/commit")
+    master, execs, launcher = local_cluster(3, conf, chkp_temp_path=tmp + "/temp", chkp_commit_path=tmp + "/commit")
+    yield master, execs, launcher
+    master.close()
+
+
+def _tables(launcher, table_id):
+    return [ex.tables.get_table(table_id) for _, ex in sorted(launcher.executors.items())]
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+def test_kv_table_op_sequence(cluster, ordered):
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id=f"kv{ordered}", num_total_blocks=16, is_ordered=ordered,
+                              update_function={"name": "add", "params": {}})
+    master.create_table(conf, execs).get(timeout=10)
+    t0, t1, t2 = _tables(launcher, conf.table_id)
+    keys = list(range(0, 400, 7)) if not ordered else [k * (2 ** 63 // 400) for k in range(0, 400, 7)]
+    for k in keys:
+        assert t0.put(k, k * 10).get(5) is None            # PUT returns the old value (None)
+    for k in keys:
+        assert t1.get(k).get(5) == k * 10                  # GET from another executor
+    assert t2.put(keys[0], 1).get(5) == keys[0] * 10        # PUT returns the previous value
+    assert t1.update(keys[0], 5).get(5) == 6               # UPDATE applies the update function at the owner
+    assert t0.put_if_absent(keys[0], 99).get(5) == 6       # PUT_IF_ABSENT keeps the existing value
+    assert t0.put_if_absent(-1 if not ordered else 3, 99).get(5) is None
+    assert t2.remove(keys[0]).get(5) == 6                  # REMOVE returns the removed value
+    assert t1.get(keys[0]).get(5) is None
+    assert t1.get_or_init(keys[0]).get(5) == 0             # GET_OR_INIT materialises initValue
+    got = t2.multi_get(keys[1:10]).get(5)
+    assert got == [k * 10 for k in keys[1:10]]
+    t0.multi_update(keys[1:10], [1] * 9).get(5)
+    assert t1.multi_get(keys[1:10]).get(5) == [k * 10 + 1 for k in keys[1:10]]
+    # local tablets partition the data: every key lives in exactly one executor
+    total = sum(t.get_local_tablet().get_num_data_items() for t in (t0, t1, t2))
+    assert total == len(keys) + 1
+    master.get_table(conf.table_id).drop().get(10)
+    assert not master.has_table(conf.table_id)
+
+
+def test_dense_table_pull_push(cluster):
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id="dense", dense=True, capacity=1000, row_dim=8, num_total_blocks=16,
+                              update_function={"name": "add", "params": {"init": "gaussian", "std": 0.1, "seed": 1}})
+    master.create_table(conf, execs).get(timeout=10)
+    t0, t1, t2 = _tables(launcher, "dense")
+    keys = np.arange(0, 1000, 3)
+    W0 = t0.multi_get_or_init(keys).get(10)
+    assert W0.shape == (len(keys), 8)
+    W0b = t1.multi_get_or_init(keys).get(10)               # same values from any executor
+    np.testing.assert_array_equal(W0, W0b)
+    d = np.ones((len(keys), 8), dtype=np.float32)
+    t1.multi_update(keys, d).get(10)
+    t2.multi_update_no_reply(keys, d)
+    time.sleep(0.3)
+    np.testing.assert_allclose(t0.multi_get_or_init(keys).get(10), W0 + 2, rtol=1e-6)
+    # duplicate keys in one push are all applied
+    t0.multi_update(np.array([5, 5, 5]), np.ones((3, 8), dtype=np.float32)).get(10)
+    base = t0.get_or_init(5).get(5)
+    t0.multi_update(np.array([5, 5]), np.ones((2, 8), dtype=np.float32)).get(10)
+    np.testing.assert_allclose(t0.get_or_init(5).get(5), base + 2, rtol=1e-6)
+
+
+def test_sgd_clamp_and_lda_update_functions(cluster):
+    master, execs, launcher = cluster
+    c1 = TableConfiguration(table_id="nmf", dense=True, capacity=100, row_dim=4, num_total_blocks=8,
+                            update_function={"name": "sgd_clamp", "params": {"step": 0.5, "lo": 0.0, "hi": 1.0,
+                                                                             "init": "uniform"}})
+    master.create_table(c1, execs).get(10)
+    t = _tables(launcher, "nmf")[0]
+    w = t.get_or_init(3).get(5)
+    assert ((w >= 0) & (w <= 1)).all()
+    t.update(3, np.full(4, 10.0, dtype=np.float32)).get(5)
+    np.testing.assert_array_equal(t.get(3).get(5), np.zeros(4, dtype=np.float32))    # clamped at 0
+    c2 = TableConfiguration(table_id="lda", num_total_blocks=8,
+                            update_function={"name": "lda_sparse", "params": {"num_topics": 5}})
+    master.create_table(c2, execs).get(10)
+    t = _tables(launcher, "lda")[1]
+    t.update(7, np.array([1, 2, 3, 1], dtype=np.int32)).get(5)
+    row = t.get(7).get(5)
+    assert list(row) == [0, 2, 0, 1, 0, 2]
+    t.update(7, np.array([1, -5], dtype=np.int32)).get(5)                              # clamp + nnz
+    assert list(t.get(7).get(5)) == [0, 0, 0, 1, 0, 1]
+
+
+def test_ownership_cache_blocks_access_until_allowed():
+    acks = []
+    oc = OwnershipCache("t", 4, "me", "driver", sync_ack=lambda *a: acks.append(a))
+    oc.init(["me", "other", "other", "me"])
+    assert oc.resolve_executor(0) is None and oc.resolve_executor(1) == "other"
+    oc.update(1, "other", "me")          # becomes incoming: access blocked until allow_access
+    got = []
+
+    def reader():
+        owner, unlock = oc.resolve_executor_with_lock(1)
+        got.append(owner)
+        unlock()
+    th = threading.Thread(target=reader); th.start()
+    time.sleep(0.15)
+    assert got == []
+    oc.allow_access_to_block(1)
+    th.join(2)
+    assert got == [None]
+    # update() waits for readers (write lock)
+    owner, unlock = oc.resolve_executor_with_lock(0)
+    done = []
+    th = threading.Thread(target=lambda: (oc.update(0, "me", "other"), done.append(1))); th.start()
+    time.sleep(0.15)
+    assert done == []
+    unlock(); th.join(2)
+    assert done == [1] and oc.resolve_executor(0) == "other"
+    # unassociation sync acks once the leaver owns nothing
+    oc.sync_unassociation(7, "other")
+    assert acks == []
+    oc.update(0, "other", "me"); oc.update(2, "other", "me")
+    assert acks == [(7, "t", "other")]
+
+
+def test_block_manager_round_robin_and_moves():
+    bm = BlockManager(12)
+    bm.init(["a", "b", "c"])
+    assert all(len(v) == 4 for v in bm.get_partition_info().values())
+    assert bm.get_owner_id(4) == "b"
+    blocks = bm.choose_blocks_to_move("a", 3)
+    assert len(blocks) == 3 and bm.choose_blocks_to_move("a", 3) == [9]    # moving blocks are not re-chosen
+    for b in blocks:
+        bm.update_owner(b, "a", "c"); bm.release_block_from_move(b)
+    assert bm.get_num_blocks("a") == 1 and bm.get_num_blocks("c") == 7
+    with pytest.raises(RuntimeError):
+        bm.update_owner(1, "b", "c")        # not chosen for migration
+
+
+@pytest.mark.parametrize("mutable", [True, False])
+def test_migration_conserves_data_and_updates_caches(cluster, mutable):
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id=f"mig{mutable}", num_total_blocks=12, is_mutable=mutable,
+                              update_function={"name": "add", "params": {}}, chunk_size=5)
+    master.create_table(conf, execs[:2]).get(10)          # executor-2 is not yet part of the table
+    table = master.get_table(conf.table_id)
+    table.subscribe([execs[2]]).get(10)                    # late subscriber gets the ownership map
+    t0 = launcher.executors[execs[0].id].tables.get_table(conf.table_id)
+    for k in range(300):
+        t0.put(k, k).get(5)
+    stop = threading.Event()
+
+    def writer():                                          # live traffic during the migration
+        i = 0
+        while not stop.is_set():
+            t0.update(i % 300, 0).get(5)
+            i += 1
+    th = threading.Thread(target=writer); th.start()
+    res = table.move_blocks(execs[0].id, execs[1].id, 4).get(20)
+    stop.set(); th.join(5)
+    assert res.is_completed and len(res.migrated_blocks) == 4
+    info = table.get_partition_info()
+    assert len(info[execs[0].id]) == 2 and len(info[execs[1].id]) == 10
+    # every executor (incl. the pure subscriber) converged to the driver's ownership truth
+    time.sleep(0.3)
+    truth = table.get_ownership_status()
+    for ex in launcher.executors.values():
+        assert ex.tables.get_components(conf.table_id).ownership.owners() == truth
+    t2 = launcher.executors[execs[2].id].tables.get_table(conf.table_id)
+    assert t2.multi_get(list(range(300))).get(10) == list(range(300))
+    # associate a new executor and move blocks onto it, then unassociate the first one
+    table.associate([execs[2]]).get(10)
+    assert table.move_blocks(execs[0].id, execs[2].id, 2).get(20).is_completed
+    table.unassociate(execs[0].id).get(20)
+    assert execs[0].id not in table.get_partition_info()
+    assert t2.multi_get(list(range(300))).get(10) == list(range(300))
+
+
+def test_checkpoint_restore_with_different_blocking(cluster):
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id="ck", dense=True, capacity=500, row_dim=4, num_total_blocks=10,
+                              update_function={"name": "add", "params": {"init": "gaussian", "std": 1.0, "seed": 2}})
+    master.create_table(conf, execs).get(10)
+    t = _tables(launcher, "ck")[0]
+    keys = np.arange(500)
+    W = t.multi_get_or_init(keys).get(10)
+    chkp_id = master.get_table("ck").checkpoint().get(20)
+    t.multi_update(keys, np.ones((500, 4), dtype=np.float32)).get(10)
+    # restore into a NEW table on 2 executors (re-blocking through multi_put)
+    master.create_table_from_chkp(chkp_id, execs[:2], table_id="ck_restored").get(20)
+    tr = launcher.executors[execs[0].id].tables.get_table("ck_restored")
+    np.testing.assert_array_equal(np.stack(tr.multi_get(keys).get(10)), W)
+    # commit + restore by path with another block count
+    master.chkp_master.commit(chkp_id)
+    time.sleep(0.3)
+    import os
+    path = os.path.join(master.chkp_commit_path, chkp_id)
+    assert os.path.isdir(path)
+    conf2 = TableConfiguration(table_id="ck_path", dense=True, capacity=500, row_dim=4, num_total_blocks=7,
+                               update_function="add", chkp_path=path)
+    master.create_table(conf2, execs).get(20)
+    tp = _tables(launcher, "ck_path")[2]
+    np.testing.assert_array_equal(np.stack(tp.multi_get(keys).get(10)), W)
+
+
+def test_fallback_reroutes_after_stale_ownership(cluster):
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id="fb", num_total_blocks=6, update_function="add")
+    master.create_table(conf, execs[:2]).get(10)
+    # executor-2 knows nothing about the table: a request sent to it bounces to the driver,
+    # which forwards it to the real owner (FallbackManager)
+    ex0 = launcher.executors[execs[0].id]
+    t0 = ex0.tables.get_table("fb")
+    t0.put(1, 41).get(5)
+    comps = ex0.tables.get_components("fb")
+    block = comps.partitioner.get_block_id(1)
+    owner = master.get_table("fb").get_owner_id(block)
+    stale = execs[2].id
+    comps.ownership._owners[block] = stale if owner != ex0.executor_id else comps.ownership._owners[block]
+    if owner != ex0.executor_id:
+        assert t0.get(1).get(5) == 41
