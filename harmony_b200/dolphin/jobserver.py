@@ -110,7 +110,8 @@ class DolphinJobEntity(JobEntity):
         p.update({"trainer_class": self.app.trainer_class, "device_trainer_class": self.app.device_trainer_class,
                   "model_table_id": self.server_tc.table_id, "input_table_id": self.worker_tc.table_id,
                   "local_model_table_id": self.local_tc.table_id if self.local_tc else None,
-                  "data_parser": self.app.input_parser, "app_id": self.app.app_id})
+                  "data_parser": self.app.input_parser, "app_id": self.app.app_id,
+                  "num_job_workers": max(1, len(self.executors))})
         return p
 
     def setup_executors_and_tables(self, executors: Sequence[AllocatedExecutor]) -> None:
@@ -179,6 +180,8 @@ class DolphinJobEntityBuilder:
 
     def build(self) -> DolphinJobEntity:
         app = load_app(self.conf["app"])
+        if self.conf.get("backend", "auto") not in ("host", "device"):
+            self.conf = self.conf.with_values(backend=self.driver.conf.get("backend", "host"))
         n = self.driver.next_job_count()
         job_id = f"{app.app_id}-{n}"
         server_tc, worker_tc, local_tc = build_tables_confs(app, self.conf, n)

@@ -55,6 +55,10 @@ class Trainer:
     def cleanup(self) -> None:
         pass
 
+    def summary(self) -> Dict[str, float]:
+        """Optional end-of-training numbers returned with the tasklet result."""
+        return {}
+
 
 class ModelAccessor:
     def push(self, key, delta) -> None: raise NotImplementedError
@@ -269,7 +273,8 @@ class ModelEvalBarrier:
 # tasklets
 # ------------------------------------------------------------------------------------------
 def build_trainer(context, params: Dict[str, Any], model_table, local_model_table, input_table):
-    cls = load_class(params["trainer_class"])
+    is_device = hasattr(model_table, "device_table") and params.get("device_trainer_class")
+    cls = load_class(params["device_trainer_class"] if is_device else params["trainer_class"])
     accessor_cls = CachedModelAccessor if params.get("model_cache_enabled") else ETModelAccessor
     if accessor_cls is CachedModelAccessor:
         accessor = CachedModelAccessor(model_table, model_table.components.update_fn)
@@ -373,8 +378,9 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.flush()
             epoch += 1
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
+        summary = self.trainer.summary()
         self.trainer.cleanup()
-        return {"num_batches": total_batches, "num_epochs": epoch}
+        return {"num_batches": total_batches, "num_epochs": epoch, **summary}
 
     def close(self) -> None:
         self._abort.set()

@@ -36,13 +36,17 @@ class DeviceTable:
     """SPMD handle: every rank of `group` constructs it collectively with the same conf."""
 
     def __init__(self, conf: TableConfiguration, arena: PeerArena, group: Optional[PeerGroup] = None,
-                 block_owners: Optional[Sequence[int]] = None, init: bool = True) -> None:
+                 block_owners: Optional[Sequence[Any]] = None, init: bool = True, collective: bool = True) -> None:
+        """collective=True : SPMD construction (every rank of `group` calls it; handles are exchanged
+        with all_gather).  collective=False: job-server construction -- the caller ships
+        `local_info()` to the driver and later feeds every peer's info to `apply_infos()`."""
         from ..ops import native
         assert conf.dense, "device tables are dense slab tables"
         self._n = native()
         self.conf = conf
         self.arena = arena
         self.group = group or arena.group
+        self.self_key = arena.self_key
         self.rank, self.world = self.group.rank, self.group.world
         self.device = torch.device("cuda", arena.device)
         self.update_fn = make_update_function(conf.update_function)
@@ -56,46 +60,57 @@ class DeviceTable:
             self.row_stride = 2 * _round_up(conf.row_dim, 32)   # kernel expects h at stride/2
         self.mode = PART_ORDERED if conf.is_ordered else PART_HASHED
         self.block_bytes = self.rows_per_block * self.row_stride * 4
-        self.owners: List[int] = list(block_owners) if block_owners is not None else \
+        self.owners: List[Any] = list(block_owners) if block_owners is not None else \
             [b % self.world for b in range(self.num_blocks)]
         # local slabs
         self._local_ptr: Dict[int, int] = {}
-        self._loc: Dict[int, Tuple[int, int, int]] = {}   # block -> (rank, seg, offset) for ALL blocks
+        self._loc: Dict[int, Tuple[Any, int, int]] = {}   # block -> (owner key, seg, offset) for ALL blocks
         for b in range(self.num_blocks):
-            if self.owners[b] == self.rank:
-                p, si, off = arena.alloc(self.block_bytes)
-                self._local_ptr[b] = p
-                self._loc[b] = (self.rank, si, off)
+            if self.owners[b] == self.self_key:
+                self._alloc_block(b)
         # pointer table lives in the arena too (so that a migrating peer can flip it remotely)
         self._ptr_tbl_ptr, tsi, toff = arena.alloc(self.num_blocks * 8)
         self.block_ptrs = arena.tensor(self._ptr_tbl_ptr, [self.num_blocks], torch.int64)
-        self._ptr_tbl_loc = (self.rank, tsi, toff)
-        self._exchange()
-        if init:
+        self.block_ptrs.zero_()
+        self._ptr_tbl_loc = (self.self_key, tsi, toff)
+        self._peer_tbl_ptrs: Dict[Any, int] = {}
+        if collective:
+            self.apply_infos(self.group.all_gather_object(self.local_info()))
+            if init:
+                self.init_local_blocks()
+            self.group.barrier()
+        elif init:
             self.init_local_blocks()
-        self.group.barrier()
+
+    def _alloc_block(self, b: int) -> int:
+        p, si, off = self.arena.alloc(self.block_bytes)
+        self._local_ptr[b] = p
+        self._loc[b] = (self.self_key, si, off)
+        return p
 
     # ---- handle exchange & pointer table ----
-    def _exchange(self) -> None:
-        mine = {"rank": self.rank,
-                "blocks": {b: loc for b, loc in self._loc.items() if loc[0] == self.rank},
-                "handles": {si: self.arena.segment_handle(si) for si in range(self.arena.num_segments())},
+    def local_info(self) -> Dict[str, Any]:
+        return {"key": self.self_key,
+                "blocks": {b: loc for b, loc in self._loc.items() if loc[0] == self.self_key},
+                "handles": {si: self.arena.segment_info(si) for si in range(self.arena.num_segments())},
                 "ptr_tbl": self._ptr_tbl_loc}
-        allinfo = self.group.all_gather_object(mine)
-        self._peer_tbl_ptrs: List[int] = [0] * self.world
-        ptrs = np.zeros(self.num_blocks, dtype=np.int64)
-        for info in allinfo:
-            r = info["rank"]
+
+    def apply_infos(self, infos: Sequence[Dict[str, Any]]) -> None:
+        """Map every peer's segments and fill the pointer table for the blocks they own."""
+        for info in infos:
+            r = info["key"]
             for si, h in info["handles"].items():
                 self.arena.map_peer(r, si, h)
             for b, (rr, si, off) in info["blocks"].items():
+                b = int(b)
                 self._loc[b] = (rr, si, off)
-                ptrs[b] = self.arena.resolve(rr, si, off)
+                self.block_ptrs[b] = self.arena.resolve(rr, si, off)
             _, tsi, toff = info["ptr_tbl"]
             self._peer_tbl_ptrs[r] = self.arena.resolve(r, tsi, toff)
-        assert (ptrs != 0).all(), "some blocks have no owner slab"
-        self.block_ptrs.copy_(torch.from_numpy(ptrs))
-        self._peer_tbl_ptrs_dev = torch.tensor(self._peer_tbl_ptrs, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)
+
+    def ptrs_complete(self) -> bool:
+        return bool((self.block_ptrs != 0).all().item())
 
     def _key_base_stride(self, b: int) -> Tuple[int, int]:
         return (b * self.rows_per_block, 1) if self.mode == PART_ORDERED else (b, self.num_blocks)
@@ -179,7 +194,7 @@ class DeviceTable:
         new_loc = None
         if self.rank == dst_rank:
             p, si, off = self.arena.alloc(self.block_bytes)
-            new_loc = (self.rank, si, off, self.arena.segment_handle(si))
+            new_loc = (self.self_key, si, off, self.arena.segment_info(si))
         infos = self.group.all_gather_object(new_loc)
         rr, si, off, handle = infos[dst_rank]
         if self.rank == dst_rank:
@@ -200,6 +215,38 @@ class DeviceTable:
         torch.cuda.synchronize(self.device)
         self.group.barrier()          # nobody references the old slab any more
         if self.rank == src_rank:
+            self.arena.free(self._local_ptr.pop(block))
+
+    # ---- non-collective migration primitives (driven by the job-server protocol) ----
+    def recv_block(self, block: int, stream: Optional[torch.cuda.Stream] = None) -> Tuple[Any, int, int, Dict[str, Any]]:
+        """Receiver half: allocate a slab and bulk-copy the block from its current owner's HBM
+        (peer mapping) on a side stream.  Returns the new location to broadcast."""
+        from ..ops import count_launch
+        src_va = int(self.block_ptrs[block].item())
+        p, si, off = self.arena.alloc(self.block_bytes)
+        s = stream or torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self._n.migrate_copy(src_va, p, self.block_bytes)
+            count_launch()
+        s.synchronize()
+        self._pending_recv = getattr(self, "_pending_recv", {})
+        self._pending_recv[block] = p
+        return (self.self_key, si, off, self.arena.segment_info(si))
+
+    def flip_block(self, block: int, new_owner: Any, loc: Tuple[Any, int, int, Any]) -> None:
+        """Ownership flip on THIS GPU: map the new slab, rewrite the pointer-table entry, release
+        the old slab when this GPU was the previous owner."""
+        rr, si, off, handle = loc
+        self.arena.map_peer(rr, si, handle)
+        old_owner = self.owners[block]
+        self.block_ptrs[block] = self.arena.resolve(rr, si, off)
+        torch.cuda.synchronize(self.device)
+        self._loc[block] = (rr, si, off)
+        self.owners[block] = new_owner
+        if new_owner == self.self_key:
+            self._local_ptr[block] = getattr(self, "_pending_recv", {}).pop(block)
+        elif old_owner == self.self_key and block in self._local_ptr:
             self.arena.free(self._local_ptr.pop(block))
 
     # ---- host import / export (checkpoint, tests) ----

@@ -317,6 +317,13 @@ class TableControlAgent:
                 fut.on_partial(None)
         return fut
 
+    def fan_out(self, executor_ids: Set[str], msg: Dict[str, Any]) -> AggregateFuture:
+        """Send `msg` (+ op_id) to every executor; the future completes with all the acks."""
+        op, fut = self._new(len(executor_ids))
+        for e in executor_ids:
+            self._m.send(e, dict(msg, op_id=op))
+        return fut
+
     def sync_ownership(self, table_id: str, deleted_executor_id: str, executor_ids: Set[str]) -> AggregateFuture:
         op, fut = self._new(len(executor_ids))
         for e in executor_ids:
@@ -656,6 +663,19 @@ class AllocatedTable:
         self._cond = threading.Condition()
         self._ongoing_migrations = 0
         self._ongoing_chkps = 0
+        self.device_infos: Dict[str, Any] = {}     # executor id -> slab locations (device backend)
+
+    @property
+    def is_device(self) -> bool:
+        return bool(self.conf is not None and self.conf.dense and self.conf.backend == "device")
+
+    def _exchange_peer_map(self, acks: List[Dict[str, Any]], targets: Set[str]) -> ResultFuture:
+        """Device backend, phase 2 of table init: ship every owner's slab map to `targets`."""
+        for a in acks:
+            if a and a.get("device_info") is not None:
+                self.device_infos[a["src"]] = a["device_info"]
+        return self._m.control.fan_out(targets, {"type": "TablePeerMap", "table_id": self.table_id,
+                                                 "infos": list(self.device_infos.values())})
 
     @property
     def table_id(self) -> str:
@@ -680,13 +700,19 @@ class AllocatedTable:
             self.sm.set_state("INITIALIZED")
             fut.on_completed(self)
 
-        def after_init(_):
+        def after_map(_=None):
             if conf.chkp_path:
                 self._m.chkp_master.load_from_path(conf.chkp_path, self).add_listener(done)
             elif conf.input_path:
                 self._m.control.load(conf.table_id, ids, conf.input_path).add_listener(done)
             else:
                 done()
+
+        def after_init(acks):
+            if self.is_device:
+                self._exchange_peer_map(acks, ids).add_listener(after_map)
+            else:
+                after_map()
         init_fut.add_listener(after_init)
         return fut
 
@@ -706,11 +732,17 @@ class AllocatedTable:
         self.block_manager.init(sorted(ids))
         fut: ResultFuture = ResultFuture()
 
-        def after_init(_):
+        def after_init(acks):
             def done(_=None):
                 self.sm.set_state("INITIALIZED")
                 fut.on_completed(self)
-            self._m.chkp_master.load(chkp_id, self).add_listener(done)
+
+            def load(_=None):
+                self._m.chkp_master.load(chkp_id, self).add_listener(done)
+            if self.is_device:
+                self._exchange_peer_map(acks, ids).add_listener(load)
+            else:
+                load()
         self._m.control.init_table(conf, ids, self.block_manager.get_ownership_status()).add_listener(after_init)
         return fut
 
@@ -724,6 +756,16 @@ class AllocatedTable:
         ids = {e.id for e in executors}
         op = self._m.subscriptions.start_subscription_init(self.table_id, ids)
         fut = self._m.control.init_table(self.conf, ids, self.block_manager.get_ownership_status())
+        if self.is_device:
+            out: ResultFuture = ResultFuture()
+
+            def after(acks):
+                def fin(_):
+                    self._m.subscriptions.finish_subscription_init(op)
+                    out.on_completed(None)
+                self._exchange_peer_map(acks, ids).add_listener(fin)
+            fut.add_listener(after)
+            return out
         fut.add_listener(lambda _: self._m.subscriptions.finish_subscription_init(op))
         return fut
 
@@ -745,6 +787,16 @@ class AllocatedTable:
             for e in ids:
                 self.block_manager.register_executor(e)
             self._m.subscriptions.finish_subscription_init(op)
+        if self.is_device and new_ids:
+            out: ResultFuture = ResultFuture()
+
+            def after(acks):
+                def fin(_):
+                    done(None)
+                    out.on_completed(None)
+                self._exchange_peer_map(acks, new_ids).add_listener(fin)
+            fut.add_listener(after)
+            return out
         fut.add_listener(done)
         return fut
 
@@ -773,7 +825,10 @@ class AllocatedTable:
         with self._cond:   # checkpoints and migrations are mutually exclusive per table
             self._cond.wait_for(lambda: self._ongoing_chkps == 0)
             self._ongoing_migrations += 1
-        fut = self._m.migrations.start_migration(self.block_manager, self.table_id, src, dst, blocks)
+        if self.is_device:
+            fut = self._device_move(src, dst, blocks)
+        else:
+            fut = self._m.migrations.start_migration(self.block_manager, self.table_id, src, dst, blocks)
 
         def done(_):
             with self._cond:
@@ -781,6 +836,32 @@ class AllocatedTable:
                 self._cond.notify_all()
         fut.add_listener(done)
         return fut
+
+    def _device_move(self, src: str, dst: str, blocks: List[int]) -> ResultFuture:
+        """Device migration: quiesce the table's accessors at a mini-batch boundary, let the
+        receiver bulk-copy the slabs over NVLink on its side stream, flip every pointer table,
+        resume.  Other tables / jobs keep running during the copy."""
+        out: ResultFuture = ResultFuture()
+        subs = self._m.subscriptions.get_subscribers(self.table_id) | self.block_manager.get_associator_ids()
+        ctl = self._m.control
+
+        def step_resume(_):
+            ctl.fan_out(subs, {"type": "TableResume", "table_id": self.table_id}).add_listener(
+                lambda _: out.on_completed(MigrationResult(True, "device migration completed", list(blocks))))
+
+        def step_flip(acks):
+            locs = acks[0]["locs"]
+            for b in blocks:
+                self.block_manager.update_owner(b, src, dst)
+                self.block_manager.release_block_from_move(b)
+            ctl.fan_out(subs, {"type": "DeviceOwnershipFlip", "table_id": self.table_id, "locs": locs,
+                               "new_owner": dst, "old_owner": src}).add_listener(step_resume)
+
+        def step_copy(_):
+            ctl.fan_out({dst}, {"type": "DeviceMoveRecv", "table_id": self.table_id,
+                                "block_ids": list(blocks)}).add_listener(step_flip)
+        ctl.fan_out(subs, {"type": "TableQuiesce", "table_id": self.table_id}).add_listener(step_copy)
+        return out
 
     def get_partition_info(self) -> Dict[str, Set[int]]:
         return self.block_manager.get_partition_info()
@@ -931,8 +1012,9 @@ class ETMaster:
 
     def on_message(self, m: Dict[str, Any]) -> None:
         t = m["type"]
-        if t in ("TableInitAck", "TableLoadAck", "TableDropAck", "OwnershipSyncAck"):
-            self.control.on_ack(m["op_id"], m.get("num_items"))
+        if t in ("TableInitAck", "TableLoadAck", "TableDropAck", "OwnershipSyncAck", "TablePeerMapAck",
+                 "TableQuiesceAck", "TableResumeAck", "DeviceMoveRecvAck", "DeviceOwnershipFlipAck"):
+            self.control.on_ack(m["op_id"], m)
         elif t == "OwnershipMoved":
             self.pool.submit(self.migrations.on_ownership_moved, m["op_id"], m["block_id"])
         elif t == "DataMoved":

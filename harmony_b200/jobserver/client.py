@@ -42,7 +42,9 @@ class JobServer:
             launcher = InProcessLauncher(_executor_factory(conf.get("backend", "auto")))
         self.et_master = ETMaster(self.transport, launcher, chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
                                   chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
-        self.driver = JobServerDriver(self.et_master, conf)
+        from ..et.launcher import detect_backend
+        self.backend = detect_backend(conf.get("backend", "auto"))
+        self.driver = JobServerDriver(self.et_master, conf.with_values(backend=self.backend))
         self._server: Optional[socketserver.ThreadingTCPServer] = None
         self._closed = threading.Event()
         self.port = int(conf.get("port", DEFAULT_PORT))
@@ -100,9 +102,13 @@ class JobServer:
 
 
 def _executor_factory(backend: str):
+    import itertools
+    from ..et.launcher import detect_backend, make_executor
+    resolved = detect_backend(backend)
+    counter = itertools.count()
+
     def factory(executor_id, transport, conf, driver_id):
-        from ..et.executor import Executor
-        return Executor(executor_id, transport, conf, driver_id)
+        return make_executor(executor_id, transport, conf, driver_id, resolved, next(counter))
     return factory
 
 

@@ -132,6 +132,9 @@ class MLRTrainer(Trainer):
             self.step *= self.decay_rate
             LOG.info("%d epochs passed. Step size decays from %g to %g", self.decay_period, prev, self.step)
 
+    def summary(self) -> Dict[str, float]:
+        return {"last_batch_loss": self.last_loss}
+
     def _loss_acc(self, data) -> Tuple[float, float, float]:
         if not data:
             return 0.0, 0.0, 0.0
@@ -163,7 +166,7 @@ def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:
         table_id=table_id, dense=True, capacity=features, row_dim=classes, dtype="float32",
         update_function={"name": "add", "params": {"init": "gaussian", "mean": 0.0,
                                                    "std": float(conf.get("model_gaussian", 0.001)), "seed": 0}},
-        backend=conf.get("backend", "host") if conf.get("backend", "host") != "auto" else "host")
+        backend=conf.get("backend", "host") if conf.get("backend", "host") in ("host", "device") else "host")
 
 
 APP = ETDolphinConfiguration(

@@ -1,0 +1,84 @@
+"""GPU-resident MLR trainer: the Dolphin Trainer SPI mapped onto the fused sm_100a kernels.
+
+pull_model  -> mlr_fwd_kernel      (PULL of the batch's feature rows from the owners' HBM fused with
+                                    the sparse dot, softmax, loss and the pre-scaled error)
+push_update -> mlr_bwd_push_kernel (gradient rows + PUSH + `w += delta` fused at the owners)
+Input blocks are converted once into device-resident CSR/CSC tensors (the input table lives in HBM).
+"""
+from __future__ import annotations
+
+import logging
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from ..dolphin.worker import Trainer
+from .mlr import batch_to_csr
+
+LOG = logging.getLogger(__name__)
+
+
+class MLRDeviceTrainer(Trainer):
+    def __init__(self, params: Dict[str, Any], model_table, input_table=None, **_: Any) -> None:
+        import torch
+        from ..models.mlr import MLRDeviceModel
+        self._torch = torch
+        self.params = params
+        self.table = model_table
+        self.dtable = model_table.device_table
+        self.comps = model_table.components
+        self.num_classes = int(params["classes"])
+        self.model = MLRDeviceModel(self.dtable, self.num_classes, float(params["step_size"]),
+                                    float(params.get("lambda", 0.0)))
+        self.decay_rate = float(params.get("decay_rate", 0.9))
+        self.decay_period = int(params.get("decay_period", 5))
+        self._cache: Dict[Any, Any] = {}
+        self._batch = None
+        self.num_workers = int(params.get("num_job_workers", 1))
+
+    def _to_device_batch(self, mini_batch):
+        from ..models.mlr import build_batch
+        key = (mini_batch[0][0], len(mini_batch)) if mini_batch else None
+        b = self._cache.get(key)
+        if b is None:
+            ptr, col, val, labels = batch_to_csr(mini_batch)
+            b = build_batch(ptr, col, val, labels).to(self.dtable.device)
+            self._cache[key] = b
+        return b
+
+    def set_mini_batch_data(self, mini_batch) -> None:
+        self._batch = self._to_device_batch(mini_batch)
+
+    def pull_model(self) -> None:
+        self.comps.gate.acquire_read()          # held from PULL to PUSH: migration waits for a batch boundary
+        self.model.stats.zero_()
+        self.model.forward(self._batch, True)
+
+    def local_compute(self) -> None:
+        pass                                    # fused into the pull / push kernels
+
+    def push_update(self) -> None:
+        try:
+            self.model.backward_push(self._batch)
+            self.model.apply_l2(self._batch.batch_size * self.num_workers)
+            self._torch.cuda.current_stream(self.dtable.device).synchronize()
+        finally:
+            self.comps.gate.release_read()
+
+    def summary(self) -> Dict[str, float]:
+        return {"last_batch_loss": float(self.model.stats[0])}
+
+    def on_epoch_finished(self, epoch_idx: int) -> None:
+        if self.decay_rate != 1 and (epoch_idx + 1) % self.decay_period == 0:
+            self.model.decay_step(self.decay_rate)
+
+    def evaluate_model(self, input_data, test_data) -> Dict[str, float]:
+        out = {}
+        for name, data in (("", list(input_data)), ("test", [(None, t) for t in test_data])):
+            if not data:
+                continue
+            b = self._to_device_batch(data)
+            loss, acc = self.model.evaluate(b)
+            out["loss" if not name else "testLoss"] = loss
+            out["avgAccuracy" if not name else "testAvgAccuracy"] = acc
+        return out

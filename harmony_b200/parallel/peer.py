@@ -46,17 +46,21 @@ class PeerArena:
 
     DEFAULT_SEGMENT = 1 << 30
 
-    def __init__(self, device: int, group: Optional[PeerGroup] = None, segment_bytes: Optional[int] = None) -> None:
+    def __init__(self, device: int, group: Optional[PeerGroup] = None, segment_bytes: Optional[int] = None,
+                 self_key: Any = None) -> None:
         from ..ops import native
         self._n = native()
         self.device = int(device)
         self.group = group or PeerGroup()
+        # identity of this arena among its peers: SPMD rank by default, executor id in the job server
+        self.self_key = self.group.rank if self_key is None else self_key
         self.segment_bytes = int(segment_bytes or os.environ.get("HB_ARENA_SEGMENT_BYTES", self.DEFAULT_SEGMENT))
         self._segments: List[Tuple[int, int]] = []            # (arena_id/base_ptr, bytes)
         self._alloc_seg: Dict[int, int] = {}                  # ptr -> segment index
         # peer mappings: (rank, seg_index) -> base VA in this process
         self._peer_base: Dict[Tuple[int, int], int] = {}
         self._peer_handles: Dict[Tuple[int, int], bytes] = {}
+        self._same_process: set = set()
 
     # ---- local allocation ----
     def alloc(self, nbytes: int) -> Tuple[int, int, int]:
@@ -83,6 +87,12 @@ class PeerArena:
     def segment_handle(self, seg_index: int) -> bytes:
         return bytes(self._n.ipc_export(self._segments[seg_index][0]))
 
+    def segment_info(self, seg_index: int) -> Dict[str, Any]:
+        """Everything a peer needs to map this segment: IPC handle for other processes, raw base
+        pointer for executors living in the SAME process (CUDA IPC cannot re-open its own handle)."""
+        return {"handle": self.segment_handle(seg_index), "pid": os.getpid(), "device": self.device,
+                "base": self._segments[seg_index][0]}
+
     def segment_base(self, seg_index: int) -> int:
         return self._segments[seg_index][0]
 
@@ -101,21 +111,28 @@ class PeerArena:
         return self._n.tensor_from_ptr(ptr, shape, list(strides), code, self.device)
 
     # ---- peer mapping ----
-    def map_peer(self, rank: int, seg_index: int, handle: bytes) -> int:
-        """Open (once) the IPC handle of segment `seg_index` of peer `rank`; returns its base VA."""
+    def map_peer(self, rank: Any, seg_index: int, handle: Any) -> int:
+        """Map (once) segment `seg_index` of peer `rank`; returns its base VA in this process.
+        `handle` is raw IPC bytes or a `segment_info()` dict."""
         key = (rank, seg_index)
         if key in self._peer_base:
             return self._peer_base[key]
-        if rank == self.group.rank:
+        if rank == self.self_key:
             base = self._segments[seg_index][0]
+        elif isinstance(handle, dict) and handle.get("pid") == os.getpid():
+            if handle["device"] != self.device:
+                self._n.enable_peer_access(self.device, handle["device"])
+            base = handle["base"]
+            self._same_process.add(key)
         else:
-            base = self._n.ipc_open(handle, self.device)
+            raw = handle["handle"] if isinstance(handle, dict) else handle
+            base = self._n.ipc_open(raw, self.device)
         self._peer_base[key] = base
         self._peer_handles[key] = handle
         return base
 
-    def resolve(self, rank: int, seg_index: int, offset: int, handle: Optional[bytes] = None) -> int:
-        if rank == self.group.rank:
+    def resolve(self, rank: Any, seg_index: int, offset: int, handle: Any = None) -> int:
+        if rank == self.self_key:
             return self._segments[seg_index][0] + offset
         key = (rank, seg_index)
         if key not in self._peer_base:
@@ -126,7 +143,7 @@ class PeerArena:
 
     def close(self) -> None:
         for (rank, _si), base in self._peer_base.items():
-            if rank != self.group.rank:
+            if rank != self.self_key and (rank, _si) not in self._same_process:
                 try:
                     self._n.ipc_close(base)
                 except Exception:  # noqa: BLE001

@@ -1,0 +1,89 @@
+"""Job server with the DEVICE backend: tables in HBM slabs, fused MLR kernels inside the Dolphin
+worker loop, device migration (quiesce -> P2P copy -> pointer flip) and checkpoint of a device table."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from helpers import write_mlr_sample  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_mlr_job_on_device_backend_matches_host_backend():
+    from harmony_b200.dolphin.launcher import DolphinJobLauncher
+    from harmony_b200.jobserver.client import JobServer
+    from harmony_b200.mlapps import mlr
+    from harmony_b200.utils.flags import Configuration
+    tmp = tempfile.mkdtemp(prefix="hbgpu")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=256, features=64, classes=4)
+    losses = {}
+    for backend in ("host", "device"):
+        port = _free_port()
+        js = JobServer(Configuration({"num_executors": 2, "port": port, "backend": backend,
+                                      "chkp_temp_path": tmp + "/t", "chkp_commit_path": tmp + "/c"})).start()
+        try:
+            args = ["-input", data, "-max_num_epochs", "8", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                    "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
+                    "-port", str(port)]
+            assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+            ok, result = js.driver.wait_job("MLR-0", timeout=300)
+            assert ok, result
+            losses[backend] = np.mean([r["last_batch_loss"] / 64.0 for r in result])
+            assert js.backend == backend
+        finally:
+            js.stop(kill=True)
+    # both backends train the same model (asynchronous interleaving differs slightly)
+    assert losses["device"] < 1.30 and abs(losses["device"] - losses["host"]) < 0.25, losses
+
+
+def test_device_table_migration_and_checkpoint_through_driver():
+    from harmony_b200.et import ExecutorConfiguration, LocalTransport, TableConfiguration
+    from harmony_b200.et.driver import ETMaster, InProcessLauncher
+    from harmony_b200.et.launcher import make_executor
+    tmp = tempfile.mkdtemp(prefix="hbgpu2")
+    transport = LocalTransport()
+    import itertools
+    cnt = itertools.count()
+    launcher = InProcessLauncher(lambda eid, tr, conf, did: make_executor(eid, tr, conf, did, "device", next(cnt)))
+    master = ETMaster(transport, launcher, chkp_temp_path=tmp + "/t", chkp_commit_path=tmp + "/c")
+    try:
+        ec = ExecutorConfiguration(chkp_temp_path=tmp + "/t", chkp_commit_path=tmp + "/c")
+        execs = master.add_executors(3, ec).get(30)
+        conf = TableConfiguration(table_id="dev", dense=True, capacity=2000, row_dim=24, num_total_blocks=12,
+                                  backend="device",
+                                  update_function={"name": "add", "params": {"init": "gaussian", "std": 0.1, "seed": 4}})
+        master.create_table(conf, execs[:2]).get(60)
+        table = master.get_table("dev")
+        t0 = launcher.executors[execs[0].id].tables.get_table("dev")
+        t1 = launcher.executors[execs[1].id].tables.get_table("dev")
+        keys = np.arange(2000)
+        W0 = t0.multi_get_or_init(keys).get()
+        np.testing.assert_array_equal(W0, t1.multi_get_or_init(keys).get())       # same view from both GPUs/executors
+        t1.multi_update(keys, np.ones((2000, 24), dtype=np.float32)).get()
+        np.testing.assert_allclose(t0.multi_get_or_init(keys).get(), W0 + 1, rtol=1e-6)
+        # migration through the driver protocol
+        res = table.move_blocks(execs[0].id, execs[1].id, 3).get(60)
+        assert res.is_completed and len(res.migrated_blocks) == 3
+        assert len(table.get_partition_info()[execs[1].id]) == 9
+        np.testing.assert_allclose(t0.multi_get_or_init(keys).get(), W0 + 1, rtol=1e-6)
+        t0.multi_update(keys, np.ones((2000, 24), dtype=np.float32)).get()
+        np.testing.assert_allclose(t1.multi_get_or_init(keys).get(), W0 + 2, rtol=1e-6)
+        # associate a third executor, move blocks onto it
+        table.associate([execs[2]]).get(60)
+        assert table.move_blocks(execs[1].id, execs[2].id, 4).get(60).is_completed
+        t2 = launcher.executors[execs[2].id].tables.get_table("dev")
+        np.testing.assert_allclose(t2.multi_get_or_init(keys).get(), W0 + 2, rtol=1e-6)
+        # checkpoint the device table and restore it into a host table with another blocking
+        chkp = table.checkpoint().get(120)
+        master.create_table_from_chkp(chkp, execs[:2], table_id="dev_restored").get(120)
+        tr = launcher.executors[execs[0].id].tables.get_table("dev_restored")
+        np.testing.assert_allclose(tr.multi_get_or_init(keys).get(), W0 + 2, rtol=1e-6)
+    finally:
+        master.close()
