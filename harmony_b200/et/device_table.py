@@ -105,8 +105,9 @@ class DeviceTable:
                 b = int(b)
                 self._loc[b] = (rr, si, off)
                 self.block_ptrs[b] = self.arena.resolve(rr, si, off)
-            _, tsi, toff = info["ptr_tbl"]
-            self._peer_tbl_ptrs[r] = self.arena.resolve(r, tsi, toff)
+            if info.get("ptr_tbl") is not None:
+                _, tsi, toff = info["ptr_tbl"]
+                self._peer_tbl_ptrs[r] = self.arena.resolve(r, tsi, toff)
         torch.cuda.synchronize(self.device)
 
     def ptrs_complete(self) -> bool:

@@ -854,6 +854,12 @@ class AllocatedTable:
             for b in blocks:
                 self.block_manager.update_owner(b, src, dst)
                 self.block_manager.release_block_from_move(b)
+                # keep the driver's slab map current for executors that subscribe later
+                key, si, off, seg_info = locs[b] if b in locs else locs[str(b)]
+                self.device_infos.get(src, {}).get("blocks", {}).pop(b, None)
+                di = self.device_infos.setdefault(dst, {"key": dst, "blocks": {}, "handles": {}, "ptr_tbl": None})
+                di["blocks"][b] = (key, si, off)
+                di["handles"][si] = seg_info
             ctl.fan_out(subs, {"type": "DeviceOwnershipFlip", "table_id": self.table_id, "locs": locs,
                                "new_owner": dst, "old_owner": src}).add_listener(step_resume)
 

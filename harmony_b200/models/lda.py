@@ -1,0 +1,89 @@
+"""LDA mini-batch on the device: pull vocabulary rows (K1) -> warp-per-document Gibbs sampler
+(K8) -> sparse integer push with clamp / nnz bookkeeping at the owners (K2+K5)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..et.device_table import DeviceTable
+
+
+@dataclass
+class LDABatch:
+    doc_ptr: torch.Tensor    # int32 [nd+1]   token offsets into the worker-local token arrays
+    tok_slot: torch.Tensor   # int32 [ntok_total_local] slot of each token's word in `vocab` (batch-local)
+    vocab: torch.Tensor      # int64 [U+1]    distinct words of the batch + the summary key V (last)
+    tok_lo: int              # first token of the batch in the worker-local z array
+    tok_hi: int
+
+    def to(self, device) -> "LDABatch":
+        return LDABatch(self.doc_ptr.to(device), self.tok_slot.to(device), self.vocab.to(device), self.tok_lo,
+                        self.tok_hi)
+
+
+def build_lda_batch(docs, tok_base: int, V: int) -> LDABatch:
+    """docs: list of int arrays (word ids). Token arrays are batch-local, z is addressed by tok_base."""
+    lens = np.asarray([len(d) for d in docs], dtype=np.int64)
+    ptr = np.zeros(len(docs) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum(lens)
+    words = np.concatenate(docs).astype(np.int64) if len(docs) else np.zeros(0, dtype=np.int64)
+    uw, slot = np.unique(words, return_inverse=True)
+    vocab = np.concatenate([uw, [V]]).astype(np.int64)
+    return LDABatch(torch.from_numpy(ptr), torch.from_numpy(slot.astype(np.int32)), torch.from_numpy(vocab),
+                    tok_base, tok_base + int(lens.sum()))
+
+
+class LDADeviceModel:
+    def __init__(self, table: DeviceTable, num_topics: int, num_vocabs: int, n_local_tokens: int,
+                 alpha: float, beta: float, seed: int = 0) -> None:
+        from ..ops import native
+        self._n = native()
+        self.table, self.K, self.V = table, num_topics, num_vocabs
+        self.alpha, self.beta, self.seed = float(alpha), float(beta), int(seed)
+        self.device = table.device
+        self.z = torch.zeros(max(1, n_local_tokens), dtype=torch.int32, device=self.device)
+        self.sum_delta = torch.zeros(num_topics, dtype=torch.int32, device=self.device)
+        self._iter = 0
+        self._rows = None
+        self._out = None
+
+    def _buffers(self, U1: int, ntok: int):
+        if self._rows is None or self._rows.shape[0] < U1:
+            self._rows = torch.empty((U1, self.table.row_stride), dtype=torch.int32, device=self.device)
+        if self._out is None or self._out[0].numel() < 2 * ntok:
+            self._out = (torch.empty(2 * ntok, dtype=torch.int64, device=self.device),
+                         torch.empty(2 * ntok, dtype=torch.int32, device=self.device),
+                         torch.empty(2 * ntok, dtype=torch.int32, device=self.device))
+        return self._rows[:U1], tuple(o[: 2 * ntok] for o in self._out)
+
+    def step_batch(self, b: LDABatch, init_mode: bool = False) -> None:
+        from ..ops import count_launch
+        ntok = b.tok_hi - b.tok_lo
+        if ntok == 0:
+            return
+        rows, (ok, ot, od) = self._buffers(b.vocab.numel(), ntok)
+        if not init_mode:
+            self._n.table_pull(*self.table.view(), b.vocab, rows)       # PULL batch vocabulary + summary row
+            count_launch()
+        nk = rows[b.vocab.numel() - 1]
+        self.sum_delta.zero_()
+        self._iter += 1
+        z_view = self.z[b.tok_lo:b.tok_hi]
+        self._n.lda_sample(b.doc_ptr, b.tok_slot, b.vocab, z_view, rows, nk, self.K, self.alpha, self.beta, self.V,
+                           self.seed + 7919 * self._iter, b.tok_lo, ok, ot, od, self.sum_delta, init_mode)
+        count_launch()
+        self.table.push_sparse_i32(ok, ot, od)                          # word-topic deltas -> owners
+        kk = torch.full((self.K,), self.V, dtype=torch.int64, device=self.device)
+        self.table.push_sparse_i32(kk, torch.arange(self.K, dtype=torch.int32, device=self.device), self.sum_delta)
+
+    def doc_topic_counts(self, b: LDABatch) -> torch.Tensor:
+        nd = b.doc_ptr.numel() - 1
+        lens = (b.doc_ptr[1:] - b.doc_ptr[:-1]).long()
+        doc_of = torch.repeat_interleave(torch.arange(nd, device=self.device), lens)
+        z = self.z[b.tok_lo:b.tok_hi].long()
+        out = torch.zeros((nd, self.K), dtype=torch.int32, device=self.device)
+        out.view(-1).index_add_(0, doc_of * self.K + z, torch.ones_like(z, dtype=torch.int32))
+        return out

@@ -36,6 +36,15 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
 void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                        int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
                        at::Tensor xval, at::Tensor D);
+// nmf_ops.cu
+void nmf_batch(at::Tensor csr_ptr, at::Tensor col_slot, at::Tensor val, at::Tensor L, at::Tensor l_row,
+               at::Tensor Rst, at::Tensor Gst, int64_t rank, double step, double lambda, double lo, double hi,
+               at::Tensor loss);
+// lda_ops.cu
+void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at::Tensor z, at::Tensor nwk,
+                at::Tensor nk, int64_t K, double alpha, double beta, int64_t V, int64_t seed, int64_t tok_base,
+                at::Tensor out_keys, at::Tensor out_topics, at::Tensor out_deltas, at::Tensor sum_delta,
+                bool init_mode);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -60,4 +69,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("clock_wait", &hb::clock_wait);
   m.def("mlr_forward", &hb::mlr_forward);
   m.def("mlr_backward_push", &hb::mlr_backward_push);
+  m.def("nmf_batch", &hb::nmf_batch);
+  m.def("lda_sample", &hb::lda_sample);
 }

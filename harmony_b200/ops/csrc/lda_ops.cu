@@ -1,0 +1,132 @@
+// LDA collapsed Gibbs sampling for one mini-batch of documents (K8), emitting the sparse
+// (word, topic, +-1) deltas that the PUSH kernel (table_ops.cu: push_sparse_i32_kernel, K2+K5)
+// reduce-adds into the owners' rows.
+//
+// Reference: dolphin/mlapps/lda/SparseLDASampler.java:141-274 (per-token resampling with the s/r/q
+// bucket decomposition -- a CPU optimisation of the SAME conditional
+//     p(z = k | .) ~ (n_dk + alpha) (n_wk + beta) / (n_k + V beta) ),
+// LDATrainer.java:317-357 (delta table build), :113-194 (initial random assignment pushed as counts).
+// GPU formulation: one warp per document; the document-topic histogram lives in shared memory,
+// the word-topic rows come from the batch-local staging buffer filled by ONE pull (K1) of the
+// batch vocabulary, every lane evaluates K/32 topics, a warp scan picks the new topic.
+#include "hb_common.cuh"
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+namespace hb {
+
+static constexpr int LDA_WARPS = 4;
+
+__global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
+    const int* __restrict__ doc_ptr, const int* __restrict__ tok_slot, const long long* __restrict__ slot_key,
+    int* __restrict__ z, int n_docs, const int* __restrict__ nwk, int nwk_stride, const int* __restrict__ nk,
+    int K, float alpha, float beta, float vbeta, unsigned long long seed, long long tok_base,
+    long long* __restrict__ out_keys, int* __restrict__ out_topics, int* __restrict__ out_deltas,
+    int* __restrict__ sum_delta, int init_mode) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int* ndk = reinterpret_cast<int*>(smem_raw) + (size_t)wid * K;
+  float* pk = reinterpret_cast<float*>(smem_raw + (size_t)LDA_WARPS * K * sizeof(int)) + (size_t)wid * K;
+  for (int d = blockIdx.x * LDA_WARPS + wid; d < n_docs; d += gridDim.x * LDA_WARPS) {
+    const int beg = doc_ptr[d], end = doc_ptr[d + 1];
+    for (int k = lane; k < K; k += 32) ndk[k] = 0;
+    __syncwarp();
+    if (!init_mode) {
+      for (int t = beg + lane; t < end; t += 32) atomicAdd(&ndk[z[t]], 1);
+    }
+    __syncwarp();
+    for (int t = beg; t < end; ++t) {
+      const int slot = tok_slot[t];
+      const int* row = nwk + (size_t)slot * nwk_stride;
+      int old = -1, nw;
+      if (init_mode) {
+        // initial uniformly random assignment
+        nw = (int)(rng_u32(seed, (unsigned long long)(tok_base + t)) % (unsigned)K);
+      } else {
+        old = z[t];
+        if (lane == 0) ndk[old] -= 1;
+        __syncwarp();
+        float lsum = 0.f;
+        for (int k = lane; k < K; k += 32) {
+          const int own = (k == old) ? 1 : 0;
+          const float a = (float)ndk[k] + alpha;
+          const float b = (float)max(row[k] - own, 0) + beta;
+          const float c = (float)max(nk[k] - own, 0) + vbeta;
+          const float p = a * b / c;
+          pk[k] = p;
+          lsum += p;
+        }
+        // inclusive scan of the lane sums (lane-major topic order)
+        float incl = lsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+        const float u = rng_uniform(seed, (unsigned long long)(tok_base + t)) * total;
+        const unsigned hit = __ballot_sync(0xffffffffu, incl > u);
+        const int src_lane = hit ? (__ffs(hit) - 1) : 31;
+        int cand = K - 1;
+        if (lane == src_lane) {
+          float acc = incl - lsum;
+          cand = -1;
+          for (int k = lane; k < K; k += 32) {
+            acc += pk[k];
+            cand = k;
+            if (acc > u) break;
+          }
+          if (cand < 0) cand = old;
+        }
+        nw = __shfl_sync(0xffffffffu, cand, src_lane);
+      }
+      if (lane == 0) {
+        ndk[nw] += 1;
+        z[t] = nw;
+        const long long key = slot_key[slot];
+        const int changed = (nw != old) ? 1 : 0;
+        out_keys[2 * (size_t)t] = key;      out_topics[2 * (size_t)t] = (old >= 0) ? old : 0;
+        out_deltas[2 * (size_t)t] = (old >= 0 && changed) ? -1 : 0;
+        out_keys[2 * (size_t)t + 1] = key;  out_topics[2 * (size_t)t + 1] = nw;
+        out_deltas[2 * (size_t)t + 1] = changed;
+        if (changed) {
+          if (old >= 0) atomicAdd(sum_delta + old, -1);
+          atomicAdd(sum_delta + nw, 1);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at::Tensor z, at::Tensor nwk,
+                at::Tensor nk, int64_t K, double alpha, double beta, int64_t V, int64_t seed, int64_t tok_base,
+                at::Tensor out_keys, at::Tensor out_topics, at::Tensor out_deltas, at::Tensor sum_delta,
+                bool init_mode) {
+  c10::cuda::CUDAGuard guard(z.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int n_docs = (int)doc_ptr.numel() - 1;
+  if (n_docs <= 0) return;
+  TORCH_CHECK(doc_ptr.scalar_type() == at::kInt && tok_slot.scalar_type() == at::kInt && z.scalar_type() == at::kInt);
+  TORCH_CHECK(slot_key.scalar_type() == at::kLong && out_keys.scalar_type() == at::kLong);
+  TORCH_CHECK(nwk.scalar_type() == at::kInt && nk.scalar_type() == at::kInt && nwk.stride(1) == 1);
+  const size_t smem = (size_t)LDA_WARPS * K * (sizeof(int) + sizeof(float));
+  TORCH_CHECK(smem <= 200 * 1024, "num_topics too large for the shared-memory sampler");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(lda_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int grid = std::min((n_docs + LDA_WARPS - 1) / LDA_WARPS, 148 * 8);
+  lda_sample_kernel<<<grid, LDA_WARPS * 32, smem, stream>>>(
+      doc_ptr.data_ptr<int>(), tok_slot.data_ptr<int>(),
+      reinterpret_cast<const long long*>(slot_key.data_ptr<int64_t>()), z.data_ptr<int>(), n_docs,
+      nwk.data_ptr<int>(), (int)nwk.stride(0), nk.data_ptr<int>(), (int)K, (float)alpha, (float)beta,
+      (float)(V * beta), (unsigned long long)seed, (long long)tok_base,
+      reinterpret_cast<long long*>(out_keys.data_ptr<int64_t>()), out_topics.data_ptr<int>(),
+      out_deltas.data_ptr<int>(), sum_delta.data_ptr<int>(), init_mode ? 1 : 0);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+}  // namespace hb

@@ -1,0 +1,84 @@
+"""NMF / LDA on the host backend through the stand-alone launcher (run_<app>.sh path)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from harmony_b200.dolphin.launcher import ETDolphinLauncher
+from harmony_b200.mlapps import lda, nmf
+
+from helpers import write_lda_sample, write_nmf_sample
+
+
+def test_nmf_standalone_loss_decreases():
+    tmp = tempfile.mkdtemp(prefix="hbnmf")
+    data = write_nmf_sample(os.path.join(tmp, "sample_nmf"), rows=80, cols=30, rank=4)
+    out = {}
+    for epochs in (1, 25):
+        res = ETDolphinLauncher.launch(nmf.APP, ["-input", data, "-max_num_epochs", str(epochs),
+                                                 "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                                                 "-num_server_blocks", "4", "-step_size", "0.01", "-rank", "4",
+                                                 "-features", "30", "-num_dolphin_workers", "2", "-num_servers", "1",
+                                                 "-decay_rate", "1.0"])
+        assert res.ok
+        out[epochs] = sum(r["last_batch_loss"] for r in res.results)
+    assert out[25] < 0.5 * out[1], out
+
+
+def test_nmf_kv_model_table_without_num_cols():
+    tmp = tempfile.mkdtemp(prefix="hbnmf2")
+    data = write_nmf_sample(os.path.join(tmp, "sample_nmf"), rows=40, cols=20, rank=3)
+    res = ETDolphinLauncher.launch(nmf.APP, ["-input", data, "-max_num_epochs", "2", "-num_mini_batches", "2",
+                                             "-num_worker_blocks", "2", "-num_server_blocks", "4",
+                                             "-step_size", "0.01", "-rank", "3", "-num_dolphin_workers", "1",
+                                             "-num_servers", "0"])
+    assert res.ok
+
+
+def test_lda_standalone_runs_and_conserves_counts():
+    tmp = tempfile.mkdtemp(prefix="hblda")
+    data = write_lda_sample(os.path.join(tmp, "sample_lda"), docs=40, vocab=30, topics=3, doc_len=20)
+    res = ETDolphinLauncher.launch(lda.APP, ["-input", data, "-max_num_epochs", "3", "-num_mini_batches", "4",
+                                             "-num_worker_blocks", "4", "-num_server_blocks", "4",
+                                             "-num_topics", "3", "-num_vocabs", "30", "-num_dolphin_workers", "2",
+                                             "-num_servers", "1"])
+    assert res.ok
+    assert sum(r["num_batches"] for r in res.results) >= 12
+
+
+def test_lda_host_trainer_keeps_global_counts_consistent():
+    """After init + a few sweeps the summary row equals the column sums of the word rows and the
+    total equals the number of tokens (the invariant the reference's update function maintains)."""
+    from harmony_b200.et import TableConfiguration, local_cluster
+    from harmony_b200.dolphin.worker import ETModelAccessor
+    master, execs, launcher = local_cluster(2)
+    try:
+        K, V = 4, 25
+        conf = dict(num_topics=K, num_vocabs=V, backend="host")
+        master.create_table(lda.model_table_conf(conf, "m"), execs).get(10)
+        master.create_table(lda.local_model_table_conf(conf, "l"), execs).get(10)
+        master.create_table(TableConfiguration(table_id="in", num_total_blocks=4, is_ordered=True,
+                                               update_function="void"), execs).get(10)
+        ex = launcher.executors[execs[0].id]
+        tin, tm, tl = (ex.tables.get_table(t) for t in ("in", "m", "l"))
+        rng = np.random.default_rng(0)
+        docs = [rng.integers(0, V, 15).astype(np.int32) for _ in range(12)]
+        part = ex.tables.get_components("in").partitioner
+        local_blocks = ex.tables.get_components("in").ownership.get_current_local_block_ids()
+        keys = [part.key_range(local_blocks[i % len(local_blocks)])[0] + i for i in range(len(docs))]
+        tin.multi_put(keys, docs).get(10)
+        tr = lda.LDATrainer(dict(conf, job_id="j"), ETModelAccessor(tm), local_model_table=tl, input_table=tin)
+        tr.init_global_settings()
+        batch = list(tin.get_local_tablet().get_data_iterator())
+        for _ in range(3):
+            tr.set_mini_batch_data(batch); tr.pull_model(); tr.local_compute(); tr.push_update()
+        rows = tm.multi_get(list(range(V + 1))).get(10)
+        mat = np.stack([r if r is not None else np.zeros(K + 1, dtype=np.int32) for r in rows])
+        assert mat[V, :K].sum() == sum(len(d) for d in docs)
+        np.testing.assert_array_equal(mat[:V, :K].sum(axis=0), mat[V, :K])
+        np.testing.assert_array_equal((mat[:, :K] > 0).sum(axis=1), mat[:, K])      # nnz bookkeeping
+        m = tr.evaluate_model(batch, [])
+        assert np.isfinite(m["docLLH"]) and np.isfinite(m["wordLLH"])
+    finally:
+        master.close()
