@@ -1,0 +1,125 @@
+"""Elastic re-partitioning on a LIVE job (reference OwnershipFirstMigrationTest, PlanCompilerTest,
+SampleOptimizersTest, WorkerStateManagerTest): AddVector self-validates that no push was lost
+while servers / workers are added, deleted or switched mid-run."""
+import os
+import tempfile
+import threading
+import time
+
+import pytest
+
+from harmony_b200.dolphin.launcher import ETDolphinLauncher
+from harmony_b200.dolphin.master import MasterSideMsgSender, WorkerStateManager
+from harmony_b200.dolphin.optimizer import (EvaluatorParameters, HomogeneousOptimizer, generate_transfer_steps,
+                                            make_optimizer)
+from harmony_b200.dolphin.plan import NAMESPACE_SERVER, NAMESPACE_WORKER, Plan, PlanCompiler, TransferStep
+from harmony_b200.et.config import TaskletConfiguration
+from harmony_b200.mlapps import examples
+
+
+def _args(optimizer, workers=2, servers=2, epochs=6):
+    path = examples.write_dummy_input(48)
+    return ["-input", path, "-num_dolphin_workers", str(workers), "-num_servers", str(servers),
+            "-max_num_epochs", str(epochs), "-num_mini_batches", "8", "-num_worker_blocks", "8",
+            "-num_server_blocks", "8", "-num_keys", "20", "-vector_size", "4", "-delta", "2",
+            "-compute_time_ms", "40", "-optimizer", optimizer, "-optimization_interval_ms", "300",
+            "-delay_after_optimization_ms", "100", "-min_num_required_batch_metrics", "1",
+            "-num_extra_resources", "1"]
+
+
+@pytest.mark.parametrize("optimizer", ["EmptyPlanOptimizer", "DeleteOneServerOptimizer", "AddOneServerOptimizer",
+                                       "MoveModelBlocksOptimizer"])
+def test_addvector_validates_under_server_reconfiguration(optimizer):
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, _args(optimizer))
+    assert res.ok, res.messages
+    if optimizer == "DeleteOneServerOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 1, W: 2)" in m for m in res.messages), res.messages
+    if optimizer == "AddOneServerOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 3, W: 2)" in m for m in res.messages), res.messages
+
+
+def test_addinteger_standalone():
+    res = ETDolphinLauncher.launch(examples.ADD_INTEGER, _args("EmptyPlanOptimizer", epochs=2))
+    assert res.ok
+
+
+def _compiler():
+    tc = lambda e: TaskletConfiguration(f"t-{e}", "x:Y")  # noqa: E731
+    return PlanCompiler("model", "input", tc, tc)
+
+
+def _types(plan):
+    out = {}
+    for op in plan.ops():
+        out[op.op_type] = out.get(op.op_type, 0) + 1
+    return out
+
+
+def test_plan_compiler_shapes():
+    c = _compiler()
+    # move only
+    p = Plan(); p.transfer_steps[NAMESPACE_SERVER].append(TransferStep("s0", "s1", 3))
+    assert _types(c.compile(p)) == {"MOVE": 1}
+    # add a worker: allocate -> (associate input, subscribe model) -> start ; move feeds the new worker first
+    p = Plan(); p.evaluators_to_add[NAMESPACE_WORKER].append("NEW"); p.transfer_steps[NAMESPACE_WORKER].append(TransferStep("w0", "NEW", 2))
+    et = c.compile(p, 1)
+    assert _types(et) == {"ALLOCATE": 1, "ASSOCIATE": 1, "SUBSCRIBE": 1, "START": 1, "MOVE": 1}
+    ops = {o.op_type: o for o in et.ops()}
+    assert et.dag.is_adjacent(ops["ALLOCATE"], ops["ASSOCIATE"]) and et.dag.is_adjacent(ops["ASSOCIATE"], ops["MOVE"])
+    assert et.dag.is_adjacent(ops["MOVE"], ops["START"]) and et.dag.get_root_vertices() == {ops["ALLOCATE"]}
+    # delete a server: stop -> move -> unassociate -> deallocate
+    p = Plan(); p.evaluators_to_delete[NAMESPACE_SERVER].append("s1"); p.transfer_steps[NAMESPACE_SERVER].append(TransferStep("s1", "s0", 4))
+    et = c.compile(p)
+    assert _types(et) == {"STOP": 1, "MOVE": 1, "UNASSOCIATE": 1, "DEALLOCATE": 1}
+    ops = {o.op_type: o for o in et.ops()}
+    assert et.dag.is_adjacent(ops["STOP"], ops["MOVE"]) and et.dag.is_adjacent(ops["MOVE"], ops["UNASSOCIATE"])
+    assert et.dag.is_adjacent(ops["UNASSOCIATE"], ops["DEALLOCATE"])
+    # switch: delete a server + add a worker => no allocate / deallocate at all
+    p = Plan(); p.evaluators_to_delete[NAMESPACE_SERVER].append("s1"); p.evaluators_to_add[NAMESPACE_WORKER].append("NEW")
+    p.transfer_steps[NAMESPACE_SERVER].append(TransferStep("s1", "s0", 4)); p.transfer_steps[NAMESPACE_WORKER].append(TransferStep("w0", "NEW", 2))
+    et = c.compile(p)
+    t = _types(et)
+    assert "ALLOCATE" not in t and "DEALLOCATE" not in t and t["MOVE"] == 2 and t["START"] == 1 and t["STOP"] == 1
+    assert {m.dst_executor_id for m in et.ops() if m.op_type == "MOVE"} == {"s0", "s1"}
+    # infeasible: two adds, no extra resources
+    p = Plan(); p.evaluators_to_add[NAMESPACE_WORKER] += ["A", "B"]
+    with pytest.raises(RuntimeError):
+        c.compile(p, 1)
+
+
+def test_homogeneous_optimizer_and_transfer_steps():
+    opt = HomogeneousOptimizer(num_total_mini_batches=100, default_bandwidth=8e9, opt_benefit_threshold=0.0)
+    workers = [EvaluatorParameters(f"w{i}", 10, {"batch_comp_time_sec": 1.0}) for i in range(2)]
+    servers = [EvaluatorParameters(f"s{i}", 8, {}) for i in range(4)]
+    # compute-bound job with tiny pulls: more workers (fewer servers) is better
+    plan = opt.optimize({NAMESPACE_SERVER: servers, NAMESPACE_WORKER: workers}, 6, {"AVG_PULL_SIZE_PER_MINI_BATCH": 1e3})
+    assert not plan.is_empty()
+    assert len(plan.get_evaluators_to_delete(NAMESPACE_SERVER)) >= 1 and len(plan.get_evaluators_to_add(NAMESPACE_WORKER)) >= 1
+    moved = sum(t.num_blocks for t in plan.get_transfer_steps(NAMESPACE_SERVER))
+    assert moved >= 8        # the deleted servers' blocks go somewhere
+    # sample optimizers produce valid plans
+    for name in ("AddOneServerOptimizer", "DeleteOneWorkerOptimizer", "ExchangeOneOptimizer"):
+        make_optimizer(name).optimize({NAMESPACE_SERVER: servers, NAMESPACE_WORKER: workers}, 7, {}).validate()
+
+
+def test_worker_state_manager_barriers_with_optimization():
+    released = []
+
+    class Sender:
+        def send_release_msg(self, w):
+            released.append(w)
+    sm = WorkerStateManager(3, Sender())
+    for w in ("a", "b"):
+        sm.on_sync_msg(w, "INIT")
+    assert released == [] and sm.sm.current_state == "INIT"
+    sm.on_sync_msg("c", "INIT")
+    assert sorted(released) == ["a", "b", "c"] and sm.sm.current_state == "RUN"
+    released.clear()
+    assert sm.try_enter_optimization() and not sm.try_enter_optimization()
+    sm.on_sync_msg("a", "RUN")                 # finishes RUN during optimisation: blocked
+    sm.on_sync_msg("d", "INIT")                # late-added worker skips the INIT barrier
+    assert released == ["d"]
+    sm.on_optimization_finished({"d"}, {"b"})  # b deleted, d added
+    assert sm.sm.current_state == "RUN_FINISHING"
+    sm.on_sync_msg("c", "RUN"); sm.on_sync_msg("d", "RUN")
+    assert sm.sm.current_state == "CLEANUP" and sorted(released[1:]) == ["a", "c", "d"]
