@@ -82,3 +82,49 @@ def test_lda_host_trainer_keeps_global_counts_consistent():
         assert np.isfinite(m["docLLH"]) and np.isfinite(m["wordLLH"])
     finally:
         master.close()
+
+
+def test_lasso_recovers_sparse_model():
+    from harmony_b200.mlapps import lasso
+    tmp = tempfile.mkdtemp(prefix="hblasso")
+    rng = np.random.default_rng(1)
+    F = 12
+    w = np.zeros(F); w[[1, 5, 9]] = [2.0, -3.0, 1.5]
+    path = os.path.join(tmp, "sample_lasso")
+    with open(path, "w") as f:
+        for _ in range(200):
+            x = rng.standard_normal(F)
+            y = x @ w + 0.01 * rng.standard_normal()
+            f.write(f"{y:.5f} " + " ".join(f"{i}:{v:.5f}" for i, v in enumerate(x)) + "\n")
+    res = ETDolphinLauncher.launch(lasso.APP, ["-input", path, "-max_num_epochs", "10", "-num_mini_batches", "4",
+                                               "-num_worker_blocks", "4", "-num_server_blocks", "2", "-features", str(F),
+                                               "-features_per_partition", "6", "-step_size", "1.0", "-lambda", "0.5",
+                                               "-model_gaussian", "0.1", "-num_dolphin_workers", "1",
+                                               "-num_servers", "1", "-decay_rate", "1.0"])
+    assert res.ok
+    assert res.results[0]["last_batch_loss"] < 0.05
+
+
+def test_gbt_regression_reduces_residual():
+    from harmony_b200.mlapps import gbt
+    tmp = tempfile.mkdtemp(prefix="hbgbt")
+    rng = np.random.default_rng(2)
+    path, meta = os.path.join(tmp, "sample_gbt"), os.path.join(tmp, "sample_gbt.meta")
+    with open(path, "w") as f:
+        for _ in range(240):
+            x = rng.random(4)
+            c = int(rng.integers(0, 3))
+            y = 3.0 * (x[0] > 0.5) + 2.0 * x[1] + (1.5 if c == 2 else 0.0)
+            f.write(f"{y:.4f} " + " ".join(f"{i}:{v:.4f}" for i, v in enumerate(x)) + f" 4:{c}\n")
+    with open(meta, "w") as f:
+        f.write("0:0 1:0 2:0 3:0 4:3 5:0\n")
+    out = {}
+    for epochs in (1, 8):
+        res = ETDolphinLauncher.launch(gbt.APP, ["-input", path, "-max_num_epochs", str(epochs), "-num_mini_batches", "3",
+                                                 "-num_worker_blocks", "3", "-num_server_blocks", "4", "-features", "5",
+                                                 "-step_size", "0.5", "-lambda", "0.0", "-gamma", "0.0",
+                                                 "-max_depth_of_tree", "3", "-leaf_min_size", "4", "-num_keys", "2",
+                                                 "-metadata_path", meta, "-num_dolphin_workers", "1", "-num_servers", "1"])
+        assert res.ok
+        out[epochs] = res.results[0]["last_batch_residual_mse"]
+    assert out[8] < 0.3 * out[1], out
