@@ -1,0 +1,7 @@
+#!/bin/bash
+# harmony_b200 launcher (CLI-compatible with the reference's jobserver/bin/run_gbt.sh; all flags are `-name value`).
+# EXAMPLE USAGE
+# ./run_gbt.sh -num_dolphin_workers 1 -num_servers 1 -input sample_gbt -metadata_path sample_gbt.meta -features 784 -step_size 0.1 -max_num_epochs 5 -num_mini_batches 4 -num_worker_blocks 4
+DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
+export PYTHONPATH="$DIR:$PYTHONPATH"
+exec python -c "import sys; from harmony_b200.mlapps.gbt import main_run as main; sys.exit(main(sys.argv[1:]))" "$@"

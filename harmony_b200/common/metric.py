@@ -1,0 +1,124 @@
+"""Generic metric tracker framework.
+
+Reference: common/.../metric/MetricsCollector.java:35-110 (start/stop aggregates the registered
+MetricTrackers and hands the result to a MetricsHandler), TimeMetricTracker, MemoryMetricTracker
+(periodic sampling), GCMetricTracker, InsertableMetricTracker, common/src/main/avro/metric.avsc.
+On a GPU box "memory" means HBM (torch.cuda.memory_stats) next to host RSS, and GC is replaced by
+CUDA-event timers.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from typing import Any, Callable, Dict, List, Optional
+
+from ..utils.misc import device_memory_mb, used_memory_mb
+
+
+class MetricTracker:
+    def start(self) -> None:
+        pass
+
+    def stop(self) -> Dict[str, float]:
+        return {}
+
+    def close(self) -> None:
+        pass
+
+
+class TimeMetricTracker(MetricTracker):
+    KEY = "METRIC_WALL_TIME_SEC"
+
+    def start(self) -> None:
+        self._t0 = time.perf_counter()
+
+    def stop(self) -> Dict[str, float]:
+        return {self.KEY: time.perf_counter() - self._t0}
+
+
+class MemoryMetricTracker(MetricTracker):
+    """Samples host RSS and device memory every `period_s`; reports max and mean."""
+
+    def __init__(self, period_s: float = 0.1) -> None:
+        self.period_s = period_s
+        self._samples: List[tuple] = []
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+
+    def start(self) -> None:
+        self._samples.clear()
+        self._stop.clear()
+
+        def run():
+            while not self._stop.wait(self.period_s):
+                self._samples.append((used_memory_mb(), device_memory_mb()))
+        self._thread = threading.Thread(target=run, daemon=True)
+        self._thread.start()
+
+    def stop(self) -> Dict[str, float]:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        s = self._samples or [(used_memory_mb(), device_memory_mb())]
+        host, dev = [a for a, _ in s], [b for _, b in s]
+        return {"METRIC_MEMORY_MAX_MB": max(host), "METRIC_MEMORY_AVG_MB": sum(host) / len(host),
+                "METRIC_DEVICE_MEMORY_MAX_MB": max(dev), "METRIC_DEVICE_MEMORY_AVG_MB": sum(dev) / len(dev)}
+
+
+class DeviceTimeMetricTracker(MetricTracker):
+    """cudaEvent-based device time of the bracketed region (replaces the JVM GC tracker)."""
+    KEY = "METRIC_DEVICE_TIME_SEC"
+
+    def start(self) -> None:
+        import torch
+        self._ok = torch.cuda.is_available()
+        if self._ok:
+            self._e0, self._e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self._e0.record()
+
+    def stop(self) -> Dict[str, float]:
+        if not self._ok:
+            return {self.KEY: 0.0}
+        import torch
+        self._e1.record()
+        torch.cuda.synchronize()
+        return {self.KEY: self._e0.elapsed_time(self._e1) / 1e3}
+
+
+class InsertableMetricTracker(MetricTracker):
+    def __init__(self) -> None:
+        self._vals: Dict[str, float] = {}
+
+    def put(self, key: str, value: float) -> None:
+        self._vals[key] = value
+
+    def stop(self) -> Dict[str, float]:
+        out, self._vals = self._vals, {}
+        return out
+
+
+class MetricsCollector:
+    def __init__(self, handler: Optional[Callable[[Dict[str, float]], None]] = None) -> None:
+        self._trackers: List[MetricTracker] = []
+        self._handler = handler
+        self.last: Dict[str, float] = {}
+
+    def register_trackers(self, trackers: List[MetricTracker]) -> None:
+        self._trackers.extend(trackers)
+
+    def start(self) -> None:
+        for t in self._trackers:
+            t.start()
+
+    def stop(self) -> Dict[str, float]:
+        out: Dict[str, float] = {}
+        for t in self._trackers:
+            out.update(t.stop())
+        self.last = out
+        if self._handler is not None:
+            self._handler(out)
+        return out
+
+    def close(self) -> None:
+        for t in self._trackers:
+            t.close()

@@ -92,6 +92,12 @@ class ETDolphinLauncher:
             job_id = f"{app.app_id}-0"
             dm = DolphinMaster(master, job_id, params, report=lambda s: (messages.append(s), LOG.info(s)))
             receiver.register(job_id, dm.metric_manager)
+            dashboard = None
+            if conf.get("dashboard_enabled"):
+                from .dashboard import DashboardConnector, DashboardServer
+                dashboard = DashboardServer(int(conf.get("dashboard_port", 9005)))
+                dm.metric_manager.sinks.append(DashboardConnector(dashboard.port))
+                messages.append(f"Dashboard: http://127.0.0.1:{dashboard.port}/")
             master.custom_handlers["TaskletCustom"] = lambda m: dm.on_worker_msg(m["payload"])
             orchestrator = None
             opt_name = conf.get("optimizer", "")
