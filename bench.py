@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--distinct_batches", type=int, default=4)
     ap.add_argument("--zipf", type=float, default=0.0)
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "pull", "ship"],
+                    help="pull: workers read/reduce model rows over NVLink (PS pull/push); "
+                         "ship: owners compute the sparse dot, only [B,C] activations cross NVLink; "
+                         "auto: ship when N > 1")
     return ap.parse_args()
 
 
@@ -152,6 +156,9 @@ def main():
     dev_batches = [hb.to(dev) for hb in host_batches]
     h2d_bytes = host_batches[0].nbytes()
 
+    mode = args.mode if args.mode != "auto" else ("ship" if world > 1 else "pull")
+    if args.impl != "harmony":
+        mode = "n/a"
     if args.impl == "harmony":
         arena = PeerArena(local_rank, group, segment_bytes=2 << 30)
         conf = TableConfiguration(table_id="model_table0", dense=True, capacity=F, row_dim=C,
@@ -161,13 +168,33 @@ def main():
         table = DeviceTable(conf, arena, group)
         model = MLRDeviceModel(table, C, args.step_size, max_batch=B)
         clock = DeviceClock(arena, group, slack=args.clock_slack)
+        if mode == "ship":
+            from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
+            ship = MLRShipModel(table, arena, group, clock, C, args.step_size, B)
+            # 2-D partition of the input: every rank derives its owner-side slices of ALL workers'
+            # blocks (same synthetic seeds on every rank: no exchange needed for the benchmark)
+            routed_host = []
+            for i in range(args.distinct_batches):
+                allw = [host_batches[i] if r == rank else
+                        synthetic_batch(B, F, C, args.nnz, seed=1000 * r + i, zipf=args.zipf) for r in range(world)]
+                routed_host.append(route_batches(table, allw, rank).pin())
+            host_batches = routed_host
+            dev_batches = [rb.to(dev) for rb in host_batches]
+            h2d_bytes = host_batches[0].nbytes()
+            model.stats = ship.stats
 
-        def step(batch):
-            clock.wait()
-            model.forward(batch, True)
-            model.backward_push(batch)
-            clock.tick()
-        parallelism = f"ps-sharded-model x{world} (co-located workers), block-hashed over {args.num_server_blocks} blocks"
+            def step(batch):
+                ship.step(batch)
+            parallelism = (f"ps-sharded-model x{world} (co-located), owner-side sparse dot; [B,C] activations "
+                           f"reduce-scattered / all-gathered over peer memory; {args.num_server_blocks} blocks")
+        else:
+            def step(batch):
+                clock.wait()
+                model.forward(batch, True)
+                model.backward_push(batch)
+                clock.tick()
+            parallelism = (f"ps-sharded-model x{world} (co-located workers), rows pulled / pushed over peer "
+                           f"memory; {args.num_server_blocks} blocks")
     else:  # NCCL all-reduce baseline: replicated model, dense gradient all-reduce, dense SGD update
         arena = PeerArena(local_rank, PeerGroup(0, 1, None), segment_bytes=2 << 30)
         one = PeerGroup(0, 1, None)
@@ -219,7 +246,7 @@ def main():
 
     # ---------------- per-phase device timing (outside the headline region) ----------------
     phase = None
-    if args.impl == "harmony":
+    if args.impl == "harmony" and mode == "pull":
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_pull = t_push = 0.0
         reps = min(args.steps, 10)
@@ -235,6 +262,12 @@ def main():
     e2e = None
     if not args.no_e2e:
         from harmony_b200.models.mlr import MLRBatch
+
+        def rebuild(views):
+            if mode == "ship":
+                from harmony_b200.models.mlr_ship import RoutedBatch
+                return RoutedBatch(MLRBatch(*views[:8]), views[8])
+            return MLRBatch(*views)
         maxn = [max(t.numel() for t in ts) for ts in zip(*[hb.tensors() for hb in host_batches])]
         staging = [[torch.empty(n, dtype=t.dtype, device=dev) for n, t in zip(maxn, host_batches[0].tensors())]
                    for _ in range(2)]                       # double-buffered device staging
@@ -247,7 +280,7 @@ def main():
                 v.copy_(src, non_blocking=True)             # H2D of this step's inputs (pinned)
                 views.append(v)
             model.stats.zero_()
-            step(MLRBatch(*views))
+            step(rebuild(views))
             return float(model.stats.cpu()[0])              # D2H of the step's loss (syncs)
         for i in range(max(3, args.warmup)):
             e2e_step(i)
@@ -263,7 +296,7 @@ def main():
 
     if rank == 0:
         value = world * args.steps / (ms / 1e3)
-        uniq = int(np.mean([hb.uniq_feat.numel() for hb in host_batches]))
+        uniq = int(np.mean([(hb.routed if mode == "ship" else hb).uniq_feat.numel() for hb in host_batches]))
         nnz = B * args.nnz
         row_bytes = table.row_stride * 4
         remote_frac = (world - 1) / world
@@ -274,7 +307,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": args.impl,
             "config": {"model": f"MLR {F}-feature x {C}-class (fp32 master weights, {F * row_bytes / 2**30:.2f} GiB sharded)",
                        "global_batch": B * world, "batch_per_worker": B, "nnz_per_instance": args.nnz,
-                       "seq_len": None, "parallelism": parallelism, "clock_slack": args.clock_slack,
+                       "seq_len": None, "parallelism": parallelism, "mode": mode,
+                       "clock_slack": 0 if mode == "ship" else args.clock_slack,
                        "l2_flush": "inputs larger than L2: ~%.2f GB of model rows touched per step per GPU vs 126 MB L2"
                                    % ((nnz + uniq) * row_bytes / 1e9),
                        "sgd": "step_size %.1e, decay_rate 0.9 / decay_period 5 epochs (applied per epoch)" % args.step_size},
@@ -285,7 +319,8 @@ def main():
                 "push_GBps_per_gpu": round(uniq * row_bytes / (phase["bwd_push_ms"] / 1e3) / 1e9, 1),
                 "pull_nvlink_GBps_per_gpu": round(nnz * row_bytes * remote_frac / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
                 "push_nvlink_GBps_per_gpu": round(uniq * row_bytes * remote_frac / (phase["bwd_push_ms"] / 1e3) / 1e9, 1)},
-            "nvlink_bytes_per_step_per_gpu": int((nnz + uniq) * row_bytes * remote_frac),
+            "nvlink_bytes_per_step_per_gpu": int((2 * B * world * row_bytes if mode == "ship"
+                                                   else (nnz + uniq) * row_bytes) * remote_frac),
         }
         if e2e is not None:
             out["e2e"] = e2e

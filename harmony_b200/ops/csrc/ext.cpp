@@ -45,6 +45,12 @@ void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at
                 at::Tensor nk, int64_t K, double alpha, double beta, int64_t V, int64_t seed, int64_t tok_base,
                 at::Tensor out_keys, at::Tensor out_topics, at::Tensor out_deltas, at::Tensor sum_delta,
                 bool init_mode);
+// mlr_ship_ops.cu
+void mlr_partial_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                         int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, int64_t B,
+                         at::Tensor logit_ptrs);
+void mlr_softmax_bcast(at::Tensor L, at::Tensor labels, int64_t num_classes, double step, at::Tensor d_ptrs,
+                       int64_t rank, at::Tensor stats);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -71,4 +77,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mlr_backward_push", &hb::mlr_backward_push);
   m.def("nmf_batch", &hb::nmf_batch);
   m.def("lda_sample", &hb::lda_sample);
+  m.def("mlr_partial_forward", &hb::mlr_partial_forward);
+  m.def("mlr_softmax_bcast", &hb::mlr_softmax_bcast);
 }

@@ -59,6 +59,28 @@ def main():
     assert err < 1e-4, f"mlr multi-gpu mismatch {err}"
     clock.barrier()
 
+    # 2b. "ship the activations" mode computes the same update (dot at the owners, only [B, C] moves)
+    from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
+    all_batches = [synthetic_batch(200, cap, classes, 11, seed=300 + r) for r in range(world)]
+    rb = route_batches(table, all_batches, rank).to(dev)
+    ship = MLRShipModel(table, arena, group, clock, classes, 0.01, 200)
+    W2 = table.to_dense().clone()
+    clock.barrier(); torch.cuda.synchronize()
+    ship.step(rb)
+    clock.barrier(); torch.cuda.synchronize(); clock.check()
+    delta = torch.zeros_like(W2)
+    loss_ref = 0.0
+    for r in range(world):
+        Wn, l, _ = mlr_reference_step(W2, all_batches[r].to(dev), classes, 0.01)
+        delta += Wn - W2
+        if r == rank:
+            loss_ref = l
+    err = float((table.to_dense() - (W2 + delta)).abs().max())
+    assert err < 1e-4, f"ship-mode mismatch {err}"
+    assert abs(float(ship.stats[0]) - loss_ref) / max(1.0, loss_ref) < 2e-3, (float(ship.stats[0]), loss_ref)
+    ship.step(rb); clock.barrier(); torch.cuda.synchronize(); clock.check()      # buffers are reusable
+    clock.barrier()
+
     # 3. migration: move block 3 to the next rank; content and subsequent pushes stay correct
     before = table.to_dense().clone()
     src = table.owners[3]; dst = (src + 1) % world

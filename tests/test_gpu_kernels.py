@@ -122,3 +122,24 @@ def test_device_clock_single(arena):
     torch.cuda.synchronize()
     c.check()
     assert int(c.clocks[0]) == 2
+
+
+def test_mlr_ship_mode_single_gpu_matches_reference(arena):
+    from harmony_b200.models.mlr import mlr_reference_step, synthetic_batch
+    from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
+    from harmony_b200.parallel.device_clock import DeviceClock
+    from harmony_b200.parallel.peer import PeerGroup
+    classes, features = 1000, 30000
+    t = _table(arena, features, classes, 64, False, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 7}})
+    g = PeerGroup()
+    clock = DeviceClock(arena, g)
+    b = synthetic_batch(300, features, classes, 17, seed=8)
+    rb = route_batches(t, [b], 0).to("cuda")
+    m = MLRShipModel(t, arena, g, clock, classes, 0.02, 300)
+    W0 = t.to_dense().clone()
+    m.step(rb)
+    Wref, loss_ref, _ = mlr_reference_step(W0, b.to("cuda"), classes, 0.02)
+    torch.testing.assert_close(t.to_dense(), Wref, rtol=2e-3, atol=2e-5)
+    assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 2e-3
+    assert float(m.L.abs().max()) == 0.0          # logits buffer re-zeroed for the next step
+    t.close()
