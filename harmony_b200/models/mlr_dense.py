@@ -1,0 +1,41 @@
+"""Dense-input MLR on the tensor cores (tcgen05 / TMEM / TMA), see ops/csrc/mlr_dense_tc.cu.
+
+`DenseMLR.logits(X)` = X[B, F] . W[F, C] where W is the (possibly multi-GPU) model table: the B
+operand tiles are TMA-loaded from the owners' slabs through one tensor map per block, so the pull
+is fused into the GEMM.  The table must be ORDERED (block b = rows [b*R, (b+1)*R)) with R % 32 == 0.
+"""
+from __future__ import annotations
+
+import torch
+
+from ..et.device_table import DeviceTable
+from ..et.partitioner import PART_ORDERED
+
+
+class DenseMLR:
+    def __init__(self, table: DeviceTable, num_classes: int) -> None:
+        from ..ops import native
+        self._n = native()
+        assert table.mode == PART_ORDERED, "dense MLR needs an ordered (range partitioned) model table"
+        assert table.rows_per_block % 32 == 0, "rows_per_block must be a multiple of 32"
+        self.table, self.num_classes = table, num_classes
+        self.device = table.device
+        self._bmaps = None
+        self._ptr_snapshot = None
+
+    def _maps(self) -> torch.Tensor:
+        ptrs = self.table.block_ptrs.cpu()
+        if self._bmaps is None or not torch.equal(ptrs, self._ptr_snapshot):   # re-encode after a migration
+            self._bmaps = self._n.make_block_tensormaps(ptrs, self.table.rows_per_block, self.table.row_stride,
+                                                        self.device.index)
+            self._ptr_snapshot = ptrs
+        return self._bmaps
+
+    def logits(self, X: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        from ..ops import count_launch
+        B = X.shape[0]
+        if out is None:
+            out = torch.empty((B, self.table.row_stride), dtype=torch.float32, device=self.device)
+        self._n.dense_logits_tf32(X, self._maps(), self.table.rows_per_block, self.table.row_stride, out)
+        count_launch()
+        return out

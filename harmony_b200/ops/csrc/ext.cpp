@@ -51,6 +51,10 @@ void mlr_partial_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t 
                          at::Tensor logit_ptrs);
 void mlr_softmax_bcast(at::Tensor L, at::Tensor labels, int64_t num_classes, double step, at::Tensor d_ptrs,
                        int64_t rank, at::Tensor stats);
+// mlr_dense_tc.cu
+at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_block, int64_t row_stride,
+                                 int64_t device);
+void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -78,5 +82,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nmf_batch", &hb::nmf_batch);
   m.def("lda_sample", &hb::lda_sample);
   m.def("mlr_partial_forward", &hb::mlr_partial_forward);
+  m.def("make_block_tensormaps", &hb::make_block_tensormaps);
+  m.def("dense_logits_tf32", &hb::dense_logits_tf32);
   m.def("mlr_softmax_bcast", &hb::mlr_softmax_bcast);
 }

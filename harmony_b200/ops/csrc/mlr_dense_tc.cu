@@ -1,0 +1,257 @@
+// Dense-input MLR forward on the 5th-gen tensor cores: logits[B, C] = X[B, F] . W[F, C].
+//
+// This is the one GEMM-shaped op of the framework (dense instances; the sparse 1M-feature path is
+// bandwidth-bound and lives in mlr_ops.cu).  The PULL of the model is fused into the GEMM: the B
+// operand tiles are TMA-loaded (cp.async.bulk.tensor) straight out of the OWNER's block slabs --
+// local HBM or an NVLink peer mapping -- through one tensor map per table block, so the model is
+// never staged or converted: the fp32 master weights are consumed as tf32 (kind::tf32).
+//
+//   warp 0      TMA producer  (A = X tile [128 x 32] K-major, B = W tile [32 x 128] MN-major, SW128)
+//   warp 1      TMEM alloc + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue: tcgen05.ld accumulators (TMEM) -> registers -> fp32 logits in global
+// 4-stage smem ring (32 KB / stage), accumulator 128 x 128 fp32 = 128 TMEM columns.
+// Reference op: MLRTrainer.predict (dolphin/mlapps/mlr/MLRTrainer.java:475-481, C sparse dots per
+// instance through Breeze) -- here one tensor-core GEMM per mini-batch.
+#include "hb_common.cuh"
+#include <cuda.h>
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+namespace hb {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 4, TC_UMMA_K = 8;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+constexpr int TC_B_BYTES = TC_BK * TC_BN * 4;          // 16 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 128;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_dst), "l"(tmap), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;          // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) dense_logits_tf32_kernel(
+    const __grid_constant__ CUtensorMap tmA, const CUtensorMap* __restrict__ tmB, float* __restrict__ out,
+    int out_stride, int M, int N, int K, int rows_per_block) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + TC_STAGES * TC_STAGE_BYTES;      // full[4], empty[4], tmem_full, tmem_slot
+  const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tmem_full = bars + 16 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TC_STAGES * TC_STAGE_BYTES + 16 * TC_STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+  const int KT = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is a warp-wide instruction; the address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TC_STAGES;
+        const uint32_t par = ((kt / TC_STAGES) & 1) ^ 1;
+        mbar_wait(empty0 + 8 * s, par);
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
+        tma_load_2d(sa, &tmA, full0 + 8 * s, kt * TC_BK, m0);
+        const int f0 = kt * TC_BK;
+        const int blk = f0 / rows_per_block, y = f0 - blk * rows_per_block;
+        const CUtensorMap* mb = tmB + blk;          // tensor map of the OWNER's slab (local or peer)
+#pragma unroll
+        for (int j = 0; j < TC_BN / 32; ++j)        // 4 column groups of 128 B (SW128 inner box limit)
+          tma_load_2d(sb + j * (TC_BK * 128), mb, full0 + 8 * s, n0 + 32 * j, y);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      // instruction descriptor (cute InstrDescriptor): D=f32, A=B=tf32, A K-major, B MN-major, N=128, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TC_STAGES;
+        mbar_wait(full0 + 8 * s, (kt / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < TC_BK / TC_UMMA_K; ++i) {
+          // A: K-major SW128, 8-row groups 1024 B apart, K-step = 8 tf32 = 32 B inside the swizzle row
+          const uint64_t ad = umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
+          // B: MN-major SW128, 128 B column groups (BK x 128 B = 4096 B apart), 8 K-rows = 1024 B
+          const uint64_t bd = umma_desc(sb + i * 1024, TC_BK * 128, 1024);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || i > 0) ? 1u : 0u);
+        }
+        tc_commit(empty0 + 8 * s);                  // smem slot is free once these MMAs retire
+      }
+      tc_commit(tmem_full);                         // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + 32 * q + lane;
+#pragma unroll
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < M) {
+        float* o = out + (size_t)row * out_stride + n0 + c * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          if (n0 + c * 32 + e < N)
+            *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    TORCH_CHECK(e == cudaSuccess && p != nullptr, "cuTensorMapEncodeTiled is not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static void encode_2d_f32(CUtensorMap* tm, void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                          uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * 4};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r);
+}
+
+// One tensor map per table block: [rows_per_block, row_stride] fp32 at the block's (local or peer) VA.
+at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_block, int64_t row_stride,
+                                 int64_t device) {
+  TORCH_CHECK(!block_ptrs_cpu.is_cuda() && block_ptrs_cpu.scalar_type() == at::kLong);
+  const int64_t nb = block_ptrs_cpu.numel();
+  std::vector<CUtensorMap> maps(nb);
+  const int64_t* p = block_ptrs_cpu.data_ptr<int64_t>();
+  for (int64_t b = 0; b < nb; ++b)
+    encode_2d_f32(&maps[b], reinterpret_cast<void*>(p[b]), (uint64_t)row_stride, (uint64_t)rows_per_block,
+                  (uint64_t)row_stride, 32, TC_BK);
+  auto out = at::empty({nb, (int64_t)sizeof(CUtensorMap)},
+                       at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (int)device));
+  cudaMemcpy(out.data_ptr(), maps.data(), nb * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
+  return out;
+}
+
+// logits[M, >=N] = X[M, K] . W[K, N]   (W rows live in the table blocks described by `bmaps`)
+void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out) {
+  c10::cuda::CUDAGuard guard(X.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kFloat && out.stride(1) == 1 && out.stride(0) % 4 == 0);
+  const int M = (int)X.size(0), K = (int)X.size(1), N = (int)n_cols;
+  TORCH_CHECK(K % TC_BK == 0 && rows_per_block % TC_BK == 0, "features and rows_per_block must be multiples of 32");
+  TORCH_CHECK(X.stride(0) % 4 == 0 && (reinterpret_cast<uintptr_t>(X.data_ptr<float>()) % 16 == 0));
+  TORCH_CHECK(out.size(0) >= M && out.size(1) >= N);
+  CUtensorMap tmA;
+  encode_2d_f32(&tmA, X.data_ptr<float>(), (uint64_t)K, (uint64_t)M, (uint64_t)X.stride(0), TC_BK, TC_BM);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dense_logits_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    attr = true;
+  }
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
+  dense_logits_tf32_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
+      tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(), (int)out.stride(0), M, N,
+      K, (int)rows_per_block);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+}  // namespace hb

@@ -143,3 +143,21 @@ def test_mlr_ship_mode_single_gpu_matches_reference(arena):
     assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 2e-3
     assert float(m.L.abs().max()) == 0.0          # logits buffer re-zeroed for the next step
     t.close()
+
+
+@pytest.mark.parametrize("B,F,C", [(128, 256, 128), (300, 1024, 1000), (4096, 4096, 1000)])
+def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C):
+    """tcgen05 (kind::tf32) GEMM whose B operand is TMA-loaded from the table's block slabs."""
+    from harmony_b200.models.mlr_dense import DenseMLR
+    t = _table(arena, F, C, max(1, F // 256), True, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 3}})
+    assert t.rows_per_block % 32 == 0
+    X = torch.randn((B, F), device="cuda")
+    W = t.to_dense()
+    out = DenseMLR(t, C).logits(X)
+    torch.cuda.synchronize()
+    ref = X.double() @ W.double()
+    err = (out[:, :C].double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err < 2e-3 * scale + 1e-3, (err, scale)       # tf32 inputs (10-bit mantissa), fp32 accumulate
+    assert float(out[:, C:].abs().max()) == 0.0 if out.shape[1] > C else True
+    t.close()
