@@ -39,3 +39,33 @@ class DenseMLR:
         self._n.dense_logits_tf32(X, self._maps(), self.table.rows_per_block, self.table.row_stride, out)
         count_launch()
         return out
+
+    # ---- full training step: tensor-core forward -> softmax -> tensor-core backward fused with the push ----
+    def step(self, X: torch.Tensor, labels: torch.Tensor, step_size: float, stats: torch.Tensor = None) -> None:
+        """X [B, F] fp32 dense instances, labels int32 [B].  W += -step * X^T (softmax(XW) - Y)."""
+        from ..ops import count_launch
+        B, F = X.shape
+        Bp = (B + 31) // 32 * 32
+        if Bp != B:                                  # the batch is the K dimension of the backward GEMM
+            Xp = torch.zeros((Bp, F), dtype=torch.float32, device=self.device)
+            Xp[:B] = X
+        else:
+            Xp = X.contiguous()
+        stride = self.table.row_stride
+        if getattr(self, "_L", None) is None or self._L.shape[0] < Bp:
+            self._L = torch.empty((Bp, stride), dtype=torch.float32, device=self.device)
+            self._D = torch.zeros((Bp, stride), dtype=torch.float32, device=self.device)
+            self._dptr = torch.tensor([self._D.data_ptr()], dtype=torch.int64, device=self.device)
+        L, D = self._L[:Bp], self._D[:Bp]
+        if Bp != B:
+            D[B:].zero_()
+        self.logits(Xp, L)
+        if stats is None:
+            stats = getattr(self, "stats", None)
+            if stats is None:
+                stats = self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._n.mlr_softmax_bcast(L[:B], labels, self.num_classes, float(step_size), self._dptr, 0, stats)
+        count_launch()
+        bp, rpb, st, _dim, mode = self.table.view()
+        self._n.dense_grad_push_tf32(Xp, D, bp, rpb, st, self.num_classes, mode)
+        count_launch()

@@ -66,19 +66,27 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor), SWIZZLE_128B.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;          // LayoutType::SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // LayoutType: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) dense_logits_tf32_kernel(
+// A_MN = false : A tile is K-major  (forward:  A = X[B, F],  M = instances, K = features)
+// A_MN = true  : A tile is MN-major (backward: A = X^T,      M = features,  K = instances)
+// PUSH = false : epilogue stores fp32 logits
+// PUSH = true  : epilogue reduce-adds the gradient tile straight into the OWNERS' table rows
+//                (GEMM fused with the PUSH + `w += delta` update, K6-bwd + K2 + K3)
+template <bool A_MN, bool PUSH>
+__global__ void __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_kernel(
     const __grid_constant__ CUtensorMap tmA, const CUtensorMap* __restrict__ tmB, float* __restrict__ out,
-    int out_stride, int M, int N, int K, int rows_per_block) {
+    int out_stride, int M, int N, int K, int rows_per_block, int dbg, int b_lbo, int b_sbo, int idesc_xor, int b_layout,
+    TableView Wtab) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024 B alignment
@@ -115,7 +123,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_logits_tf32_kernel(
         mbar_wait(empty0 + 8 * s, par);
         const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
         mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
-        tma_load_2d(sa, &tmA, full0 + 8 * s, kt * TC_BK, m0);
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j)      // A^T: 4 column groups of 32 features x BK instances
+            tma_load_2d(sa + j * (TC_BK * 128), &tmA, full0 + 8 * s, m0 + 32 * j, kt * TC_BK);
+        } else {
+          tma_load_2d(sa, &tmA, full0 + 8 * s, kt * TC_BK, m0);
+        }
         const int f0 = kt * TC_BK;
         const int blk = f0 / rows_per_block, y = f0 - blk * rows_per_block;
         const CUtensorMap* mb = tmB + blk;          // tensor map of the OWNER's slab (local or peer)
@@ -128,20 +142,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_logits_tf32_kernel(
     if (lane == 0) {
       // ===== MMA issuer (one thread) =====
       // instruction descriptor (cute InstrDescriptor): D=f32, A=B=tf32, A K-major, B MN-major, N=128, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | (1u << 16) |
                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kt = 0; kt < KT; ++kt) {
         const int s = kt % TC_STAGES;
         mbar_wait(full0 + 8 * s, (kt / TC_STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        if (dbg && kt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+          const float* fa = reinterpret_cast<const float*>(smem + s * TC_STAGE_BYTES);
+          const float* fb = fa + TC_A_BYTES / 4;
+          printf("[tc dbg] tmem_base=%08x base=%08x A[0..3]=%f %f %f %f  B[0..3]=%f %f %f %f idesc=%08x\n", tmem_base,
+                 base, fa[0], fa[1], fa[2], fa[3], fb[0], fb[1], fb[2], fb[3], idesc ^ (uint32_t)idesc_xor);
+        }
 #pragma unroll
         for (int i = 0; i < TC_BK / TC_UMMA_K; ++i) {
           // A: K-major SW128, 8-row groups 1024 B apart, K-step = 8 tf32 = 32 B inside the swizzle row
-          const uint64_t ad = umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
+          const uint64_t ad = A_MN ? umma_desc(sa + i * 1024, TC_BK * 128, 512, 1)
+                                   : umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
           // B: MN-major SW128, 128 B column groups (BK x 128 B = 4096 B apart), 8 K-rows = 1024 B
-          const uint64_t bd = umma_desc(sb + i * 1024, TC_BK * 128, 1024);
-          tc_mma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || i > 0) ? 1u : 0u);
+          const uint64_t bd = umma_desc(sb + i * 1024, b_lbo, b_sbo, (uint32_t)b_layout);
+          tc_mma_tf32(tmem_base, ad, bd, idesc ^ (uint32_t)idesc_xor, (kt > 0 || i > 0) ? 1u : 0u);
         }
         tc_commit(empty0 + 8 * s);                  // smem slot is free once these MMAs retire
       }
@@ -167,7 +188,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_logits_tf32_kernel(
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
+      if (dbg && c == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+        printf("[tc dbg] epi warp %d q %d taddr=%08x v0..3 = %f %f %f %f\n", warp, q, taddr, __uint_as_float(v[0]),
+               __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+      if (PUSH) {
+        if (row < M) {
+          float* o = row_ptr<float>(Wtab, (long long)row) + n0 + c * 32;   // owner's row (local or peer)
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            if (n0 + c * 32 + e < N)
+              red_add_f4_sys(o + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+        }
+      } else if (row < M) {
         float* o = out + (size_t)row * out_stride + n0 + c * 32;
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
@@ -203,27 +236,29 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static void encode_2d_f32(CUtensorMap* tm, void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
-                          uint32_t box_inner, uint32_t box_outer) {
+                          uint32_t box_inner, uint32_t box_outer,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_stride_elems * 4};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code ", (int)r);
 }
 
 // One tensor map per table block: [rows_per_block, row_stride] fp32 at the block's (local or peer) VA.
 at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_block, int64_t row_stride,
-                                 int64_t device) {
+                                 int64_t device, int64_t swizzle_mode) {
   TORCH_CHECK(!block_ptrs_cpu.is_cuda() && block_ptrs_cpu.scalar_type() == at::kLong);
   const int64_t nb = block_ptrs_cpu.numel();
   std::vector<CUtensorMap> maps(nb);
   const int64_t* p = block_ptrs_cpu.data_ptr<int64_t>();
   for (int64_t b = 0; b < nb; ++b)
     encode_2d_f32(&maps[b], reinterpret_cast<void*>(p[b]), (uint64_t)row_stride, (uint64_t)rows_per_block,
-                  (uint64_t)row_stride, 32, TC_BK);
+                  (uint64_t)row_stride, 32, TC_BK,
+                  swizzle_mode == 1 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
   auto out = at::empty({nb, (int64_t)sizeof(CUtensorMap)},
                        at::TensorOptions().dtype(at::kByte).device(at::kCUDA, (int)device));
   cudaMemcpy(out.data_ptr(), maps.data(), nb * sizeof(CUtensorMap), cudaMemcpyHostToDevice);
@@ -231,7 +266,8 @@ at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_blo
 }
 
 // logits[M, >=N] = X[M, K] . W[K, N]   (W rows live in the table blocks described by `bmaps`)
-void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out) {
+void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out,
+                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout) {
   c10::cuda::CUDAGuard guard(X.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
@@ -244,13 +280,55 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
   encode_2d_f32(&tmA, X.data_ptr<float>(), (uint64_t)K, (uint64_t)M, (uint64_t)X.stride(0), TC_BK, TC_BM);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(dense_logits_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(dense_gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     attr = true;
   }
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
-  dense_logits_tf32_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
+  TableView none{};
+  dense_gemm_tf32_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
       tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(), (int)out.stride(0), M, N,
-      K, (int)rows_per_block);
+      K, (int)rows_per_block, (int)dbg, (int)(b_lbo ? b_lbo : TC_BK * 128), (int)(b_sbo ? b_sbo : 512),
+      (int)idesc_xor, (int)(b_layout ? b_layout : 1), none);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// W[f, :] += sum_b X[b, f] * D[b, :]   (D is pre-scaled by -step).  GEMM M = features, N = classes, K = batch;
+// the epilogue reduce-adds each 128 x 128 gradient tile into the owners' rows: no gradient buffer exists.
+void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
+                          int64_t row_stride, int64_t n_classes, int64_t mode) {
+  c10::cuda::CUDAGuard guard(X.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
+  TORCH_CHECK(D.is_cuda() && D.scalar_type() == at::kFloat && D.dim() == 2 && D.stride(1) == 1);
+  const int Bk = (int)X.size(0), F = (int)X.size(1);
+  TORCH_CHECK(Bk % TC_BK == 0, "batch must be a multiple of 32 for the tensor-core backward");
+  TORCH_CHECK(D.size(0) >= Bk && D.stride(0) == row_stride);
+  CUtensorMap tmA, tmD;
+  // A^T tiles come from X [B, F] (features contiguous): box = 32 features x 32 instances, 32B-atom swizzle
+  encode_2d_f32(&tmA, X.data_ptr<float>(), (uint64_t)F, (uint64_t)Bk, (uint64_t)X.stride(0), 32, TC_BK,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  encode_2d_f32(&tmD, D.data_ptr<float>(), (uint64_t)row_stride, (uint64_t)Bk, (uint64_t)D.stride(0), 32, TC_BK,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  auto dmap = at::empty({(int64_t)sizeof(CUtensorMap)}, at::TensorOptions().dtype(at::kByte).device(X.device()));
+  cudaMemcpyAsync(dmap.data_ptr(), &tmD, sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    attr = true;
+  }
+  TableView W;
+  W.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
+  W.num_blocks = (int)block_ptrs.numel();
+  W.rows_per_block = (int)rows_per_block;
+  W.row_stride = (int)row_stride;
+  W.row_dim = (int)n_classes;
+  W.mode = (int)mode;
+  const int N = (int)row_stride;
+  dim3 grid((N + TC_BN - 1) / TC_BN, (F + TC_BM - 1) / TC_BM);
+  dense_gemm_tf32_kernel<true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
+      tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30, 0, TC_BK * 128, 512, 0,
+      1, W);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -161,3 +161,26 @@ def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C):
     assert err < 2e-3 * scale + 1e-3, (err, scale)       # tf32 inputs (10-bit mantissa), fp32 accumulate
     assert float(out[:, C:].abs().max()) == 0.0 if out.shape[1] > C else True
     t.close()
+
+
+@pytest.mark.parametrize("B,F,C", [(64, 256, 100), (500, 2048, 1000)])
+def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C):
+    """Forward GEMM + softmax + backward GEMM whose epilogue reduce-adds into the table rows."""
+    from harmony_b200.models.mlr_dense import DenseMLR
+    t = _table(arena, F, C, max(1, F // 256), True, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 3}})
+    X = torch.randn((B, F), device="cuda") * 0.5
+    y = torch.randint(0, C, (B,), device="cuda", dtype=torch.int32)
+    W0 = t.to_dense().clone()
+    m = DenseMLR(t, C)
+    m.step(X, y, 0.01)
+    torch.cuda.synchronize()
+    logits = X.double() @ W0.double()
+    p = torch.softmax(logits, dim=1)
+    loss_ref = float(-torch.log(p[torch.arange(B), y.long()]).sum())
+    p[torch.arange(B), y.long()] -= 1.0
+    Wref = W0.double() - 0.01 * (X.double().t() @ p)
+    err = float((t.to_dense().double() - Wref).abs().max())
+    upd = float((Wref - W0.double()).abs().max())
+    assert err < 5e-3 * upd + 1e-6, (err, upd)
+    assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 5e-3
+    t.close()
