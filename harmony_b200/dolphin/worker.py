@@ -377,6 +377,8 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.add_custom_metric(em.to_dict())
             self.context.metric_collector.flush()
             epoch += 1
+        if self.use_task_units:
+            self.context.task_units.leave(self.job_id)
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
         summary = self.trainer.summary()
         self.trainer.cleanup()

@@ -512,6 +512,13 @@ class GlobalTaskUnitScheduler:
         for k, waiters in release:
             self._release(k, waiters)
 
+    def on_leave(self, job_id: str, executor_id: str) -> None:
+        """A worker finished its loop: it no longer takes part in the job's unit barriers."""
+        with self._lock:
+            n = self._job_size.get(job_id)
+        if n is not None and n > 1:
+            self.on_job_resize(job_id, n - 1)
+
     def on_wait(self, m: Dict[str, Any]) -> None:
         key = (m["job_id"], m["unit_name"], m["seq"])
         with self._lock:
@@ -819,6 +826,8 @@ class AllocatedTable:
         self.sm.check_state("INITIALIZED")
         if dst not in self.block_manager.get_partition_info():
             raise NotAssociatedError(f"{dst} is not associated with {self.table_id}")
+        if src == dst:
+            return CompletedFuture(MigrationResult(True, "source and destination are the same executor", []))
         blocks = self.block_manager.choose_blocks_to_move(src, num_blocks)
         if not blocks:
             return CompletedFuture(MigrationResult(False, f"There is no block to move in {src}", []))
@@ -1037,6 +1046,8 @@ class ETMaster:
             self.chkp_master.on_load_done(m["op_id"], m.get("num_items"))
         elif t == "TaskUnitWait":
             self.task_units.on_wait(m)
+        elif t == "TaskUnitLeave":
+            self.task_units.on_leave(m["job_id"], m["executor_id"])
         elif t == "TaskletStatus":
             with self._lock:
                 rt = self._tasklets.get((m["executor_id"], m["tasklet_id"]))

@@ -37,14 +37,28 @@ class MigrationExecutor:
         self._sem = threading.Semaphore(MAX_CONCURRENT_MIGRATIONS)
         self._incoming: Dict[Tuple[str, int], Dict[str, Any]] = {}
         self._lock = threading.Lock()
+        # dedicated sender thread (the reference uses 2): pool threads must never block on the
+        # in-flight limit, the acks that release it are served by the same pool
+        import queue
+        self._queue: "queue.Queue" = queue.Queue()
+        self._sender = threading.Thread(target=self._sender_loop, name=f"{executor.executor_id}-mig-sender",
+                                        daemon=True)
+        self._sender.start()
 
     # ---------------- sender side ----------------
     def on_move_init(self, m: Dict[str, Any]) -> None:
         for block_id in m["block_ids"]:
-            self._ex.pool.submit(self._move_one, m["op_id"], m["table_id"], block_id, m["receiver_id"])
+            self._queue.put((m["op_id"], m["table_id"], block_id, m["receiver_id"]))
+
+    def _sender_loop(self) -> None:
+        while True:
+            item = self._queue.get()
+            if item is None:
+                return
+            self._sem.acquire()              # <= MAX_CONCURRENT_MIGRATIONS blocks in flight
+            self._move_one(*item)
 
     def _move_one(self, op_id: int, table_id: str, block_id: int, receiver: str) -> None:
-        self._sem.acquire()
         try:
             comps = self._ex.tables.get_components(table_id)
             if comps.conf.is_mutable:

@@ -167,6 +167,12 @@ class LocalTaskUnitScheduler:
         if ev is not None:
             ev.set()
 
+    def leave(self, job_id: str) -> None:
+        """This executor's worker of `job_id` is done: stop counting it in the global unit barrier."""
+        if self.enabled:
+            self._ex.send_to_driver({"type": "TaskUnitLeave", "job_id": job_id,
+                                     "executor_id": self._ex.executor_id})
+
     def on_task_unit_finished(self, tasklet_id: str, unit: TaskUnitInfo) -> None:
         if not self.enabled or unit.resource == VOID:
             return

@@ -266,6 +266,7 @@ class JobServerDriver:
         self._job_masters: Dict[str, JobMaster] = {}
         self._active_jobs: Set[str] = set()
         self.job_results: Dict[str, Any] = {}
+        self.job_finish_times: Dict[str, float] = {}
         self._job_counter = itertools.count()
         self._lock = threading.Condition()
         self._client_sink = client_sink
@@ -317,6 +318,7 @@ class JobServerDriver:
             self._job_masters.pop(job_id, None)
             self._active_jobs.discard(job_id)
             self.job_results[job_id] = (ok, result)
+            self.job_finish_times[job_id] = time.time()
             self._lock.notify_all()
 
     def running_jobs(self) -> List[str]:

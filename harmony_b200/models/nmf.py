@@ -57,8 +57,11 @@ class NMFDeviceModel:
         self.step, self.lam, self.max_val = float(step), float(lam), float(max_val)
         self.device = table.device
         g = torch.Generator(device=self.device).manual_seed(seed)
-        self.L = (init_lo + (init_hi - init_lo) * torch.rand((n_local_rows, rank), device=self.device, generator=g)
-                  ).clamp_(0.0, max_val)
+        rp = (rank + 3) // 4 * 4                                   # rows padded for 128-bit accesses
+        self._Lbuf = torch.zeros((n_local_rows, rp), dtype=torch.float32, device=self.device)
+        self.L = self._Lbuf[:, :rank]
+        self.L.copy_((init_lo + (init_hi - init_lo) * torch.rand((n_local_rows, rank), device=self.device,
+                                                                 generator=g)).clamp_(0.0, max_val))
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._R = self._G = None
 
@@ -74,7 +77,7 @@ class NMFDeviceModel:
         self._n.table_pull(*self.table.view(), b.ucols, R)            # PULL the batch's columns once
         count_launch()
         G.zero_()
-        self._n.nmf_batch(b.csr_ptr, b.col_slot, b.val, self.L, b.l_row, R, G, self.rank, self.step, self.lam,
+        self._n.nmf_batch(b.csr_ptr, b.col_slot, b.val, self._Lbuf, b.l_row, R, G, self.rank, self.step, self.lam,
                           0.0, self.max_val, self.loss)
         count_launch(2 if self.lam != 0.0 else 1)
         self.table.push(b.ucols, G)                                    # PUSH + clamp(w - step g) at the owners

@@ -35,7 +35,7 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
                  double step, c10::optional<at::Tensor> D, at::Tensor stats);
 void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                        int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
-                       at::Tensor xval, at::Tensor D);
+                       at::Tensor xval, at::Tensor D, bool local_rmw);
 // nmf_ops.cu
 void nmf_batch(at::Tensor csr_ptr, at::Tensor col_slot, at::Tensor val, at::Tensor L, at::Tensor l_row,
                at::Tensor Rst, at::Tensor Gst, int64_t rank, double step, double lambda, double lo, double hi,
@@ -81,7 +81,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("clock_publish", &hb::clock_publish);
   m.def("clock_wait", &hb::clock_wait);
   m.def("mlr_forward", &hb::mlr_forward);
-  m.def("mlr_backward_push", &hb::mlr_backward_push);
+  m.def("mlr_backward_push", &hb::mlr_backward_push, py::arg("block_ptrs"), py::arg("rows_per_block"),
+        py::arg("row_stride"), py::arg("num_classes"), py::arg("mode"), py::arg("uniq_feat"), py::arg("feat_ptr"),
+        py::arg("samp"), py::arg("xval"), py::arg("D"), py::arg("local_rmw") = false);
   m.def("nmf_batch", &hb::nmf_batch);
   m.def("lda_sample", &hb::lda_sample);
   m.def("mlr_partial_forward", &hb::mlr_partial_forward);

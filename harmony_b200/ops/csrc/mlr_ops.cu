@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_fwd_kernel(
   }
 }
 
-template <int VEC>
+// LOCAL_RMW = false : PUSH with 128-bit red.add (several workers may update the same row concurrently)
+// LOCAL_RMW = true  : every row is owned by THIS GPU and touched by exactly one CTA of this launch
+//                     (ship mode: the owner folds all workers' error rows), so a plain vector
+//                     load-add-store replaces the L2 atomic units
+template <int VEC, bool LOCAL_RMW>
 __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
     TableView W, const int* __restrict__ uniq_feat, const int* __restrict__ feat_ptr,
     const int* __restrict__ samp, const float* __restrict__ xval, int U, const float* __restrict__ D,
@@ -193,7 +197,15 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int c0 = 4 * (tid + k * MLR_THREADS);
-      if (c0 < W.row_stride) red_add_f4_sys_hint(dst + c0, acc[k], pol_stream);   // PUSH + `w += delta`
+      if (c0 < W.row_stride) {
+        if (LOCAL_RMW) {
+          float4 w = ld_hint_f4(dst + c0, pol_stream);
+          w.x += acc[k].x; w.y += acc[k].y; w.z += acc[k].z; w.w += acc[k].w;
+          st_hint_f4(dst + c0, w, pol_stream);
+        } else {
+          red_add_f4_sys_hint(dst + c0, acc[k], pol_stream);   // PUSH + `w += delta`
+        }
+      }
     }
   }
 }
@@ -246,7 +258,7 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
 
 void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                        int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
-                       at::Tensor xval, at::Tensor D) {
+                       at::Tensor xval, at::Tensor D, bool local_rmw) {
   c10::cuda::CUDAGuard guard(block_ptrs.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TableView W = mlr_view(block_ptrs, rows_per_block, row_stride, num_classes, mode);
@@ -258,7 +270,10 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
   const int vec = (int)((row_stride / 4 + MLR_THREADS - 1) / MLR_THREADS);
   const int grid = std::min(U, 148 * 8);
 #define LAUNCH_BWD(V)                                                                               \
-  mlr_bwd_push_kernel<V><<<grid, MLR_THREADS, 0, stream>>>(                                         \
+  if (local_rmw) mlr_bwd_push_kernel<V, true><<<grid, MLR_THREADS, 0, stream>>>(                    \
+      W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),                 \
+      xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);                             \
+  else mlr_bwd_push_kernel<V, false><<<grid, MLR_THREADS, 0, stream>>>(                             \
       W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),                 \
       xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);
   if (vec <= 1) { LAUNCH_BWD(1) } else if (vec == 2) { LAUNCH_BWD(2) } else { LAUNCH_BWD(4) }

@@ -153,6 +153,69 @@ __global__ void __launch_bounds__(SHIP_THREADS) mlr_softmax_bcast_kernel(
   if (tid == 0 && stats != nullptr) { atomicAdd(stats + 0, tl); atomicAdd(stats + 1, tc); }
 }
 
+// Warp-per-instance variant for row_stride <= 1024 floats: 8 float4 per lane, warp shuffles only
+// (no block barriers), 8 instances per CTA.  NV = float4 chunks per lane.
+template <int NV>
+__global__ void __launch_bounds__(256) mlr_softmax_bcast_warp_kernel(
+    float* __restrict__ L, int l_stride, const int* __restrict__ labels, int B, int C, float step,
+    const long long* __restrict__ d_ptrs, int n_owners, int rank, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float wloss = 0.f, whit = 0.f;
+  for (int b = wglobal; b < B; b += nwarps) {
+    float* Lrow = L + (size_t)b * l_stride;
+    float4 v[NV];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane + 32 * k);
+      v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (c0 < l_stride) {
+        v[k] = *reinterpret_cast<const float4*>(Lrow + c0);
+        *reinterpret_cast<float4*>(Lrow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 0 >= C) v[k].x = -INFINITY;
+        if (c0 + 1 >= C) v[k].y = -INFINITY;
+        if (c0 + 2 >= C) v[k].z = -INFINITY;
+        if (c0 + 3 >= C) v[k].w = -INFINITY;
+      }
+      tmax = fmaxf(tmax, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    }
+    const float m = warp_max(tmax);
+    float tsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      v[k].x = __expf(v[k].x - m); v[k].y = __expf(v[k].y - m);
+      v[k].z = __expf(v[k].z - m); v[k].w = __expf(v[k].w - m);
+      tsum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float inv = 1.f / warp_sum(tsum);
+    const int y = labels[b];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane + 32 * k);
+      if (c0 >= l_stride) continue;
+      float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      float d[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + q;
+        float p = fminf(fmaxf(e[q] * inv, SHIP_ZERO_THRESHOLD), 1.f - SHIP_ZERO_THRESHOLD);
+        if (c == y) { wloss += -__logf(p); whit += (e[q] >= 1.f) ? 1.f : 0.f; p -= 1.f; }
+        d[q] = (c < C) ? -step * p : 0.f;
+      }
+      const float4 dv = make_float4(d[0], d[1], d[2], d[3]);
+      for (int g = 0; g < n_owners; ++g) {
+        float* dst = reinterpret_cast<float*>(d_ptrs[g]) + ((size_t)rank * B + b) * l_stride + c0;
+        st_stream_f4(dst, dv);
+      }
+    }
+  }
+  wloss = warp_sum(wloss);
+  whit = warp_sum(whit);
+  if (lane == 0 && stats != nullptr && (wloss != 0.f || whit != 0.f)) { atomicAdd(stats + 0, wloss); atomicAdd(stats + 1, whit); }
+}
+
 static TableView ship_view(const at::Tensor& block_ptrs, int64_t rows_per_block, int64_t row_stride,
                            int64_t row_dim, int64_t mode) {
   TableView v;
@@ -193,6 +256,19 @@ void mlr_softmax_bcast(at::Tensor L, at::Tensor labels, int64_t num_classes, dou
   if (B == 0) return;
   const int stride = (int)L.stride(0);
   TORCH_CHECK(stride % 32 == 0 && stride <= 4096 && L.stride(1) == 1);
+  if (stride <= 1024) {       // warp-per-instance fast path
+    const int nv = (stride / 4 + 31) / 32;
+    const int gridw = std::min((B + 7) / 8, 148 * 8);
+#define LAUNCH_SW(NVv)                                                                                  \
+    mlr_softmax_bcast_warp_kernel<NVv><<<gridw, 256, 0, stream>>>(                                      \
+        L.data_ptr<float>(), stride, labels.data_ptr<int>(), B, (int)num_classes, (float)step,          \
+        reinterpret_cast<const long long*>(d_ptrs.data_ptr<int64_t>()), (int)d_ptrs.numel(), (int)rank, \
+        stats.data_ptr<float>());
+    if (nv <= 1) { LAUNCH_SW(1) } else if (nv <= 2) { LAUNCH_SW(2) } else if (nv <= 4) { LAUNCH_SW(4) } else { LAUNCH_SW(8) }
+#undef LAUNCH_SW
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
   const int vec = (stride / 4 + SHIP_THREADS - 1) / SHIP_THREADS;
   const int grid = std::min(B, 148 * 16);
 #define LAUNCH_SB(V)                                                                                  \
