@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--scheduler", default="SchedulerImpl")
     ap.add_argument("--scale", type=float, default=1.0, help="dataset size multiplier")
     ap.add_argument("--epochs", type=int, default=6)
+    ap.add_argument("--repartition_after_s", type=float, default=0.2)
     a = ap.parse_args()
     import numpy as np
     from helpers import write_lda_sample, write_mlr_sample, write_nmf_sample
@@ -68,9 +69,10 @@ def main():
     def repartition():
         m = js.et_master
         deadline = time.time() + 120
-        while time.time() < deadline and not m.has_table("model_table0"):
-            time.sleep(0.05)
-        time.sleep(1.0)
+        while time.time() < deadline and not (m.has_table("model_table0") and
+                                              m.get_table("model_table0").sm.current_state == "INITIALIZED"):
+            time.sleep(0.02)
+        time.sleep(a.repartition_after_s)
         if not m.has_table("model_table0") or a.executors < 2:
             return
         table = m.get_table("model_table0")

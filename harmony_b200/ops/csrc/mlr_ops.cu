@@ -163,8 +163,13 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
     const int beg = feat_ptr[u], end = feat_ptr[u + 1];
     float* dst = row_ptr<float>(W, (long long)uniq_feat[u]);
     float4 acc[VEC];
+    float4 wrow[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < VEC; ++k) {
+      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // LOCAL_RMW: issue the read of the model row FIRST so its DRAM latency overlaps the D gathers
+      if (LOCAL_RMW) wrow[k] = ld_row_hint_f4(dst, 4 * (tid + k * MLR_THREADS), W.row_stride, pol_stream);
+    }
     int j = beg;
     for (; j + 4 <= end; j += 4) {
       float4 d[4][VEC];
@@ -199,13 +204,67 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
       const int c0 = 4 * (tid + k * MLR_THREADS);
       if (c0 < W.row_stride) {
         if (LOCAL_RMW) {
-          float4 w = ld_hint_f4(dst + c0, pol_stream);
+          float4 w = wrow[k];
           w.x += acc[k].x; w.y += acc[k].y; w.z += acc[k].z; w.w += acc[k].w;
           st_hint_f4(dst + c0, w, pol_stream);
         } else {
           red_add_f4_sys_hint(dst + c0, acc[k], pol_stream);   // PUSH + `w += delta`
         }
       }
+    }
+  }
+}
+
+// Warp-per-feature variant (row_stride <= 1024 floats): every warp owns one distinct feature, 8 x
+// 128-bit chunks per lane, no block barriers => ~3x more rows in flight per SM than the CTA-per-feature
+// kernel, which is what this latency-bound gather -> reduce-add chain needs.
+template <int NV>
+__global__ void __launch_bounds__(256) mlr_bwd_push_warp_kernel(
+    TableView W, const int* __restrict__ uniq_feat, const int* __restrict__ feat_ptr,
+    const int* __restrict__ samp, const float* __restrict__ xval, int U, const float* __restrict__ D,
+    int d_stride) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint64_t pol_keep = l2_policy_evict_last();
+  const uint64_t pol_stream = l2_policy_evict_first();
+  for (int u = wglobal; u < U; u += nwarps) {
+    const int beg = feat_ptr[u], end = feat_ptr[u + 1];
+    float* dst = row_ptr<float>(W, (long long)uniq_feat[u]);
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = beg;
+    for (; j + 2 <= end; j += 2) {
+      const float* d0 = D + (size_t)samp[j] * d_stride;
+      const float* d1 = D + (size_t)samp[j + 1] * d_stride;
+      const float x0 = xval[j], x1 = xval[j + 1];
+      float4 a[NV], b[NV];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        a[k] = ld_row_hint_f4(d0, 4 * (lane + 32 * k), d_stride, pol_keep);
+        b[k] = ld_row_hint_f4(d1, 4 * (lane + 32 * k), d_stride, pol_keep);
+      }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        acc[k].x = fmaf(x0, a[k].x, fmaf(x1, b[k].x, acc[k].x)); acc[k].y = fmaf(x0, a[k].y, fmaf(x1, b[k].y, acc[k].y));
+        acc[k].z = fmaf(x0, a[k].z, fmaf(x1, b[k].z, acc[k].z)); acc[k].w = fmaf(x0, a[k].w, fmaf(x1, b[k].w, acc[k].w));
+      }
+    }
+    if (j < end) {
+      const float* d0 = D + (size_t)samp[j] * d_stride;
+      const float x0 = xval[j];
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float4 a = ld_row_hint_f4(d0, 4 * (lane + 32 * k), d_stride, pol_keep);
+        acc[k].x = fmaf(x0, a.x, acc[k].x); acc[k].y = fmaf(x0, a.y, acc[k].y);
+        acc[k].z = fmaf(x0, a.z, acc[k].z); acc[k].w = fmaf(x0, a.w, acc[k].w);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane + 32 * k);
+      if (c0 < W.row_stride) red_add_f4_sys_hint(dst + c0, acc[k], pol_stream);
     }
   }
 }
@@ -267,6 +326,18 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
   TORCH_CHECK(uniq_feat.scalar_type() == at::kInt && feat_ptr.scalar_type() == at::kInt &&
               samp.scalar_type() == at::kInt && xval.scalar_type() == at::kFloat);
   TORCH_CHECK(D.scalar_type() == at::kFloat && D.stride(0) == row_stride && D.stride(1) == 1);
+  if (!local_rmw && row_stride <= 1024) {     // warp-per-feature fast path
+    const int nv = (int)((row_stride / 4 + 31) / 32);
+    const int gridw = std::min((U + 7) / 8, 148 * 16);
+#define LAUNCH_BW(NVv)                                                                             \
+    mlr_bwd_push_warp_kernel<NVv><<<gridw, 256, 0, stream>>>(                                      \
+        W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),               \
+        xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);
+    if (nv <= 1) { LAUNCH_BW(1) } else if (nv <= 2) { LAUNCH_BW(2) } else if (nv <= 4) { LAUNCH_BW(4) } else { LAUNCH_BW(8) }
+#undef LAUNCH_BW
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
   const int vec = (int)((row_stride / 4 + MLR_THREADS - 1) / MLR_THREADS);
   const int grid = std::min(U, 148 * 8);
 #define LAUNCH_BWD(V)                                                                               \
