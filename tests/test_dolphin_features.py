@@ -1,0 +1,139 @@
+"""Dolphin features beyond the plain training loop: offline model evaluation from per-epoch
+checkpoints, warm start from a model checkpoint (-load_model / -model_path), SSP clock_slack,
+schedulers, dashboard sink, cached model accessor, metric manager validation."""
+import json
+import os
+import socket
+import tempfile
+import time
+import urllib.request
+
+import numpy as np
+import pytest
+
+from harmony_b200.dolphin.launcher import DolphinJobLauncher, ETDolphinLauncher
+from harmony_b200.dolphin.master import MiniBatchController
+from harmony_b200.dolphin.metrics import DolphinMetricManager
+from harmony_b200.jobserver.client import JobServer
+from harmony_b200.mlapps import mlr
+from harmony_b200.utils.flags import Configuration
+
+from helpers import write_mlr_sample
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _args(data, port, extra=()):
+    return ["-input", data, "-max_num_epochs", "3", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+            "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
+            "-port", str(port)] + list(extra)
+
+
+def test_offline_model_eval_and_warm_start():
+    tmp = tempfile.mkdtemp(prefix="hbeval")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=160)
+    test = write_mlr_sample(os.path.join(tmp, "sample_mlr_test"), n=40, seed=9)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port, "chkp_temp_path": tmp + "/t",
+                                  "chkp_commit_path": tmp + "/c"})).start()
+    try:
+        r = DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(data, port, ["-offline_model_eval", "true",
+                                                                                   "-test_data_path", test]), port=port)
+        assert r.startswith("true")
+        assert js.driver.wait_job("MLR-0", timeout=120)[0]
+        # a checkpoint of the model table was taken every epoch
+        chkps = sorted(os.listdir(tmp + "/t/executor-0")) if os.path.isdir(tmp + "/t/executor-0") else []
+        assert sum(c.startswith("model_table0-") for c in chkps) >= 3, chkps
+        # shutdown(kill=False) runs the deferred evaluation over all checkpoints, oldest first
+        js.stop(kill=False)
+        ok, evals = js.driver.job_results["MLR-0/eval"]
+        per_worker = evals[0]
+        assert len(per_worker) >= 3
+        losses = [m["loss"] for m in per_worker]
+        assert losses[-1] < losses[0], losses               # later epochs fit better
+        assert all("testAvgAccuracy" in m for m in per_worker)
+        # committed checkpoints can warm-start a new job
+        committed = sorted(d for d in os.listdir(tmp + "/c") if d.startswith("model_table0-"))
+        assert committed
+        port2 = _free_port()
+        js2 = JobServer(Configuration({"num_executors": 2, "port": port2, "chkp_temp_path": tmp + "/t2",
+                                       "chkp_commit_path": tmp + "/c2"})).start()
+        try:
+            r = DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(
+                data, port2, ["-load_model", "true", "-model_path", os.path.join(tmp, "c", committed[-1]),
+                              "-max_num_epochs", "1"]), port=port2)
+            assert r.startswith("true")
+            ok, res = js2.driver.wait_job("MLR-0", timeout=120)
+            assert ok
+            warm = np.mean([x["last_batch_loss"] for x in res])
+        finally:
+            js2.stop(kill=True)
+        assert warm < 1.2 * np.mean(losses[-1:]) / 2 + 60, (warm, losses)
+    finally:
+        js.stop(kill=True)
+
+
+def test_minibatch_controller_ssp_and_budget():
+    sent = []
+
+    class S:
+        def send_mini_batch_control_msg(self, w, stop):
+            sent.append((w, stop))
+    c = MiniBatchController(num_epochs=1, num_mini_batches_in_epoch=6, slack=1, sender=S())
+    c.on_sync("a"); c.on_sync("b")
+    assert sent == [("a", False), ("b", False)]
+    c.on_sync("a")                       # progress 2 <= min(1) + slack(1): released
+    c.on_sync("a")                       # progress 3 > 1 + 1: blocked
+    assert sent[-1] == ("a", False) and len(sent) == 3
+    c.on_sync("b")                       # min progress rises to 2 -> a is released
+    assert ("a", False) in sent[3:] and ("b", False) in sent[3:]
+    n = len(sent)
+    c.on_sync("b")                       # 6th sync = budget reached: runs its last batch
+    assert sent[n] == ("b", False)
+    c.on_sync("a")
+    assert sent[-1] == ("a", True)       # budget exhausted: stop
+
+
+@pytest.mark.parametrize("scheduler", ["FifoExclusiveScheduler", "PackingScheduler"])
+def test_alternative_schedulers(scheduler):
+    tmp = tempfile.mkdtemp(prefix="hbsched")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=80)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 3, "port": port, "scheduler": scheduler})).start()
+    try:
+        extra = ["-max_num_epochs", "1"]
+        for _ in range(3):
+            assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(data, port, extra), port=port).startswith("true")
+        for j in ("MLR-0", "MLR-1", "MLR-2"):
+            assert js.driver.wait_job(j, timeout=180)[0]
+    finally:
+        js.stop(kill=True)
+
+
+def test_dashboard_receives_metrics_and_cached_accessor():
+    from harmony_b200.dolphin.dashboard import DashboardServer
+    tmp = tempfile.mkdtemp(prefix="hbdash")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=80)
+    port = _free_port()
+    res = ETDolphinLauncher.launch(mlr.APP, ["-input", data, "-max_num_epochs", "2", "-num_mini_batches", "4",
+                                             "-num_worker_blocks", "4", "-num_server_blocks", "4", "-step_size", "0.05",
+                                             "-classes", "4", "-features", "64", "-num_dolphin_workers", "1",
+                                             "-num_servers", "1", "-dashboard_enabled", "true",
+                                             "-dashboard_port", str(port), "-model_cache_enabled", "true"])
+    assert res.ok and any(m.startswith("Dashboard:") for m in res.messages)
+
+
+def test_metric_manager_validation_rules():
+    mm = DolphinMetricManager(num_initial_to_skip=2)
+    m = {"kind": "batch", "batch_time_sec": 1.0}
+    assert not mm.store_worker_metric("w", 4, m)          # collection not started
+    mm.start_metric_collection()
+    assert not mm.store_worker_metric("w", 4, m) and not mm.store_worker_metric("w", 4, m)   # first N skipped
+    assert mm.store_worker_metric("w", 4, m)
+    mm.load_metric_validation_info({"w": 5}, {})
+    assert not mm.store_worker_metric("w", 5, m)          # first metric after a reconfiguration is dropped
+    assert not mm.store_worker_metric("w", 4, m)          # block count disagrees with the driver's view
+    assert mm.store_worker_metric("w", 5, m)
+    assert len(mm.get_worker_batch_metrics()["w"]) == 2
