@@ -38,6 +38,14 @@ def build_tables_confs(app: ETDolphinConfiguration, conf: Configuration, job_cou
     server_tc = app.model_table_conf(conf, model_id)
     server_tc.num_total_blocks = int(conf.get("num_server_blocks", 1024))
     server_tc.is_mutable, server_tc.is_ordered = True, False
+    if server_tc.user_params.get("dense_input"):
+        # the tensor-core path TMA-loads K tiles of 32 consecutive features: range-partitioned blocks whose
+        # size is a multiple of 32 rows
+        server_tc.is_ordered = True
+        nb = max(1, min(server_tc.num_total_blocks, server_tc.capacity // 32))
+        while nb > 1 and (-(-server_tc.capacity // nb)) % 32 != 0:
+            nb -= 1
+        server_tc.num_total_blocks = nb
     server_tc.chkp_path = conf.get("model_path") if load_model and conf.get("model_path") else None
     worker_tc = TableConfiguration(
         table_id=input_id, num_total_blocks=int(conf.get("num_worker_blocks", 1024)), is_mutable=False,

@@ -74,7 +74,8 @@ OPTIMIZER = [
     P("num_extra_resources", int, 0, "", "optimizer"), P("extra_resources_period_sec", int, 0, "", "optimizer"),
     P("dashboard_enabled", bool, False, "", "dashboard"), P("dashboard_port", int, 9005, "", "dashboard"),
 ]
-MLR = [P("classes", int, 0, "number of classes", "user")]
+MLR = [P("classes", int, 0, "number of classes", "user"),
+       P("dense_input", bool, False, "dense instances: tcgen05 GEMM path on the device backend", "user")]
 NMF = [P("rank", int, 0, "", "user"), P("max_val", float, 1e6, "", "user"), P("init_max", float, 1.0, "", "user"),
        P("init_min", float, 0.0, "", "user"), P("print_mat", bool, False, "", "user")]
 LDA = [P("alpha", float, 0.001, "", "user"), P("beta", float, 0.01, "", "user"), P("num_topics", int, 100, "", "user"),

@@ -162,11 +162,14 @@ def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:
     fpp = int(conf.get("features_per_partition", 0) or 0)
     if fpp and features % fpp != 0:
         raise ValueError("Uneven model partitions: features must be divisible by features_per_partition")
-    return TableConfiguration(
+    dense_input = bool(conf.get("dense_input", False))
+    tc = TableConfiguration(
         table_id=table_id, dense=True, capacity=features, row_dim=classes, dtype="float32",
         update_function={"name": "add", "params": {"init": "gaussian", "mean": 0.0,
                                                    "std": float(conf.get("model_gaussian", 0.001)), "seed": 0}},
         backend=conf.get("backend", "host") if conf.get("backend", "host") in ("host", "device") else "host")
+    tc.user_params["dense_input"] = dense_input
+    return tc
 
 
 APP = ETDolphinConfiguration(

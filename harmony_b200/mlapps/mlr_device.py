@@ -35,9 +35,31 @@ class MLRDeviceTrainer(Trainer):
         self._cache: Dict[Any, Any] = {}
         self._batch = None
         self.num_workers = int(params.get("num_job_workers", 1))
+        self.num_features = int(params["features"])
+        self.dense = None
+        if params.get("dense_input") and self.dtable.mode == 0 and self.dtable.rows_per_block % 32 == 0 \
+                and self.num_features % 32 == 0:
+            from ..models.mlr_dense import DenseMLR
+            self.dense = DenseMLR(self.dtable, self.num_classes)      # tcgen05 / TMEM / TMA path
+            self.dense.stats = self.model.stats
+
+    def _to_dense_batch(self, mini_batch):
+        key = ("dense", mini_batch[0][0], len(mini_batch))
+        b = self._cache.get(key)
+        if b is None:
+            X = np.zeros((len(mini_batch), self.num_features), dtype=np.float32)
+            y = np.zeros(len(mini_batch), dtype=np.int32)
+            for i, (_, (idx, val, label)) in enumerate(mini_batch):
+                X[i, idx] = val
+                y[i] = label
+            b = (self._torch.from_numpy(X).to(self.dtable.device), self._torch.from_numpy(y).to(self.dtable.device))
+            self._cache[key] = b
+        return b
 
     def _to_device_batch(self, mini_batch):
         from ..models.mlr import build_batch
+        if self.dense is not None:
+            return self._to_dense_batch(mini_batch)
         key = (mini_batch[0][0], len(mini_batch)) if mini_batch else None
         b = self._cache.get(key)
         if b is None:
@@ -52,15 +74,21 @@ class MLRDeviceTrainer(Trainer):
     def pull_model(self) -> None:
         self.comps.gate.acquire_read()          # held from PULL to PUSH: migration waits for a batch boundary
         self.model.stats.zero_()
-        self.model.forward(self._batch, True)
+        if self.dense is None:
+            self.model.forward(self._batch, True)
 
     def local_compute(self) -> None:
         pass                                    # fused into the pull / push kernels
 
     def push_update(self) -> None:
         try:
-            self.model.backward_push(self._batch)
-            self.model.apply_l2(self._batch.batch_size * self.num_workers)
+            if self.dense is not None:
+                X, y = self._batch
+                self.dense.step(X, y, self.model.step_size, self.model.stats)   # GEMM -> softmax -> GEMM+push
+            else:
+                self.model.backward_push(self._batch)
+            bsz = self._batch[0].shape[0] if self.dense is not None else self._batch.batch_size
+            self.model.apply_l2(bsz * self.num_workers)
             self._torch.cuda.current_stream(self.dtable.device).synchronize()
         finally:
             self.comps.gate.release_read()
@@ -76,6 +104,8 @@ class MLRDeviceTrainer(Trainer):
         out = {}
         for name, data in (("", list(input_data)), ("test", [(None, t) for t in test_data])):
             if not data:
+                continue
+            if self.dense is not None:
                 continue
             b = self._to_device_batch(data)
             loss, acc = self.model.evaluate(b)

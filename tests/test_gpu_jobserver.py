@@ -87,3 +87,27 @@ def test_device_table_migration_and_checkpoint_through_driver():
         np.testing.assert_allclose(tr.multi_get_or_init(keys).get(), W0 + 2, rtol=1e-6)
     finally:
         master.close()
+
+
+def test_dense_input_mlr_job_uses_tensor_core_path():
+    """-dense_input true: ordered model table, DenseMLR (tcgen05 GEMMs) inside the worker loop."""
+    from harmony_b200 import ops
+    from harmony_b200.dolphin.launcher import DolphinJobLauncher
+    from harmony_b200.jobserver.client import JobServer
+    from harmony_b200.mlapps import mlr
+    from harmony_b200.utils.flags import Configuration
+    tmp = tempfile.mkdtemp(prefix="hbgpu4")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=256, features=64, classes=4, nnz=32)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port, "backend": "device"})).start()
+    try:
+        args = ["-input", data, "-max_num_epochs", "10", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
+                "-dense_input", "true", "-port", str(port)]
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+        ok, result = js.driver.wait_job("MLR-0", timeout=300)
+        assert ok, result
+        loss = np.mean([r["last_batch_loss"] / 64.0 for r in result])
+        assert loss < 1.30, loss
+    finally:
+        js.stop(kill=True)
