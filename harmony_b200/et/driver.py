@@ -1017,6 +1017,7 @@ class ETMaster:
         self.metrics = MetricManager(self)
         self.custom_handlers: Dict[str, Callable[[Dict[str, Any]], None]] = {}   # msg type -> handler
         self.centcomm_handlers: Dict[str, Callable[[Dict[str, Any]], None]] = {}
+        self.failure_listeners: List[Callable[[str, str], None]] = []
         self.chkp_temp_path, self.chkp_commit_path = chkp_temp_path, chkp_commit_path
         transport.register(driver_id, self.on_message)
 
@@ -1117,6 +1118,34 @@ class ETMaster:
         if ae is not None:
             ae.on_closed()
         self.launcher.terminate(executor_id)
+
+    def on_executor_failed(self, executor_id: str, reason: str = "") -> None:
+        """EvaluatorFailedHandler (driver/impl/EvaluatorFailedHandler.java:39-42): the executor is
+        unregistered; tasklets it was running are reported as Failed so their jobs fail instead of
+        hanging (the reference throws in the driver, TODO #677)."""
+        LOG.error("executor %s failed: %s", executor_id, reason)
+        with self._lock:
+            ae = self.executors.pop(executor_id, None)
+            rts = [rt for (eid, _), rt in self._tasklets.items() if eid == executor_id and not rt.is_done()]
+        for rt in rts:
+            try:
+                rt.sm.set_state("FAILED")
+            except Exception:  # noqa: BLE001
+                pass
+            rt._result.on_completed(TaskletResult(rt.tasklet_id, executor_id, "Failed", None,
+                                                  f"executor {executor_id} failed: {reason}"))
+        self.chkp_master.on_executor_closed(executor_id)
+        if ae is not None:
+            ae.on_closed()
+        try:
+            self.launcher.terminate(executor_id)        # reclaim whatever is left of it
+        except Exception:  # noqa: BLE001
+            LOG.exception("terminate of failed executor %s", executor_id)
+        for cb in list(self.failure_listeners):
+            try:
+                cb(executor_id, reason)
+            except Exception:  # noqa: BLE001
+                LOG.exception("failure listener failed")
 
     def get_executor(self, executor_id: str) -> AllocatedExecutor:
         with self._lock:

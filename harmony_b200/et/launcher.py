@@ -72,8 +72,17 @@ class SubprocessLauncher(ExecutorLauncher):
         cmd = [sys.executable, "-m", "harmony_b200.et.executor_main", "--id", executor_id,
                "--driver", f"{self.name_server[0]}:{self.name_server[1]}", "--driver-id", master.driver_id,
                "--backend", self.backend, "--ordinal", str(ordinal), "--conf", json.dumps(conf.to_dict())]
-        self._procs[executor_id] = subprocess.Popen(cmd, env=env)
-        # the child registers itself with an ExecutorRegister message
+        proc = subprocess.Popen(cmd, env=env)
+        self._procs[executor_id] = proc
+        # the child registers itself with an ExecutorRegister message; a monitor thread turns an
+        # unexpected exit into an executor-failed event (failure detection)
+
+        def monitor():
+            rc = proc.wait()
+            if executor_id in self._procs and rc != 0:
+                self._procs.pop(executor_id, None)
+                master.on_executor_failed(executor_id, f"process exited with code {rc}")
+        threading.Thread(target=monitor, name=f"monitor-{executor_id}", daemon=True).start()
 
     def terminate(self, executor_id: str) -> None:
         p = self._procs.pop(executor_id, None)

@@ -232,3 +232,43 @@ def test_fallback_reroutes_after_stale_ownership(cluster):
     comps.ownership._owners[block] = stale if owner != ex0.executor_id else comps.ownership._owners[block]
     if owner != ex0.executor_id:
         assert t0.get(1).get(5) == 41
+
+
+def test_migration_manager_concurrent_bidirectional_moves_and_late_subscriber(cluster):
+    """Reference MigrationManagerTest: concurrent moves in both directions conserve the blocks and
+    every subscriber (incl. one added while moves are in flight) converges to the driver's truth."""
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id="mm", num_total_blocks=24, update_function="add", chunk_size=3)
+    master.create_table(conf, execs[:2]).get(10)
+    table = master.get_table("mm")
+    t0 = launcher.executors[execs[0].id].tables.get_table("mm")
+    for k in range(240):
+        t0.put(k, k).get(5)
+    f1 = table.move_blocks(execs[0].id, execs[1].id, 5)
+    f2 = table.move_blocks(execs[1].id, execs[0].id, 3)
+    sub = table.subscribe([execs[2]])
+    r1, r2 = f1.get(30), f2.get(30)
+    sub.get(30)
+    assert r1.is_completed and r2.is_completed
+    info = table.get_partition_info()
+    assert len(info[execs[0].id]) + len(info[execs[1].id]) == 24
+    assert len(info[execs[0].id]) == 12 - 5 + 3 and table.block_manager.num_moving() == 0
+    time.sleep(0.3)
+    truth = table.get_ownership_status()
+    for ex in launcher.executors.values():
+        assert ex.tables.get_components("mm").ownership.owners() == truth
+    t2 = launcher.executors[execs[2].id].tables.get_table("mm")
+    assert t2.multi_get(list(range(240))).get(10) == list(range(240))
+
+
+def test_executor_failure_fails_running_tasklets(cluster):
+    from harmony_b200.et.config import TaskletConfiguration
+    master, execs, launcher = cluster
+    seen = []
+    master.failure_listeners.append(lambda e, r: seen.append(e))
+    rt = execs[0].submit_tasklet(TaskletConfiguration("idle", "harmony_b200.dolphin.worker:ServerTasklet", None, {}))
+    time.sleep(0.2)
+    master.on_executor_failed(execs[0].id, "injected fault")
+    res = rt.get_task_result(timeout=5)
+    assert not res.is_success and "injected fault" in res.error
+    assert seen == [execs[0].id] and execs[0].id not in master.executors

@@ -111,3 +111,28 @@ def test_dense_input_mlr_job_uses_tensor_core_path():
         assert loss < 1.30, loss
     finally:
         js.stop(kill=True)
+
+
+def test_device_backend_with_executor_processes():
+    """One OS process per executor on the device backend: slab locations travel as CUDA-IPC handles
+    inside TableInitAck / TablePeerMap, kernels in one process reduce into another process' HBM."""
+    import time
+    from harmony_b200.dolphin.launcher import DolphinJobLauncher
+    from harmony_b200.jobserver.client import JobServer
+    from harmony_b200.mlapps import mlr
+    from harmony_b200.utils.flags import Configuration
+    tmp = tempfile.mkdtemp(prefix="hbgpu5")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=256, features=64, classes=4)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port, "backend": "device", "executor_mode": "process",
+                                  "chkp_temp_path": tmp + "/t", "chkp_commit_path": tmp + "/c"})).start()
+    try:
+        args = ["-input", data, "-max_num_epochs", "8", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64", "-port", str(port)]
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+        ok, result = js.driver.wait_job("MLR-0", timeout=600)
+        assert ok, result
+        loss = np.mean([r["last_batch_loss"] / 64.0 for r in result])
+        assert loss < 1.30, loss
+    finally:
+        js.stop(kill=True)

@@ -1,0 +1,89 @@
+"""Utility layer (reference: utils/src/test DAGImplTest, LongRangeUtilsTest; StateMachine; Tang flags)."""
+import json
+
+import numpy as np
+import pytest
+
+from harmony_b200.utils import DAG, Configuration, FlagError, IllegalStateError, Param, ParamRegistry, StateMachine
+from harmony_b200.utils import trace
+from harmony_b200.utils.codecs import (DenseVectorCodec, IntegerCodec, LongCodec, SerializableCodec, SparseArrayCodec,
+                                       SparseVectorCodec)
+from harmony_b200.utils.misc import generate_dense_long_ranges, get_num_units, murmur3_32
+
+
+def test_state_machine_transitions():
+    sm = (StateMachine.new_builder().add_state("A").add_state("B").add_state("C").add_transition("A", "B")
+          .add_transition("B", "C").set_initial_state("A").build())
+    sm.check_state("A")
+    with pytest.raises(IllegalStateError):
+        sm.set_state("C")
+    assert sm.compare_and_set_state("A", "B") and not sm.compare_and_set_state("A", "B")
+    sm.set_state("C")
+    with pytest.raises(IllegalStateError):
+        sm.check_state("A")
+    with pytest.raises(ValueError):
+        StateMachine.new_builder().add_state("A").add_state("A")
+
+
+def test_dag_roots_degrees_cycles():
+    d = DAG()
+    for v in "abcd":
+        assert d.add_vertex(v)
+    assert not d.add_vertex("a")
+    d.add_edge("a", "b"); d.add_edge("a", "c"); d.add_edge("b", "d"); d.add_edge("c", "d")
+    assert d.get_root_vertices() == {"a"} and d.get_in_degree("d") == 2 and d.is_adjacent("a", "b")
+    with pytest.raises(ValueError):
+        d.add_edge("d", "a")
+    d.remove_vertex("a")
+    assert d.get_root_vertices() == {"b", "c"} and d.get_num_vertices() == 3
+    d.remove_edge("b", "d")
+    assert d.get_in_degree("d") == 1
+    assert set(json.loads(d.to_json())["vertices"]) == {"b", "c", "d"}
+
+
+def test_flags_parse_merge_serialize():
+    reg = ParamRegistry([Param("num_executors", int, 1, group="driver"), Param("local", bool, True, group="client"),
+                         Param("step_size", float, None, group="user", required=False), Param("input", str, None)])
+    conf, unknown = reg.parse(["-num_executors", "5", "-local", "false", "-step_size", "0.1", "-foo", "bar"],
+                              allow_unknown=True)
+    assert conf["num_executors"] == 5 and conf["local"] is False and conf["step_size"] == 0.1 and unknown == ["-foo", "bar"]
+    with pytest.raises(FlagError):
+        reg.parse(["-foo", "bar"])
+    with pytest.raises(FlagError):
+        reg.parse(["-num_executors"])
+    back = Configuration.deserialize(conf.serialize())
+    assert dict(back) == dict(conf)
+    assert dict(conf.extract(reg.by_group("driver"))) == {"num_executors": 5}
+    assert conf.merge({"x": 1}).with_values(y=2)["y"] == 2
+
+
+def test_long_ranges_and_murmur():
+    r = generate_dense_long_ranges([5, 1, 2, 3, 9, 10])
+    assert r == [(1, 3), (5, 5), (9, 10)] and get_num_units(r) == 6
+    assert murmur3_32(b"") == 0 and murmur3_32(b"hello") == 0x248bfa47 and murmur3_32(b"hello", 1) != murmur3_32(b"hello")
+
+
+def test_codecs_roundtrip():
+    assert IntegerCodec().decode(IntegerCodec().encode(-7)) == -7
+    assert LongCodec().decode(LongCodec().encode(2 ** 40)) == 2 ** 40
+    v = np.arange(5, dtype=np.float32) * 0.5
+    np.testing.assert_array_equal(DenseVectorCodec().decode(DenseVectorCodec().encode(v)), v)
+    n, i, x = SparseVectorCodec().decode(SparseVectorCodec().encode((100, [3, 50], [1.5, -2.0])))
+    assert n == 100 and list(i) == [3, 50] and list(x) == [1.5, -2.0]
+    row = np.array([0, 4, 0, 2, 2], dtype=np.int32)
+    np.testing.assert_array_equal(SparseArrayCodec(4).decode(SparseArrayCodec(4).encode(row)), row)
+    assert SerializableCodec().decode(SerializableCodec().encode({"a": [1, 2]})) == {"a": [1, 2]}
+
+
+def test_trace_spans_dump(tmp_path):
+    trace.enable(True); trace.clear()
+    with trace.span("PULL", job="j"):
+        with trace.span("COMP"):
+            pass
+    p = tmp_path / "t.json"
+    assert trace.dump(str(p)) == 2
+    ev = json.loads(p.read_text())["traceEvents"]
+    assert {e["name"] for e in ev} == {"PULL", "COMP"} and all(e["ph"] == "X" for e in ev)
+    trace.enable(False)
+    t = trace.Tracer(); t.start_timer(); t.record_time(2)
+    assert t.total_elapsed_time() >= 0 and t.avg_time_per_elem() >= 0
