@@ -302,10 +302,36 @@ class ETTaskRunner:
             for s in deleted_servers:
                 self.server_tasklets.pop(s, None)
 
-    def wait_and_get_results(self, timeout: Optional[float] = None):
+    def wait_and_get_results(self, timeout: Optional[float] = None, on_failure=None):
+        """Waits for every worker; when one FAILS the others are aborted (they would otherwise wait
+        for it at a barrier forever) and the job fails fast."""
         with self._lock:
             workers = list(self.worker_tasklets.values())
-        results = [w.get_task_result(timeout) for w in workers]
+        failed = threading.Event()
+        for w in workers:
+            w._result.add_listener(lambda r: failed.set() if (r is not None and not r.is_success) else None)
+        deadline = None if timeout is None else time.time() + timeout
+        while not all(w.is_done() for w in workers):
+            if failed.wait(0.05):
+                if on_failure is not None:
+                    on_failure()
+                for w in workers:
+                    if not w.is_done():
+                        try:
+                            w.stop()
+                        except Exception:  # noqa: BLE001
+                            pass
+                break
+            if deadline is not None and time.time() > deadline:
+                raise TimeoutError("workers did not finish in time")
+        grace = 15.0 if failed.is_set() else timeout
+        results = []
+        for w in workers:
+            try:
+                results.append(w.get_task_result(grace))
+            except TimeoutError:
+                from ..et.driver import TaskletResult
+                results.append(TaskletResult(w.tasklet_id, w.executor_id, "Failed", None, "aborted after a peer failed"))
         with self._lock:
             servers = list(self.server_tasklets.values())
         for s in servers:
@@ -407,7 +433,16 @@ class DolphinMaster:
             self.task_runner.submit_server(ex)
         for ex in workers:
             self.task_runner.submit_worker(ex, self.worker_params())
-        results = self.task_runner.wait_and_get_results(timeout=float(p.get("job_timeout_sec", 3600)))
+        def release_all():       # unblock every barrier a surviving worker may be parked in
+            for ex in workers:
+                try:
+                    self.sender.send_mini_batch_control_msg(ex.id, True)
+                    self.sender.send_release_msg(ex.id)
+                    self.sender.send_release_msg(ex.id)
+                except Exception:  # noqa: BLE001
+                    pass
+        results = self.task_runner.wait_and_get_results(timeout=float(p.get("job_timeout_sec", 3600)),
+                                                        on_failure=release_all)
         for ex in workers:
             try:
                 self._m.metrics.stop_metric_collection(ex.id)

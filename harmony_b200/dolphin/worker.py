@@ -318,6 +318,10 @@ class WorkerTasklet(Tasklet):
         sched = self.context.task_units
         if self.use_task_units:
             sched.wait_schedule(self.context.tasklet_id, info)
+        if self._abort.is_set():
+            if self.use_task_units:
+                sched.on_task_unit_finished(self.context.tasklet_id, info)
+            raise RuntimeError("tasklet aborted")
         t0 = time.perf_counter()
         try:
             with trace.span(name, job=self.job_id):
@@ -387,6 +391,9 @@ class WorkerTasklet(Tasklet):
     def close(self) -> None:
         self._abort.set()
         self.mini_batch_barrier.on_control_msg(True)
+        self.global_barrier.on_release_msg()
+        self.global_barrier.on_release_msg()
+        self.context.task_units.abort(self.context.tasklet_id)
 
 
 class ServerTasklet(Tasklet):

@@ -74,7 +74,8 @@ def load_class(path: str):
 class TaskletRuntime:
     def __init__(self, executor, num_tasklets: int) -> None:
         self._ex = executor
-        self._pool = new_fixed_thread_pool(max(1, num_tasklets), f"{executor.executor_id}-tasklet")
+        # daemon threads bounded by a semaphore (a parked tasklet must never block interpreter exit)
+        self._slots = threading.Semaphore(max(1, num_tasklets))
         self._tasklets: Dict[str, Tasklet] = {}
         self._lock = threading.Lock()
 
@@ -86,7 +87,12 @@ class TaskletRuntime:
             if conf.tasklet_id in self._tasklets:
                 raise RuntimeError(f"tasklet {conf.tasklet_id} already running")
             self._tasklets[conf.tasklet_id] = tasklet
-        self._pool.submit(self._run, conf.tasklet_id, tasklet)
+        threading.Thread(target=self._run_slot, args=(conf.tasklet_id, tasklet), daemon=True,
+                         name=f"{self._ex.executor_id}-tasklet-{conf.tasklet_id}").start()
+
+    def _run_slot(self, tasklet_id: str, tasklet: Tasklet) -> None:
+        with self._slots:
+            self._run(tasklet_id, tasklet)
 
     def _status(self, tasklet_id: str, status: str, result: Any = None, error: Optional[str] = None) -> None:
         self._ex.send_to_driver({"type": "TaskletStatus", "tasklet_id": tasklet_id,
@@ -131,7 +137,6 @@ class TaskletRuntime:
                 t.close()
             except Exception:  # noqa: BLE001
                 pass
-        self._pool.shutdown(wait=False)
 
 
 class LocalTaskUnitScheduler:
@@ -159,6 +164,14 @@ class LocalTaskUnitScheduler:
                                  "unit_name": unit.unit_name, "seq": unit.seq})
         ev.wait()
         self._sems[unit.resource].acquire()
+
+    def abort(self, tasklet_id: str) -> None:
+        """Wake every unit wait of `tasklet_id` (its job is being aborted)."""
+        with self._lock:
+            keys = [k for k in self._ready if k[0] == tasklet_id]
+            evs = [self._ready.pop(k) for k in keys]
+        for ev in evs:
+            ev.set()
 
     def on_ready(self, m: Dict[str, Any]) -> None:
         key = (m["tasklet_id"], m["job_id"], m["unit_name"], m["seq"])

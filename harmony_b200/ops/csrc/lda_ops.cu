@@ -113,11 +113,8 @@ void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at
   TORCH_CHECK(nwk.scalar_type() == at::kInt && nk.scalar_type() == at::kInt && nwk.stride(1) == 1);
   const size_t smem = (size_t)LDA_WARPS * K * (sizeof(int) + sizeof(float));
   TORCH_CHECK(smem <= 200 * 1024, "num_topics too large for the shared-memory sampler");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lda_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  // per-device attribute: set on every launch (executors of one process may drive different GPUs)
+  cudaFuncSetAttribute(lda_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int grid = std::min((n_docs + LDA_WARPS - 1) / LDA_WARPS, 148 * 8);
   lda_sample_kernel<<<grid, LDA_WARPS * 32, smem, stream>>>(
       doc_ptr.data_ptr<int>(), tok_slot.data_ptr<int>(),

@@ -278,12 +278,8 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
   TORCH_CHECK(out.size(0) >= M && out.size(1) >= N);
   CUtensorMap tmA;
   encode_2d_f32(&tmA, X.data_ptr<float>(), (uint64_t)K, (uint64_t)M, (uint64_t)X.stride(0), TC_BK, TC_BM);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(dense_gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    attr = true;
-  }
+  // per-device attribute (several executors of one process may drive different GPUs): set it every launch
+  cudaFuncSetAttribute(dense_gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   TableView none{};
   dense_gemm_tf32_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
@@ -312,11 +308,7 @@ void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int
                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   auto dmap = at::empty({(int64_t)sizeof(CUtensorMap)}, at::TensorOptions().dtype(at::kByte).device(X.device()));
   cudaMemcpyAsync(dmap.data_ptr(), &tmD, sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    attr = true;
-  }
+  cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   TableView W;
   W.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
   W.num_blocks = (int)block_ptrs.numel();

@@ -42,3 +42,24 @@ def write_lda_sample(path, docs=60, vocab=50, topics=3, doc_len=30, seed=0):
             ws = [rng.choice(vocab, p=phi[t]) for t in z]
             f.write(" ".join(str(w) for w in ws) + "\n")
     return path
+
+
+class FailingTrainer:
+    """Trainer that raises in local_compute on ONE executor (fail-fast test)."""
+
+    def __init__(self, params, model_accessor, context=None, **_):
+        self.ctx = context
+        self.victim = params.get("victim")
+
+    def init_global_settings(self): pass
+    def set_mini_batch_data(self, b): pass
+    def pull_model(self): pass
+
+    def local_compute(self):
+        if self.ctx.executor.executor_id == self.victim:
+            raise RuntimeError("injected trainer failure")
+
+    def push_update(self): pass
+    def on_epoch_finished(self, e): pass
+    def cleanup(self): pass
+    def summary(self): return {}

@@ -137,3 +137,38 @@ def test_metric_manager_validation_rules():
     assert not mm.store_worker_metric("w", 4, m)          # block count disagrees with the driver's view
     assert mm.store_worker_metric("w", 5, m)
     assert len(mm.get_worker_batch_metrics()["w"]) == 2
+
+
+def test_job_fails_fast_when_one_worker_fails():
+    """A failing worker must fail the JOB quickly (the others are parked at barriers), not the server."""
+    from harmony_b200.dolphin.conf import ETDolphinConfiguration
+    from harmony_b200.mlapps import examples
+    import helpers  # noqa: F401
+    app = ETDolphinConfiguration(app_id="Failing", trainer_class="helpers:FailingTrainer", input_parser="example",
+                                 model_table_conf=examples._vec_table, parameters=examples.P.EXAMPLES)
+    import sys
+    sys.modules["failing_app"] = type(sys)("failing_app")
+    sys.modules["failing_app"].APP = app
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 3, "port": port})).start()
+    try:
+        data = examples.write_dummy_input(30)
+        conf_args = ["-input", data, "-max_num_epochs", "3", "-num_mini_batches", "6", "-num_worker_blocks", "6",
+                     "-num_server_blocks", "4", "-num_keys", "4", "-port", str(port)]
+        from harmony_b200.dolphin.launcher import parse_job_conf
+        conf = parse_job_conf(app, conf_args).with_values(
+            job_entity_builder="harmony_b200.dolphin.jobserver:DolphinJobEntityBuilder", app="failing_app:APP",
+            victim="executor-1")
+        t0 = time.time()
+        from harmony_b200.jobserver.client import CommandSender
+        assert CommandSender(port).send_job_submit_command(conf.serialize()).startswith("true")
+        ok, result = js.driver.wait_job("Failing-0", timeout=60)
+        assert not ok and "injected trainer failure" in str(result)
+        assert time.time() - t0 < 40
+        # the server survives and runs the next job
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(
+            write_mlr_sample(os.path.join(tempfile.mkdtemp(), "s"), n=60), port, ["-max_num_epochs", "1"]), port=port
+        ).startswith("true")
+        assert js.driver.wait_job("MLR-1", timeout=120)[0]
+    finally:
+        js.stop(kill=True)

@@ -104,8 +104,8 @@ def test_nmf_and_lda_jobs_on_device_backend():
         # two concurrent jobs sharing the same two GPU executors
         assert DolphinJobLauncher.submit_job(nmf.APP_PATH, nmf.APP, a1, port=port).startswith("true")
         assert DolphinJobLauncher.submit_job(lda.APP_PATH, lda.APP, a2, port=port).startswith("true")
-        ok1, r1 = js.driver.wait_job("NMF-0", timeout=300)
-        ok2, r2 = js.driver.wait_job("LDA-1", timeout=300)
+        ok1, r1 = js.driver.wait_job("NMF-0", timeout=120)
+        ok2, r2 = js.driver.wait_job("LDA-1", timeout=120)
         assert ok1, r1
         assert ok2, r2
         assert all(np.isfinite(r["last_batch_loss"]) for r in r1)

@@ -33,7 +33,7 @@ def test_mlr_job_on_device_backend_matches_host_backend():
                     "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
                     "-port", str(port)]
             assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
-            ok, result = js.driver.wait_job("MLR-0", timeout=300)
+            ok, result = js.driver.wait_job("MLR-0", timeout=120)
             assert ok, result
             losses[backend] = np.mean([r["last_batch_loss"] / 64.0 for r in result])
             assert js.backend == backend
@@ -105,7 +105,7 @@ def test_dense_input_mlr_job_uses_tensor_core_path():
                 "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
                 "-dense_input", "true", "-port", str(port)]
         assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
-        ok, result = js.driver.wait_job("MLR-0", timeout=300)
+        ok, result = js.driver.wait_job("MLR-0", timeout=120)
         assert ok, result
         loss = np.mean([r["last_batch_loss"] / 64.0 for r in result])
         assert loss < 1.30, loss
@@ -130,7 +130,7 @@ def test_device_backend_with_executor_processes():
         args = ["-input", data, "-max_num_epochs", "8", "-num_mini_batches", "4", "-num_worker_blocks", "4",
                 "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64", "-port", str(port)]
         assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
-        ok, result = js.driver.wait_job("MLR-0", timeout=600)
+        ok, result = js.driver.wait_job("MLR-0", timeout=180)
         assert ok, result
         loss = np.mean([r["last_batch_loss"] / 64.0 for r in result])
         assert loss < 1.30, loss
