@@ -272,22 +272,39 @@ def main():
         staging = [[torch.empty(n, dtype=t.dtype, device=dev) for n, t in zip(maxn, host_batches[0].tensors())]
                    for _ in range(2)]                       # double-buffered device staging
 
-        def e2e_step(i):
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def prefetch(i):
+            """H2D of step i's inputs from pinned host memory on the copy stream (double buffered: the
+            buffer was last read by step i-2, whose loss has already been read back => it is free)."""
             hbt = host_batches[i % len(host_batches)]
             views = []
-            for dst, src in zip(staging[i % 2], hbt.tensors()):
-                v = dst[: src.numel()]
-                v.copy_(src, non_blocking=True)             # H2D of this step's inputs (pinned)
-                views.append(v)
-            model.stats.zero_()
-            step(rebuild(views))
-            return float(model.stats.cpu()[0])              # D2H of the step's loss (syncs)
-        for i in range(max(3, args.warmup)):
-            e2e_step(i)
+            with torch.cuda.stream(copy_stream):
+                for dst, src in zip(staging[i % 2], hbt.tensors()):
+                    v = dst[: src.numel()]
+                    v.copy_(src, non_blocking=True)
+                    views.append(v)
+                ready[i % 2].record(copy_stream)
+            return views
+
+        def e2e_run(n):
+            last = 0.0
+            nxt = prefetch(0)
+            for i in range(n):
+                views = nxt
+                main_stream.wait_event(ready[i % 2])        # this step's inputs have landed
+                model.stats.zero_()
+                step(rebuild(views))
+                if i + 1 < n:
+                    nxt = prefetch(i + 1)                   # overlaps with the kernels of step i
+                last = float(model.stats.cpu()[0])          # D2H of this step's loss (syncs the step)
+            return last
+        e2e_run(max(3, args.warmup))
         barrier_sync()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            last_loss = e2e_step(i)
+        last_loss = e2e_run(args.steps)
         barrier_sync()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {"value": round(world * args.steps / (e2e_ms / 1e3), 3), "unit": "mini-batches/s",
