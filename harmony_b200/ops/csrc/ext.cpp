@@ -55,9 +55,9 @@ void mlr_softmax_bcast(at::Tensor L, at::Tensor labels, int64_t num_classes, dou
 at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_block, int64_t row_stride,
                                  int64_t device, int64_t swizzle_mode);
 void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out,
-                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout);
+                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout, bool use_2cta);
 void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
-                          int64_t row_stride, int64_t n_classes, int64_t mode);
+                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -87,11 +87,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("nmf_batch", &hb::nmf_batch);
   m.def("lda_sample", &hb::lda_sample);
   m.def("mlr_partial_forward", &hb::mlr_partial_forward);
-  m.def("dense_grad_push_tf32", &hb::dense_grad_push_tf32);
+  m.def("dense_grad_push_tf32", &hb::dense_grad_push_tf32, py::arg("X"), py::arg("D"), py::arg("block_ptrs"),
+        py::arg("rows_per_block"), py::arg("row_stride"), py::arg("n_classes"), py::arg("mode"),
+        py::arg("use_2cta") = false);
   m.def("make_block_tensormaps", &hb::make_block_tensormaps, py::arg("block_ptrs_cpu"), py::arg("rows_per_block"),
         py::arg("row_stride"), py::arg("device"), py::arg("swizzle_mode") = 1);
   m.def("dense_logits_tf32", &hb::dense_logits_tf32, py::arg("X"), py::arg("bmaps"), py::arg("rows_per_block"),
         py::arg("n_cols"), py::arg("out"), py::arg("dbg") = 0, py::arg("b_lbo") = 0, py::arg("b_sbo") = 0,
-        py::arg("idesc_xor") = 0, py::arg("b_layout") = 0);
+        py::arg("idesc_xor") = 0, py::arg("b_layout") = 0, py::arg("use_2cta") = false);
   m.def("mlr_softmax_bcast", &hb::mlr_softmax_bcast);
 }

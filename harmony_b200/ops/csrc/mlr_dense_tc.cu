@@ -39,12 +39,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && ++spins > 200000000u) __trap();      // a protocol bug must fault, never hang the GPU
   } while (!ok);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int x, int y) {
@@ -218,6 +220,167 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_kernel(
   }
 }
 
+
+// ===================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile (128 of the 256 columns), the leader issues
+// tcgen05.mma.cta_group::2 (M = 256), both CTAs keep 128 x 256 fp32 accumulators in their TMEM.
+// Per CTA the staged bytes per K-step are unchanged (32 KB) while the math doubles: 64 FLOP per
+// staged byte instead of 32, which lifts the L2-bandwidth ceiling that bounds the 1-CTA kernel.
+// ===================================================================================================
+constexpr int T2_BN = 256, T2_STAGES = 6, T2_TMEM_COLS = 256;
+constexpr int T2_SMEM_BYTES = T2_STAGES * TC_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const void* tmap, uint32_t leader_bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_dst), "l"(tmap), "r"(leader_bar & kPeerBitMask), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool A_MN, bool PUSH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_2cta_kernel(
+    const __grid_constant__ CUtensorMap tmA, const CUtensorMap* __restrict__ tmB, float* __restrict__ out,
+    int out_stride, int M, int N, int K, int rows_per_block, TableView Wtab) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + T2_STAGES * TC_STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * T2_STAGES, tmem_full = bars + 16 * T2_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_STAGES * TC_STAGE_BYTES + 16 * T2_STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int m0 = (blockIdx.x >> 1) * 256 + (int)cta_rank * TC_BM;   // this CTA's 128 rows of the 256-row tile
+  const int n0 = blockIdx.y * T2_BN;
+  const int nb0 = n0 + (int)cta_rank * 128;                          // this CTA's half of the B tile
+  const int KT = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(T2_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs; transaction bytes are credited to the LEADER's barrier) =====
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % T2_STAGES;
+        mbar_wait(empty0 + 8 * s, ((kt / T2_STAGES) & 1) ^ 1);
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+        if (leader) mbar_expect_tx(full0 + 8 * s, 2 * TC_STAGE_BYTES);
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < TC_BM / 32; ++j)
+            tma_load_2d_2cta(sa + j * (TC_BK * 128), &tmA, full0 + 8 * s, m0 + 32 * j, kt * TC_BK);
+        } else {
+          tma_load_2d_2cta(sa, &tmA, full0 + 8 * s, kt * TC_BK, m0);
+        }
+        const int f0 = kt * TC_BK;
+        const int blk = f0 / rows_per_block, y = f0 - blk * rows_per_block;
+        const CUtensorMap* mb = tmB + blk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tma_load_2d_2cta(sb + j * (TC_BK * 128), mb, full0 + 8 * s, nb0 + 32 * j, y);
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===== MMA issuer: leader CTA only, M = 256 across the pair, N = 256 =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | (1u << 16) |
+                             ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % T2_STAGES;
+        mbar_wait(full0 + 8 * s, (kt / T2_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int i = 0; i < TC_BK / TC_UMMA_K; ++i) {
+          const uint64_t ad = A_MN ? umma_desc(sa + i * 1024, TC_BK * 128, 512, 1)
+                                   : umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
+          const uint64_t bd = umma_desc(sb + i * 1024, TC_BK * 128, 512, 1);
+          tc_mma_tf32_2cta(tmem_base, ad, bd, idesc, (kt > 0 || i > 0) ? 1u : 0u);
+        }
+        tc_commit_2cta(empty0 + 8 * s);             // frees the stage in BOTH CTAs
+      }
+      tc_commit_2cta(tmem_full);                    // accumulators complete in BOTH CTAs
+    }
+  } else {
+    // ===== epilogue (each CTA drains its own 128 x 256 accumulator) =====
+    const int q = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+    for (int c = 0; c < T2_BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int col0 = n0 + c * 32;
+      if (PUSH) {
+        if (row < M) {
+          float* o = row_ptr<float>(Wtab, (long long)row) + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            if (col0 + e < N)
+              red_add_f4_sys(o + e, make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+        }
+      } else if (row < M) {
+        float* o = out + (size_t)row * out_stride + col0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          if (col0 + e < N)
+            *reinterpret_cast<float4*>(o + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                            __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                               // both CTAs are done with TMEM / peer smem
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(T2_TMEM_COLS) : "memory");
+  }
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -267,7 +430,7 @@ at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_blo
 
 // logits[M, >=N] = X[M, K] . W[K, N]   (W rows live in the table blocks described by `bmaps`)
 void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out,
-                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout) {
+                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout, bool use_2cta) {
   c10::cuda::CUDAGuard guard(X.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
@@ -280,8 +443,17 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
   encode_2d_f32(&tmA, X.data_ptr<float>(), (uint64_t)K, (uint64_t)M, (uint64_t)X.stride(0), TC_BK, TC_BM);
   // per-device attribute (several executors of one process may drive different GPUs): set it every launch
   cudaFuncSetAttribute(dense_gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   TableView none{};
+  if (use_2cta && dbg == 0) {
+    cudaFuncSetAttribute(dense_gemm_tf32_2cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    dim3 grid2(2 * ((M + 255) / 256), (N + T2_BN - 1) / T2_BN);
+    dense_gemm_tf32_2cta_kernel<false, false><<<grid2, TC_THREADS, T2_SMEM_BYTES, stream>>>(
+        tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(), (int)out.stride(0), M, N,
+        K, (int)rows_per_block, none);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
+  dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   dense_gemm_tf32_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
       tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(), (int)out.stride(0), M, N,
       K, (int)rows_per_block, (int)dbg, (int)(b_lbo ? b_lbo : TC_BK * 128), (int)(b_sbo ? b_sbo : 512),
@@ -292,7 +464,7 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
 // W[f, :] += sum_b X[b, f] * D[b, :]   (D is pre-scaled by -step).  GEMM M = features, N = classes, K = batch;
 // the epilogue reduce-adds each 128 x 128 gradient tile into the owners' rows: no gradient buffer exists.
 void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
-                          int64_t row_stride, int64_t n_classes, int64_t mode) {
+                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta) {
   c10::cuda::CUDAGuard guard(X.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
@@ -317,6 +489,14 @@ void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int
   W.row_dim = (int)n_classes;
   W.mode = (int)mode;
   const int N = (int)row_stride;
+  if (use_2cta) {
+    cudaFuncSetAttribute(dense_gemm_tf32_2cta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    dim3 grid2(2 * ((F + 255) / 256), (N + T2_BN - 1) / T2_BN);
+    dense_gemm_tf32_2cta_kernel<true, true><<<grid2, TC_THREADS, T2_SMEM_BYTES, stream>>>(
+        tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30, W);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+    return;
+  }
   dim3 grid((N + TC_BN - 1) / TC_BN, (F + TC_BM - 1) / TC_BM);
   dense_gemm_tf32_kernel<true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
       tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30, 0, TC_BK * 128, 512, 0,
