@@ -145,15 +145,16 @@ def test_mlr_ship_mode_single_gpu_matches_reference(arena):
     t.close()
 
 
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("B,F,C", [(128, 256, 128), (300, 1024, 1000), (4096, 4096, 1000)])
-def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C):
+def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C, two_cta):
     """tcgen05 (kind::tf32) GEMM whose B operand is TMA-loaded from the table's block slabs."""
     from harmony_b200.models.mlr_dense import DenseMLR
     t = _table(arena, F, C, max(1, F // 256), True, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 3}})
     assert t.rows_per_block % 32 == 0
     X = torch.randn((B, F), device="cuda")
     W = t.to_dense()
-    out = DenseMLR(t, C).logits(X)
+    out = DenseMLR(t, C, use_2cta=two_cta).logits(X)
     torch.cuda.synchronize()
     ref = X.double() @ W.double()
     err = (out[:, :C].double() - ref).abs().max().item()
@@ -163,15 +164,16 @@ def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C):
     t.close()
 
 
+@pytest.mark.parametrize("two_cta", [False, True])
 @pytest.mark.parametrize("B,F,C", [(64, 256, 100), (500, 2048, 1000)])
-def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C):
+def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C, two_cta):
     """Forward GEMM + softmax + backward GEMM whose epilogue reduce-adds into the table rows."""
     from harmony_b200.models.mlr_dense import DenseMLR
     t = _table(arena, F, C, max(1, F // 256), True, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 3}})
     X = torch.randn((B, F), device="cuda") * 0.5
     y = torch.randint(0, C, (B,), device="cuda", dtype=torch.int32)
     W0 = t.to_dense().clone()
-    m = DenseMLR(t, C)
+    m = DenseMLR(t, C, use_2cta=two_cta)
     m.step(X, y, 0.01)
     torch.cuda.synchronize()
     logits = X.double() @ W0.double()
