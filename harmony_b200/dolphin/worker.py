@@ -353,9 +353,16 @@ class WorkerTasklet(Tasklet):
                 self.trainer.set_mini_batch_data(batch)
                 self.accessor.get_and_reset_metrics()
                 t0 = time.perf_counter()
-                self._unit("PULL", NET, seq, self.trainer.pull_model)
-                comp = self._unit("COMP", CPU, seq, self.trainer.local_compute)
-                self._unit("PUSH", NET, seq, self.trainer.push_update)
+                if getattr(self.trainer, "fused_step", False):
+                    # device trainers fuse pull/compute/push into back-to-back kernels: ONE task unit
+                    # (one driver round trip) per mini-batch instead of three
+                    def fused():
+                        self.trainer.pull_model(); self.trainer.local_compute(); self.trainer.push_update()
+                    self._unit("STEP", NET, seq, fused)
+                else:
+                    self._unit("PULL", NET, seq, self.trainer.pull_model)
+                    self._unit("COMP", CPU, seq, self.trainer.local_compute)
+                    self._unit("PUSH", NET, seq, self.trainer.push_update)
                 seq += 1
                 bt = time.perf_counter() - t0
                 am = self.accessor.get_and_reset_metrics()

@@ -10,6 +10,8 @@ from .lda import doc_llh, word_llh
 
 
 class LDADeviceTrainer(Trainer):
+    fused_step = True      # pull / compute / push are back-to-back kernels on one stream
+
     def __init__(self, params: Dict[str, Any], model_table, local_model_table=None, input_table=None,
                  **_: Any) -> None:
         import torch

@@ -19,6 +19,8 @@ LOG = logging.getLogger(__name__)
 
 
 class MLRDeviceTrainer(Trainer):
+    fused_step = True      # pull / compute / push are back-to-back kernels on one stream
+
     def __init__(self, params: Dict[str, Any], model_table, input_table=None, **_: Any) -> None:
         import torch
         from ..models.mlr import MLRDeviceModel
