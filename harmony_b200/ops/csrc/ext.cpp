@@ -23,6 +23,8 @@ void table_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_strid
                 at::Tensor keys, at::Tensor deltas, int64_t fn, double step, double lo, double hi, double eps);
 void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
                            int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K);
+void table_push_scalar_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor values, int64_t op);
 void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_dim, int64_t kind, double a,
                double b, int64_t seed, int64_t row_key_base, int64_t key_stride);
 void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes);
@@ -75,6 +77,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("table_pull", &hb::table_pull);
   m.def("table_push", &hb::table_push);
   m.def("table_push_sparse_i32", &hb::table_push_sparse_i32);
+  m.def("table_push_scalar_i32", &hb::table_push_scalar_i32);
   m.def("init_slab", &hb::init_slab);
   m.def("migrate_copy", &hb::migrate_copy);
   m.def("flip_owner", &hb::flip_owner);

@@ -151,6 +151,17 @@ __global__ void __launch_bounds__(256) push_sparse_i32_kernel(TableView t, const
   else if (old > 0 && nv == 0) atom_add_s32_sys(row + K, -1);
 }
 
+// Integer scatter-reduce of one value per key (Pregel message combiners, K13): op 0 = add, 1 = min.
+// The combine runs in the owner's memory system: messages to the same vertex from any GPU meet there.
+__global__ void __launch_bounds__(256) push_scalar_i32_kernel(TableView t, const long long* __restrict__ keys,
+                                                              const int* __restrict__ values, int n, int op) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int* p = row_ptr<int>(t, keys[i]);
+  if (op == 0) asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" :: "l"(p), "r"(values[i]) : "memory");
+  else asm volatile("red.relaxed.sys.global.min.s32 [%0], %1;" :: "l"(p), "r"(values[i]) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Initialisers: eager initValue for every row of a block slab (lazy init in the reference).
 // ------------------------------------------------------------------------------------------
@@ -306,6 +317,19 @@ void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_
   push_sparse_i32_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
       v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), topics.data_ptr<int>(),
       deltas.data_ptr<int>(), (int)n, (int)K);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void table_push_scalar_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor values, int64_t op) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && values.scalar_type() == at::kInt && values.numel() == n);
+  push_scalar_i32_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
+      v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), values.data_ptr<int>(), (int)n, (int)op);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -111,3 +111,35 @@ def test_nmf_and_lda_jobs_on_device_backend():
         assert all(np.isfinite(r["last_batch_loss"]) for r in r1)
     finally:
         js.stop(kill=True)
+
+
+def test_device_pregel_pagerank_and_sssp(arena):
+    from harmony_b200.parallel.peer import PeerGroup
+    from harmony_b200.pregel.device import DevicePregel, partition_adjacency
+    rng = np.random.default_rng(0)
+    V = 500
+    adj = {v: [(int(t), int(rng.integers(1, 9))) for t in rng.choice(V, size=rng.integers(1, 6), replace=False)]
+           for v in range(V)}
+    eng = DevicePregel(arena, PeerGroup(), V, partition_adjacency(adj, V, 0, 1))
+    pr = eng.pagerank(10, 0.85)
+    ref = np.ones(V)
+    for _ in range(10):
+        nxt = np.full(V, 0.15)
+        for v, es in adj.items():
+            for t, _ in es:
+                nxt[t] += 0.85 * ref[v] / len(es)
+        ref = nxt
+    np.testing.assert_allclose([pr[v] for v in range(V)], ref, rtol=1e-4)
+    sp = eng.shortest_path(source=3)
+    import heapq
+    dist = {3: 0}; pq = [(0, 3)]
+    while pq:
+        d, v = heapq.heappop(pq)
+        if d > dist.get(v, 1 << 60):
+            continue
+        for t, w in adj[v]:
+            if d + w < dist.get(t, 1 << 60):
+                dist[t] = d + w; heapq.heappush(pq, (d + w, t))
+    for v in range(V):
+        assert sp[v] == dist.get(v, 2 ** 31 - 1), v
+    eng.close()

@@ -87,3 +87,25 @@ def test_trace_spans_dump(tmp_path):
     trace.enable(False)
     t = trace.Tracer(); t.start_timer(); t.record_time(2)
     assert t.total_elapsed_time() >= 0 and t.avg_time_per_elem() >= 0
+
+
+def test_linalg_vector_matrix_api():
+    import torch
+    from harmony_b200.common.linalg import MatrixFactory, VectorFactory
+    vf, mf = VectorFactory(), MatrixFactory()
+    a, b = vf.create_dense([1, 2, 3]), vf.create_dense_ones(3)
+    assert a.dot(b) == 6 and a.add(b).t.tolist() == [2, 3, 4] and a.sub(1).t.tolist() == [0, 1, 2]
+    s = vf.create_sparse([0, 2], [5.0, -1.0], 3)
+    assert not s.is_dense() and s.active_size() == 2 and a.dot(s) == 2 and s.dot(a) == 2
+    a.axpy(2.0, s)
+    assert a.t.tolist() == [11, 2, 1] and a.slice(1, 3).t.tolist() == [2, 1]
+    assert vf.concat_dense([b, b]).length() == 6 and a.scale(2).div(2).t.tolist() == [11, 2, 1]
+    m = mf.create_dense([1, 2, 3, 4, 5, 6], 2, 3)            # column-major
+    assert m.get(1, 0) == 2 and m.rows() == 2 and m.columns() == 3
+    assert m.mmul(vf.create_dense([1, 1, 1])).t.tolist() == [9, 12]
+    assert m.transpose().mmul(m).t.shape == (3, 3) and m.slice_column(2).t.tolist() == [5, 6]
+    sp = mf.horzcat_vec_sparse([s, s])
+    assert not sp.is_dense() and sp.to_dense().t.tolist() == [[5, 5], [0, 0], [-1, -1]]
+    assert sp.transpose().mmul(vf.create_dense([1, 1, 1])).t.tolist() == [4, 4]
+    m.put_row(0, vf.create_dense([0, 0, 0])); m.addi(1).muli(2)
+    assert m.t.tolist() == [[2, 2, 2], [6, 10, 14]]
