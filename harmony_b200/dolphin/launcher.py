@@ -65,7 +65,14 @@ class ETDolphinLauncher:
         num_servers = int(conf.get("num_servers", 1))
         colocated = num_servers == 0
         transport = LocalTransport()
-        master = ETMaster(transport, InProcessLauncher(), chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
+        # -backend auto|host|device: on a GPU box the stand-alone job also runs on HBM tables + fused kernels
+        import itertools
+        from ..et.launcher import detect_backend, make_executor
+        backend = detect_backend(conf.get("backend", "auto"))
+        conf = conf.with_values(backend=backend)
+        ordinal = itertools.count()
+        launcher = InProcessLauncher(lambda eid, tr, ec_, did: make_executor(eid, tr, ec_, did, backend, next(ordinal)))
+        master = ETMaster(transport, launcher, chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
                           chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
         messages: List[str] = []
         receiver = ETDolphinMetricReceiver()

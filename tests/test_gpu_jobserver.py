@@ -136,3 +136,21 @@ def test_device_backend_with_executor_processes():
         assert loss < 1.30, loss
     finally:
         js.stop(kill=True)
+
+
+@pytest.mark.parametrize("optimizer", ["DeleteOneServerOptimizer", "MoveModelBlocksOptimizer"])
+def test_addvector_elastic_reconfiguration_on_device_backend(optimizer):
+    """OwnershipFirstMigrationTest on GPUs: servers and workers are separate device executors, the model
+    table lives in HBM slabs, a server is deleted / blocks are moved mid-run and AddVector still validates."""
+    from harmony_b200.dolphin.launcher import ETDolphinLauncher
+    from harmony_b200.mlapps import examples
+    path = examples.write_dummy_input(48)
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, [
+        "-input", path, "-num_dolphin_workers", "2", "-num_servers", "2", "-max_num_epochs", "6",
+        "-num_mini_batches", "8", "-num_worker_blocks", "8", "-num_server_blocks", "8", "-num_keys", "20",
+        "-vector_size", "4", "-delta", "2", "-compute_time_ms", "30", "-optimizer", optimizer,
+        "-optimization_interval_ms", "300", "-delay_after_optimization_ms", "100",
+        "-min_num_required_batch_metrics", "1", "-backend", "device"], extra_conf={"job_timeout_sec": 120})
+    assert res.ok, res.messages
+    if optimizer == "DeleteOneServerOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 1, W: 2)" in m for m in res.messages), res.messages
