@@ -119,7 +119,8 @@ class DolphinJobEntity(JobEntity):
                   "model_table_id": self.server_tc.table_id, "input_table_id": self.worker_tc.table_id,
                   "local_model_table_id": self.local_tc.table_id if self.local_tc else None,
                   "data_parser": self.app.input_parser, "app_id": self.app.app_id,
-                  "num_job_workers": max(1, len(self.executors))})
+                  "num_job_workers": max(1, len(self.executors)),
+                  "job_executor_ids": [e.id for e in self.executors]})
         return p
 
     def setup_executors_and_tables(self, executors: Sequence[AllocatedExecutor]) -> None:

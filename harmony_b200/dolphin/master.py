@@ -383,6 +383,8 @@ class DolphinMaster:
         self.task_runner = ETTaskRunner(master, job_id)
         self.task_runner.msg_handler = self.on_worker_msg
         self.sender = MasterSideMsgSender(self.task_runner)
+        from .group import MasterSideRendezvous
+        self.rendezvous = MasterSideRendezvous(lambda w, body: self.sender._send(w, body))
         self.metric_manager = DolphinMetricManager(int(params.get("num_initial_batch_metrics_to_skip", 0)))
         self.metric_manager.model_table_id = params.get("model_table_id")
         self.state_manager: Optional[WorkerStateManager] = None
@@ -407,6 +409,8 @@ class DolphinMaster:
             self.progress_tracker.on_progress_msg(body["executor_id"], body["progress"])
         elif t == "ModelEvalAskMsg":
             self._on_model_eval_ask(body["executor_id"])
+        elif t == "GroupGather":
+            self.rendezvous.on_msg(body)
         else:
             LOG.warning("unknown dolphin message %s", t)
 

@@ -75,7 +75,9 @@ OPTIMIZER = [
     P("dashboard_enabled", bool, False, "", "dashboard"), P("dashboard_port", int, 9005, "", "dashboard"),
 ]
 MLR = [P("classes", int, 0, "number of classes", "user"),
-       P("dense_input", bool, False, "dense instances: tcgen05 GEMM path on the device backend", "user")]
+       P("dense_input", bool, False, "dense instances: tcgen05 GEMM path on the device backend", "user"),
+       P("mlr_mode", str, "pull", "pull: model rows move (PS pull/push); ship: activations move (owner-side dot, "
+                                  "BSP lockstep, device backend, num_worker_blocks % workers == 0)", "user")]
 NMF = [P("rank", int, 0, "", "user"), P("max_val", float, 1e6, "", "user"), P("init_max", float, 1.0, "", "user"),
        P("init_min", float, 0.0, "", "user"), P("print_mat", bool, False, "", "user")]
 LDA = [P("alpha", float, 0.001, "", "user"), P("beta", float, 0.01, "", "user"), P("num_topics", int, 100, "", "user"),

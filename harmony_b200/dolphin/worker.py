@@ -167,16 +167,18 @@ class ETTrainingDataProvider(TrainingDataProvider):
     """One local block of the input table is one mini-batch; blocks are shuffled every epoch and
     the provider tolerates blocks that migrate away in the middle of an epoch."""
 
-    def __init__(self, input_table) -> None:
+    def __init__(self, input_table, shuffle: bool = True) -> None:
         self._table = input_table
         self._blocks: List[int] = []
+        self.shuffle = shuffle
 
     def _tablet(self):
         return self._table.get_local_tablet()
 
     def prepare_data_for_epoch(self) -> None:
-        self._blocks = list(self._tablet().get_block_ids())
-        random.shuffle(self._blocks)
+        self._blocks = sorted(self._tablet().get_block_ids(), reverse=True)   # popped from the end: ascending
+        if self.shuffle:
+            random.shuffle(self._blocks)
 
     def get_num_batches_per_epoch(self) -> int:
         return len(self._tablet().get_block_ids())
@@ -299,9 +301,16 @@ class WorkerTasklet(Tasklet):
         self.model_table = acc.get_table(p["model_table_id"])
         self.input_table = acc.get_table(p["input_table_id"])
         self.local_model_table = acc.get_table(p["local_model_table_id"]) if p.get("local_model_table_id") else None
-        self.trainer, self.accessor = build_trainer(context, p, self.model_table, self.local_model_table,
-                                                    self.input_table)
-        self.data_provider = ETTrainingDataProvider(self.input_table)
+        # rendezvous group of this job's workers (rank = position among the job's executors)
+        ex_ids = list(p.get("job_executor_ids") or [context.executor.executor_id])
+        from .group import WorkerSideGroup
+        context.job_group = WorkerSideGroup(
+            ex_ids.index(context.executor.executor_id) if context.executor.executor_id in ex_ids else 0, len(ex_ids),
+            context.executor.executor_id, lambda body: context.send_to_driver({"job_id": self.job_id, "dolphin": body}))
+        self._trainer_args = (context, p, self.model_table, self.local_model_table, self.input_table)
+        self.trainer, self.accessor = build_trainer(*self._trainer_args)
+        self.data_provider = ETTrainingDataProvider(self.input_table,
+                                                    shuffle=not getattr(self.trainer, "wants_sorted_batches", False))
         self.max_epochs = int(p.get("max_num_epochs", 1))
         self.use_task_units = bool(p.get("task_units_enabled", True))
 
@@ -312,6 +321,10 @@ class WorkerTasklet(Tasklet):
             self.global_barrier.on_release_msg()
         elif t == "MiniBatchControlMsg":
             self.mini_batch_barrier.on_control_msg(payload["stop"])
+        elif t == "GroupGatherRes":
+            grp = getattr(self.context, "job_group", None)
+            if grp is not None:
+                grp.on_msg(payload)
 
     def _unit(self, name: str, resource: str, seq: int, fn) -> float:
         info = TaskUnitInfo(self.job_id, name, resource, seq)

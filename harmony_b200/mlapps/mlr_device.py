@@ -20,6 +20,7 @@ LOG = logging.getLogger(__name__)
 
 class MLRDeviceTrainer(Trainer):
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
+    wants_sorted_batches = False
 
     def __init__(self, params: Dict[str, Any], model_table, input_table=None, **_: Any) -> None:
         import torch
@@ -38,12 +39,60 @@ class MLRDeviceTrainer(Trainer):
         self._batch = None
         self.num_workers = int(params.get("num_job_workers", 1))
         self.num_features = int(params["features"])
+        self.ship = None
+        if params.get("mlr_mode") == "ship":
+            self._init_ship(params, input_table, _.get("context"))
         self.dense = None
         if params.get("dense_input") and self.dtable.mode == 0 and self.dtable.rows_per_block % 32 == 0 \
                 and self.num_features % 32 == 0:
             from ..models.mlr_dense import DenseMLR
             self.dense = DenseMLR(self.dtable, self.num_classes)      # tcgen05 / TMEM / TMA path
             self.dense.stats = self.model.stats
+
+    # ---- "ship the activations" mode inside the job server (see models/mlr_ship.py) ----
+    def _init_ship(self, params, input_table, context) -> None:
+        from ..models.mlr import build_batch
+        from ..models.mlr_ship import MLRShipModel, route_batches
+        from ..parallel.device_clock import DeviceClock
+        group = getattr(context, "job_group", None)
+        tablet = input_table.get_local_tablet()
+        blocks = sorted(tablet.get_block_ids())
+        host, first_key = [], {}
+        for s_idx, b in enumerate(blocks):
+            data = sorted(tablet.get_data_in_block(b), key=lambda kv: kv[0])
+            if not data:
+                continue
+            first_key[min(k for k, _ in data)] = len(host)
+            ptr, col, val, labels = batch_to_csr(data)
+            host.append((ptr, col, val, labels))
+        if group is None:
+            return
+        sizes = group.all_gather_object((len(host), max((len(h[3]) for h in host), default=0)), tag="ship-sizes")
+        n_steps, B = sizes[0][0], max(sz[1] for sz in sizes)
+        if any(sz[0] != n_steps for sz in sizes) or n_steps == 0:
+            return                                        # uneven blocks: stay in pull mode (same on every worker)
+        padded = []
+        for ptr, col, val, labels in host:                # pad every mini-batch to B rows (label -1 = no instance)
+            n = len(labels)
+            ptr = np.concatenate([ptr, np.full(B - n, ptr[-1], dtype=ptr.dtype)])
+            labels = np.concatenate([labels, np.full(B - n, -1, dtype=labels.dtype)])
+            padded.append(build_batch(ptr.astype(np.int32), col, val, labels))
+        everyone = group.all_gather_object([[t.numpy() for t in mb.tensors()[:4]] for mb in padded], tag="ship-data")
+        ex_ids = list(params.get("job_executor_ids") or [])
+        owner_ranks = [ex_ids.index(o) if o in ex_ids else -1 for o in self.dtable.owners]
+        if any(r < 0 for r in owner_ranks):
+            return
+        ctx = context.executor.device_ctx
+        clock = DeviceClock(ctx.arena, group)
+        self.ship = MLRShipModel(self.dtable, ctx.arena, group, clock, self.num_classes, self.model.step_size, B)
+        self.ship.stats = self.model.stats
+        self._ship_owner_ranks = list(self.dtable.owners)
+        self._ship_steps = []
+        for s_idx in range(n_steps):
+            allw = [build_batch(*everyone[w][s_idx]) for w in range(group.world)]
+            self._ship_steps.append(route_batches(self.dtable, allw, group.rank, owner_ranks).to(self.dtable.device))
+        self._ship_first_key = first_key
+        self.wants_sorted_batches = True
 
     def _to_dense_batch(self, mini_batch):
         key = ("dense", mini_batch[0][0], len(mini_batch))
@@ -71,12 +120,15 @@ class MLRDeviceTrainer(Trainer):
         return b
 
     def set_mini_batch_data(self, mini_batch) -> None:
+        if self.ship is not None:
+            self._batch = self._ship_steps[self._ship_first_key[min(k for k, _ in mini_batch)]]
+            return
         self._batch = self._to_device_batch(mini_batch)
 
     def pull_model(self) -> None:
         self.comps.gate.acquire_read()          # held from PULL to PUSH: migration waits for a batch boundary
         self.model.stats.zero_()
-        if self.dense is None:
+        if self.dense is None and self.ship is None:
             self.model.forward(self._batch, True)
 
     def local_compute(self) -> None:
@@ -84,12 +136,18 @@ class MLRDeviceTrainer(Trainer):
 
     def push_update(self) -> None:
         try:
-            if self.dense is not None:
+            if self.ship is not None:
+                if list(self.dtable.owners) != self._ship_owner_ranks:
+                    raise RuntimeError("ship mode does not support re-partitioning the model table mid-job")
+                self.ship.step_size = self.model.step_size
+                self.ship.step(self._batch)               # BSP lockstep over the job's workers (device clocks)
+            elif self.dense is not None:
                 X, y = self._batch
                 self.dense.step(X, y, self.model.step_size, self.model.stats)   # GEMM -> softmax -> GEMM+push
             else:
                 self.model.backward_push(self._batch)
-            bsz = self._batch[0].shape[0] if self.dense is not None else self._batch.batch_size
+            bsz = self.ship.B if self.ship is not None else (
+                self._batch[0].shape[0] if self.dense is not None else self._batch.batch_size)
             self.model.apply_l2(bsz * self.num_workers)
             self._torch.cuda.current_stream(self.dtable.device).synchronize()
         finally:

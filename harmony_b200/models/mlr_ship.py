@@ -24,10 +24,13 @@ from ..parallel.peer import PeerArena, PeerGroup
 from .mlr import MLRBatch, build_batch
 
 
-def owner_of_features(table: DeviceTable, feats: np.ndarray) -> np.ndarray:
+def owner_of_features(table: DeviceTable, feats: np.ndarray, owner_ranks: Optional[Sequence[int]] = None) -> np.ndarray:
+    """Rank of the GPU owning each feature row.  `owner_ranks[b]` overrides table.owners when the owners are
+    executor ids (job-server mode) instead of SPMD ranks."""
     feats = np.asarray(feats, dtype=np.int64)
     blocks = feats // table.rows_per_block if table.mode == PART_ORDERED else feats % table.num_blocks
-    return np.asarray(table.owners, dtype=np.int64)[blocks]
+    owners = table.owners if owner_ranks is None else owner_ranks
+    return np.asarray(owners, dtype=np.int64)[blocks]
 
 
 @dataclass
@@ -49,14 +52,15 @@ class RoutedBatch:
         return self.routed.nbytes() + self.labels.numel() * 4
 
 
-def route_batches(table: DeviceTable, worker_batches: Sequence[MLRBatch], rank: int) -> RoutedBatch:
+def route_batches(table: DeviceTable, worker_batches: Sequence[MLRBatch], rank: int,
+                  owner_ranks: Optional[Sequence[int]] = None) -> RoutedBatch:
     """Build rank's owner-side slices from every worker's mini-batch (done once per input block)."""
     B = worker_batches[0].batch_size
     ptrs, cols, vals = [np.zeros(1, dtype=np.int64)], [], []
     for w, mb in enumerate(worker_batches):
         assert mb.batch_size == B, "ship mode needs equally sized mini-batches"
         ptr, col, val = mb.csr_ptr.numpy().astype(np.int64), mb.csr_col.numpy(), mb.csr_val.numpy()
-        mine = owner_of_features(table, col) == rank
+        mine = owner_of_features(table, col, owner_ranks) == rank
         rows = np.repeat(np.arange(B), np.diff(ptr))[mine]
         counts = np.bincount(rows, minlength=B)
         ptrs.append(ptrs[-1][-1] + np.cumsum(counts))

@@ -172,3 +172,23 @@ def test_job_fails_fast_when_one_worker_fails():
         assert js.driver.wait_job("MLR-1", timeout=120)[0]
     finally:
         js.stop(kill=True)
+
+
+def test_control_plane_group_rendezvous():
+    """WorkerSideGroup / MasterSideRendezvous: rank-ordered all_gather over the job's message channel."""
+    import threading
+    from harmony_b200.dolphin.group import MasterSideRendezvous, WorkerSideGroup
+    groups = {}
+    rdv = MasterSideRendezvous(lambda w, body: groups[w].on_msg(body))
+    for r in range(3):
+        groups[f"w{r}"] = WorkerSideGroup(r, 3, f"w{r}", rdv.on_msg)
+    out = {}
+
+    def run(r):
+        g = groups[f"w{r}"]
+        out[r] = (g.all_gather_object({"r": r}), g.all_gather_object(r * 10))
+        g.barrier()
+    ts = [threading.Thread(target=run, args=(r,)) for r in (2, 0, 1)]
+    [t.start() for t in ts]; [t.join(10) for t in ts]
+    for r in range(3):
+        assert out[r] == ([{"r": 0}, {"r": 1}, {"r": 2}], [0, 10, 20])

@@ -154,3 +154,29 @@ def test_addvector_elastic_reconfiguration_on_device_backend(optimizer):
     assert res.ok, res.messages
     if optimizer == "DeleteOneServerOptimizer":
         assert any("(S: 2, W: 2) -> (S: 1, W: 2)" in m for m in res.messages), res.messages
+
+
+def test_mlr_ship_mode_inside_job_server():
+    """-mlr_mode ship: owner-side dot + activation exchange over peer memory, rendezvous of handles
+    through the job's master, BSP lockstep by device clocks -- same model quality as the pull mode."""
+    from harmony_b200.dolphin.launcher import DolphinJobLauncher
+    from harmony_b200.jobserver.client import JobServer
+    from harmony_b200.mlapps import mlr
+    from harmony_b200.utils.flags import Configuration
+    tmp = tempfile.mkdtemp(prefix="hbgpu6")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=256, features=64, classes=4)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port, "backend": "device"})).start()
+    try:
+        losses = {}
+        for i, mode in enumerate(("pull", "ship")):
+            args = ["-input", data, "-max_num_epochs", "8", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                    "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
+                    "-mlr_mode", mode, "-port", str(port)]
+            assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+            ok, result = js.driver.wait_job(f"MLR-{i}", timeout=120)
+            assert ok, result
+            losses[mode] = np.mean([r["last_batch_loss"] / 64.0 for r in result])
+        assert losses["ship"] < 1.30 and abs(losses["ship"] - losses["pull"]) < 0.25, losses
+    finally:
+        js.stop(kill=True)
