@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--nnz_per_row", type=int, default=16)
     ap.add_argument("--batch_rows", type=int, default=131072)
     ap.add_argument("--distinct_batches", type=int, default=8)
+    ap.add_argument("--impl", default="harmony", choices=["harmony", "nccl"],
+                    help="nccl: replicated R, dense gradient all-reduce, local SGD+clamp (baseline)")
     a = ap.parse_args()
     import torch
     world, rank, lr, dev = init_dist()
@@ -32,7 +34,7 @@ def main():
     from harmony_b200.models.nmf import NMFBatch, NMFDeviceModel
     from harmony_b200.parallel.device_clock import DeviceClock
     from harmony_b200.parallel.peer import PeerArena, PeerGroup
-    group = PeerGroup.from_env()
+    group = PeerGroup.from_env() if a.impl == "harmony" else PeerGroup(0, 1, None)
     arena = PeerArena(lr, group, segment_bytes=256 << 20)
     conf = TableConfiguration(table_id="model_table0", dense=True, capacity=a.cols, row_dim=a.rank, num_total_blocks=64,
                               backend="device", update_function={"name": "sgd_clamp", "params": {
@@ -51,7 +53,27 @@ def main():
                                 torch.rand(n * k, device=dev, generator=g),
                                 torch.arange(row0, row0 + n, dtype=torch.int32, device=dev), ucols))
 
+    if a.impl == "nccl":
+        import torch.distributed as dist
+        from harmony_b200.ops import native
+        nat = native()
+        R = table.to_dense().contiguous()                      # replicated model [cols, rank]
+        Rp = torch.zeros((a.cols, table.row_stride), device=dev); Rp[:, : a.rank] = R
+        G = torch.zeros_like(Rp)
+        full_cols = [b.ucols[b.col_slot.long()].int() for b in batches]   # slot == column id on the replica
+
+        def step_nccl(i):
+            b = batches[i]
+            G.zero_()
+            nat.nmf_batch(b.csr_ptr, full_cols[i], b.val, model._Lbuf, b.l_row, Rp, G, a.rank, 1e-4, 0.0, 0.0, 1e6,
+                          model.loss)
+            if world > 1:
+                dist.all_reduce(G)
+            Rp.sub_(G, alpha=1e-4).clamp_(0.0, 1e6)
+
     def step(b):
+        if a.impl == "nccl":
+            return step_nccl(batches.index(b))
         clock.wait()
         model.step_batch(b)
         clock.tick()
@@ -71,7 +93,7 @@ def main():
     emit(rank, {"metric": "mini-batches/sec (whole box, device-timed, max over ranks), NMF", "value": round(world * a.steps / (ms / 1e3), 2),
                 "unit": "mini-batches/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "dtype": "fp32",
-                "data": "synthetic", "gpu_launches": ops.launches(),
+                "data": "synthetic", "gpu_launches": ops.launches(), "impl": a.impl,
                 "nnz_per_sec_per_gpu": round(nnz / (ms / a.steps / 1e3), 0),
                 "config": {"model": f"NMF rank {a.rank}, {a.rows_per_gpu * world} x {a.cols} sparse, {a.nnz_per_row} nnz/row",
                            "batch_rows": a.batch_rows, "L_bytes_per_gpu": a.rows_per_gpu * a.rank * 4,

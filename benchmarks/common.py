@@ -42,5 +42,10 @@ def max_over_ranks(x: float, dev, world) -> float:
 
 
 def emit(rank: int, out: dict) -> None:
+    """Print the result line on rank 0, then tear the process group down so nothing follows it on the stream."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
