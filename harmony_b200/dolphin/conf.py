@@ -26,6 +26,7 @@ class ETDolphinConfiguration:
     has_input_data_key: bool = False
     parameters: List[Param] = field(default_factory=list)
     device_trainer_class: Optional[str] = None    # GPU-resident trainer (fused kernels)
+    device_trainer_host_model: bool = False       # the GPU trainer keeps its model in a host table (GBT forest)
 
     @property
     def has_local_model_table(self) -> bool:

@@ -116,6 +116,7 @@ class DolphinJobEntity(JobEntity):
     def worker_params(self) -> Dict[str, Any]:
         p = dict(self.conf)
         p.update({"trainer_class": self.app.trainer_class, "device_trainer_class": self.app.device_trainer_class,
+                  "device_trainer_host_model": self.app.device_trainer_host_model,
                   "model_table_id": self.server_tc.table_id, "input_table_id": self.worker_tc.table_id,
                   "local_model_table_id": self.local_tc.table_id if self.local_tc else None,
                   "data_parser": self.app.input_parser, "app_id": self.app.app_id,

@@ -93,6 +93,7 @@ class ETDolphinLauncher:
             master.create_table(worker_tc, workers).get(timeout=3600)
             params = dict(conf)
             params.update({"trainer_class": app.trainer_class, "device_trainer_class": app.device_trainer_class,
+                           "device_trainer_host_model": app.device_trainer_host_model,
                            "model_table_id": server_tc.table_id, "input_table_id": worker_tc.table_id,
                            "local_model_table_id": local_tc.table_id if local_tc else None,
                            "data_parser": app.input_parser, "app_id": app.app_id, "task_units_enabled": False})

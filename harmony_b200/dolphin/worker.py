@@ -275,7 +275,9 @@ class ModelEvalBarrier:
 # tasklets
 # ------------------------------------------------------------------------------------------
 def build_trainer(context, params: Dict[str, Any], model_table, local_model_table, input_table):
-    is_device = hasattr(model_table, "device_table") and params.get("device_trainer_class")
+    has_gpu = getattr(getattr(context, "executor", None), "device_ctx", None) is not None
+    is_device = bool(params.get("device_trainer_class")) and (
+        hasattr(model_table, "device_table") or (has_gpu and bool(params.get("device_trainer_host_model"))))
     cls = load_class(params["device_trainer_class"] if is_device else params["trainer_class"])
     accessor_cls = CachedModelAccessor if params.get("model_cache_enabled") else ETModelAccessor
     if accessor_cls is CachedModelAccessor:
@@ -308,9 +310,7 @@ class WorkerTasklet(Tasklet):
             ex_ids.index(context.executor.executor_id) if context.executor.executor_id in ex_ids else 0, len(ex_ids),
             context.executor.executor_id, lambda body: context.send_to_driver({"job_id": self.job_id, "dolphin": body}))
         self._trainer_args = (context, p, self.model_table, self.local_model_table, self.input_table)
-        self.trainer, self.accessor = build_trainer(*self._trainer_args)
-        self.data_provider = ETTrainingDataProvider(self.input_table,
-                                                    shuffle=not getattr(self.trainer, "wants_sorted_batches", False))
+        self.trainer = self.accessor = self.data_provider = None
         self.max_epochs = int(p.get("max_num_epochs", 1))
         self.use_task_units = bool(p.get("task_units_enabled", True))
 
@@ -346,6 +346,11 @@ class WorkerTasklet(Tasklet):
 
     def run(self) -> Any:
         ex_id = self.context.executor.executor_id
+        # the trainer is built on the tasklet's own thread, AFTER the runtime registered the tasklet: a trainer
+        # that rendezvouses with its peers in the constructor (ship mode) needs the master's replies routed to it
+        self.trainer, self.accessor = build_trainer(*self._trainer_args)
+        self.data_provider = ETTrainingDataProvider(self.input_table,
+                                                    shuffle=not getattr(self.trainer, "wants_sorted_batches", False))
         self.trainer.init_global_settings()
         self.global_barrier.await_()                       # INIT barrier
         seq = 0
@@ -406,7 +411,7 @@ class WorkerTasklet(Tasklet):
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
         summary = self.trainer.summary()
         self.trainer.cleanup()
-        return {"num_batches": total_batches, "num_epochs": epoch, **summary}
+        return {"num_batches": total_batches, "num_epochs": epoch, "trainer": type(self.trainer).__name__, **summary}
 
     def close(self) -> None:
         self._abort.set()

@@ -218,7 +218,9 @@ def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:
 
 
 APP = ETDolphinConfiguration(app_id="GBT", trainer_class="harmony_b200.mlapps.gbt:GBTTrainer", input_parser="gbt",
-                             model_table_conf=model_table_conf, parameters=P.GBT)
+                             model_table_conf=model_table_conf, parameters=P.GBT,
+                             device_trainer_class="harmony_b200.mlapps.gbt_device:GBTDeviceTrainer",
+                             device_trainer_host_model=True)
 APP_PATH = "harmony_b200.mlapps.gbt:APP"
 
 

@@ -118,7 +118,8 @@ def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:
 
 
 APP = ETDolphinConfiguration(app_id="Lasso", trainer_class="harmony_b200.mlapps.lasso:LassoTrainer",
-                             input_parser="lasso", model_table_conf=model_table_conf)
+                             input_parser="lasso", model_table_conf=model_table_conf,
+                             device_trainer_class="harmony_b200.mlapps.lasso_device:LassoDeviceTrainer")
 APP_PATH = "harmony_b200.mlapps.lasso:APP"
 
 

@@ -77,11 +77,20 @@ class LDADeviceTrainer(Trainer):
         if not data:
             return {"docLLH": 0.0, "wordLLH": 0.0}
         b = self._to_batch(data)
-        rows = self.dtable.pull(b.vocab).cpu().numpy()
-        ndk = self.model.doc_topic_counts(b).cpu().numpy()
-        lens = np.asarray([len(d) for _, d in data], dtype=np.float64)
-        return {"docLLH": doc_llh(ndk, lens, self.K, self.alpha),
-                "wordLLH": word_llh(rows[:-1], rows[-1], self.K, self.V, self.beta)}
+        # K9 on the device: the lgamma sums run over the pulled count rows where they are (k12_ops.cu)
+        import math
+        from ..ops import native
+        nat = native()
+        rows = self.dtable.pull(b.vocab)                                   # [U + 1, stride] int32, last = summary
+        ndk = self.model.doc_topic_counts(b)
+        lens = self._torch.tensor([len(d) for _, d in data], dtype=self._torch.float64, device=rows.device)
+        K, V, a, be = self.K, self.V, self.alpha, self.beta
+        n_words = rows.shape[0] - 1
+        word = K * (math.lgamma(V * be) - V * math.lgamma(be)) + nat.lgamma_sum_i32(rows[:-1], K, be) \
+            + math.lgamma(be) * K * (V - n_words) - nat.lgamma_sum_i32(rows[-1:], K, V * be)
+        doc = len(data) * (math.lgamma(K * a) - K * math.lgamma(a)) + nat.lgamma_sum_i32(ndk, K, a) \
+            - float(self._torch.lgamma(lens + K * a).sum())
+        return {"docLLH": doc, "wordLLH": word}
 
     def cleanup(self) -> None:
         if self.local_table is not None and self._docs:

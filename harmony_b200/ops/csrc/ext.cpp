@@ -60,6 +60,17 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
                        int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout, bool use_2cta);
 void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
                           int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta);
+// k12_ops.cu
+void lasso_cd(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+              at::Tensor Xt, at::Tensor y, double lambda, double step, at::Tensor w_new, at::Tensor w_old,
+              at::Tensor stats);
+void gbt_level(at::Tensor X, at::Tensor order, at::Tensor ftype, at::Tensor node_of, at::Tensor g,
+               int64_t node_base, int64_t num_nodes, int64_t leaf_min, double lam, double gamma, double step,
+               bool allow_split, at::Tensor t_feature, at::Tensor t_thr, at::Tensor t_mask, at::Tensor t_value,
+               at::Tensor t_leaf);
+void gbt_predict(at::Tensor X, at::Tensor t_feature, at::Tensor t_thr, at::Tensor t_mask, at::Tensor t_value,
+                 at::Tensor t_leaf, at::Tensor out);
+double lgamma_sum_i32(at::Tensor x, int64_t cols, double c);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -99,4 +110,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("n_cols"), py::arg("out"), py::arg("dbg") = 0, py::arg("b_lbo") = 0, py::arg("b_sbo") = 0,
         py::arg("idesc_xor") = 0, py::arg("b_layout") = 0, py::arg("use_2cta") = false);
   m.def("mlr_softmax_bcast", &hb::mlr_softmax_bcast);
+  m.def("lasso_cd", &hb::lasso_cd);
+  m.def("gbt_level", &hb::gbt_level);
+  m.def("gbt_predict", &hb::gbt_predict);
+  m.def("lgamma_sum_i32", &hb::lgamma_sum_i32);
 }

@@ -63,3 +63,18 @@ class FailingTrainer:
     def on_epoch_finished(self, e): pass
     def cleanup(self): pass
     def summary(self): return {}
+
+
+class RendezvousTrainer(FailingTrainer):
+    """Trainer whose CONSTRUCTOR gathers an object from every worker of the job through the control-plane group
+    (what the MLR ship mode does with its buffer addresses)."""
+
+    def __init__(self, params, model_accessor, context=None, **kw):
+        super().__init__(params, model_accessor, context=context, **kw)
+        g = context.job_group
+        self.seen = g.all_gather_object((g.rank, context.executor.executor_id), tag="hello")
+
+    def local_compute(self): pass
+
+    def summary(self):
+        return {"group": [list(x) for x in self.seen]}

@@ -192,3 +192,34 @@ def test_control_plane_group_rendezvous():
     [t.start() for t in ts]; [t.join(10) for t in ts]
     for r in range(3):
         assert out[r] == ([{"r": 0}, {"r": 1}, {"r": 2}], [0, 10, 20])
+
+
+def test_trainer_constructor_can_rendezvous_with_its_peers():
+    """Regression: the trainer is built after the tasklet is registered, so the master's group-gather replies reach
+    a trainer that blocks in its constructor (ship-mode MLR exchanges peer buffer addresses there)."""
+    from harmony_b200.dolphin.conf import ETDolphinConfiguration
+    from harmony_b200.dolphin.launcher import parse_job_conf
+    from harmony_b200.jobserver.client import CommandSender
+    from harmony_b200.mlapps import examples
+    import helpers  # noqa: F401
+    import sys
+    app = ETDolphinConfiguration(app_id="Rdv", trainer_class="helpers:RendezvousTrainer", input_parser="example",
+                                 model_table_conf=examples._vec_table, parameters=examples.P.EXAMPLES)
+    sys.modules["rdv_app"] = type(sys)("rdv_app")
+    sys.modules["rdv_app"].APP = app
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 3, "port": port})).start()
+    try:
+        data = examples.write_dummy_input(30)
+        conf = parse_job_conf(app, ["-input", data, "-max_num_epochs", "2", "-num_mini_batches", "6",
+                                    "-num_worker_blocks", "6", "-num_server_blocks", "4", "-num_keys", "4",
+                                    "-port", str(port)]).with_values(
+            job_entity_builder="harmony_b200.dolphin.jobserver:DolphinJobEntityBuilder", app="rdv_app:APP")
+        assert CommandSender(port).send_job_submit_command(conf.serialize()).startswith("true")
+        ok, result = js.driver.wait_job("Rdv-0", timeout=60)
+        assert ok, result
+        for r in result:
+            assert sorted(x[0] for x in r["group"]) == [0, 1, 2]
+            assert sorted(x[1] for x in r["group"]) == ["executor-0", "executor-1", "executor-2"]
+    finally:
+        js.stop(kill=True)

@@ -143,3 +143,128 @@ def test_device_pregel_pagerank_and_sssp(arena):
     for v in range(V):
         assert sp[v] == dist.get(v, 2 ** 31 - 1), v
     eng.close()
+
+
+# ---- K12 / K9: Lasso coordinate descent, GBT split search / prediction, lgamma sums (ops/csrc/k12_ops.cu) ----------
+def test_lasso_cd_kernel_matches_float64_coordinate_descent(arena):
+    from harmony_b200.et.config import TableConfiguration
+    from harmony_b200.et.device_table import DeviceTable
+    from harmony_b200.mlapps.lasso import sthresh
+    from harmony_b200.ops import native
+    F, fpp, B, lam, step = 48, 12, 700, 0.3, 0.5
+    conf = TableConfiguration(table_id="lasso_w", dense=True, capacity=F // fpp, row_dim=fpp, num_total_blocks=4,
+                              is_ordered=False, backend="device",
+                              update_function={"name": "add", "params": {"init": "gaussian", "std": 0.1, "seed": 5}})
+    t = DeviceTable(conf, arena)
+    rng = np.random.default_rng(0)
+    wt = np.zeros(F); wt[[3, 17, 40]] = [2.0, -1.0, 0.7]
+    X = rng.standard_normal((B, F)).astype(np.float32)
+    X[:, 7] = 0.0                                                      # an all-zero column is skipped
+    y = (X @ wt + 0.01 * rng.standard_normal(B)).astype(np.float32)
+    w0 = t.to_dense().reshape(-1).double().cpu().numpy()
+    # float64 reference of the reference algorithm
+    w = w0.copy(); pre = X.astype(np.float64) @ w
+    for j in range(F):
+        if abs(w[j]) < 1e-9:
+            continue
+        col = X[:, j].astype(np.float64); nrm = float(col @ col)
+        if nrm < 1e-9:
+            continue
+        pre -= col * w[j]
+        w[j] = sthresh(float(col @ (y - pre)) / nrm, lam, nrm)
+        pre += col * w[j]
+    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    w_new = torch.zeros(F, device="cuda"); w_old = torch.zeros(F, device="cuda"); stats = torch.zeros(4, device="cuda")
+    native().lasso_cd(*t.view(), Xt, torch.from_numpy(y).cuda(), lam, step, w_new, w_old, stats)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(w_new.cpu().numpy(), w, rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(w_old.cpu().numpy(), w0, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(t.to_dense().reshape(-1).cpu().numpy(), w0 + step * (w - w0), rtol=2e-3, atol=2e-4)
+    assert abs(float(stats[0]) - float(((pre - y) ** 2).mean())) < 1e-3
+    t.close()
+
+
+def _gbt_data(n, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, 5)).astype(np.float32)
+    X[:, 2] = np.round(X[:, 2] * 8) / 8                                # repeated values: equal neighbours are no split
+    X[:, 4] = rng.integers(0, 5, n)                                    # categorical
+    y = 3.0 * (X[:, 0] > 0.5) + 2.0 * X[:, 1] + np.where(X[:, 4] == 2, 1.5, 0.0) + 0.05 * rng.standard_normal(n)
+    return X, y.astype(np.float64)
+
+
+@pytest.mark.parametrize("depth,leaf_min,lam,gamma", [(3, 4, 0.0, 0.0), (5, 2, 1.0, 0.05)])
+def test_gbt_device_tree_matches_cpu_builder(depth, leaf_min, lam, gamma):
+    from harmony_b200.mlapps.gbt import GBTTrainer
+    from harmony_b200.models.gbt import DeviceTreeBuilder
+    X, y = _gbt_data(600, 3)
+    types = {0: 0, 1: 0, 2: 0, 3: 0, 4: 5}
+    cpu = GBTTrainer.__new__(GBTTrainer)
+    cpu.num_features, cpu.types, cpu.lam, cpu.gamma = 5, types, lam, gamma
+    cpu.max_depth, cpu.leaf_min, cpu.step = depth, leaf_min, 0.5
+    ref = cpu._build(X, y)
+    b = DeviceTreeBuilder("cuda:0", 5, types, depth, leaf_min, lam, gamma)
+    Xd = torch.from_numpy(X).cuda()
+    t = b.build(Xd, b.presort(Xd), torch.from_numpy(y).cuda(), 0.5)
+    got = b.to_host_tree(t)
+    np.testing.assert_array_equal(got.is_leaf, ref.is_leaf)
+    np.testing.assert_array_equal(got.feature, ref.feature)
+    np.testing.assert_allclose(got.threshold, ref.threshold, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(got.value, ref.value, rtol=1e-5, atol=1e-6)
+    assert got.categories == ref.categories
+    assert (~ref.is_leaf & (ref.feature >= 0)).sum() >= 3               # a real tree was grown
+    # forest prediction kernel == per-sample host traversal
+    forest = [ref, got]
+    pred = b.predict(Xd, b.pack_forest(forest)).cpu().numpy()
+    np.testing.assert_allclose(pred, sum(tr.predict_many(X) for tr in forest), rtol=1e-6, atol=1e-6)
+
+
+def test_lgamma_sum_kernel():
+    from scipy.special import gammaln
+    from harmony_b200.ops import native
+    x = torch.randint(-3, 500, (777, 40), dtype=torch.int32, device="cuda")
+    got = native().lgamma_sum_i32(x, 33, 0.1)
+    ref = float(gammaln(np.maximum(x[:, :33].cpu().numpy(), 0) + 0.1).sum())
+    assert abs(got - ref) < 1e-6 * abs(ref)
+
+
+def test_lasso_and_gbt_jobs_on_device_backend():
+    """Same scenarios as tests/test_apps_cpu.py, on the device backend (LassoDeviceTrainer / GBTDeviceTrainer)."""
+    from harmony_b200.dolphin.launcher import ETDolphinLauncher
+    from harmony_b200.mlapps import gbt, lasso
+    tmp = tempfile.mkdtemp(prefix="hbk12")
+    rng = np.random.default_rng(1)
+    F = 12
+    w = np.zeros(F); w[[1, 5, 9]] = [2.0, -3.0, 1.5]
+    path = os.path.join(tmp, "sample_lasso")
+    with open(path, "w") as f:
+        for _ in range(200):
+            x = rng.standard_normal(F)
+            f.write(f"{x @ w + 0.01 * rng.standard_normal():.5f} " + " ".join(f"{i}:{v:.5f}" for i, v in enumerate(x)) + "\n")
+    res = ETDolphinLauncher.launch(lasso.APP, ["-input", path, "-max_num_epochs", "10", "-num_mini_batches", "4",
+                                               "-num_worker_blocks", "4", "-num_server_blocks", "2", "-features", str(F),
+                                               "-features_per_partition", "6", "-step_size", "1.0", "-lambda", "0.5",
+                                               "-model_gaussian", "0.1", "-num_dolphin_workers", "1",
+                                               "-num_servers", "0", "-decay_rate", "1.0", "-backend", "device"])
+    assert res.ok and res.results[0]["trainer"] == "LassoDeviceTrainer", res.results
+    assert res.results[0]["last_batch_loss"] < 0.05
+    rng = np.random.default_rng(2)
+    path, meta = os.path.join(tmp, "sample_gbt"), os.path.join(tmp, "sample_gbt.meta")
+    with open(path, "w") as f:
+        for _ in range(240):
+            x = rng.random(4); c = int(rng.integers(0, 3))
+            y = 3.0 * (x[0] > 0.5) + 2.0 * x[1] + (1.5 if c == 2 else 0.0)
+            f.write(f"{y:.4f} " + " ".join(f"{i}:{v:.4f}" for i, v in enumerate(x)) + f" 4:{c}\n")
+    with open(meta, "w") as f:
+        f.write("0:0 1:0 2:0 3:0 4:3 5:0\n")
+    out = {}
+    for epochs in (1, 8):
+        res = ETDolphinLauncher.launch(gbt.APP, ["-input", path, "-max_num_epochs", str(epochs), "-num_mini_batches", "3",
+                                                 "-num_worker_blocks", "3", "-num_server_blocks", "4", "-features", "5",
+                                                 "-step_size", "0.5", "-lambda", "0.0", "-gamma", "0.0",
+                                                 "-max_depth_of_tree", "3", "-leaf_min_size", "4", "-num_keys", "2",
+                                                 "-metadata_path", meta, "-num_dolphin_workers", "1", "-num_servers", "0",
+                                                 "-backend", "device"])
+        assert res.ok and res.results[0]["trainer"] == "GBTDeviceTrainer", res.results
+        out[epochs] = res.results[0]["last_batch_residual_mse"]
+    assert out[8] < 0.3 * out[1], out
