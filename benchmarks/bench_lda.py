@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--doc_len", type=int, default=200)
     ap.add_argument("--distinct_batches", type=int, default=4)
     ap.add_argument("--zipf", type=float, default=1.1)
+    ap.add_argument("--impl", default="harmony", choices=["harmony", "nccl"],
+                    help="nccl: full table replica per GPU, sparse deltas all-gathered and applied everywhere (baseline)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -32,7 +34,7 @@ def main():
     from harmony_b200.models.lda import LDADeviceModel, build_lda_batch
     from harmony_b200.parallel.device_clock import DeviceClock
     from harmony_b200.parallel.peer import PeerArena, PeerGroup
-    group = PeerGroup.from_env()
+    group = PeerGroup.from_env() if a.impl == "harmony" else PeerGroup(0, 1, None)
     arena = PeerArena(lr, group, segment_bytes=1 << 30)
     V, K = a.vocab, a.topics
     conf = TableConfiguration(table_id="model_table0", dense=True, capacity=V + 1, row_dim=K + 1, dtype="int32",
@@ -41,6 +43,19 @@ def main():
     ntok_batch = a.docs_per_batch * a.doc_len
     model = LDADeviceModel(table, K, V, ntok_batch * a.distinct_batches, alpha=0.1, beta=0.01, seed=rank)
     clock = DeviceClock(arena, group)
+    if a.impl == "nccl" and world > 1:
+        import torch.distributed as dist
+
+        def exchange(ok, ot, od, sd):
+            outs = []
+            for t in (ok, ot, od):
+                g = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+                dist.all_gather_into_tensor(g, t.contiguous())
+                outs.append(g)
+            sd = sd.clone()
+            dist.all_reduce(sd)
+            return outs[0], outs[1], outs[2], sd
+        model.exchange = exchange
     rng = np.random.default_rng(7 + rank)
     batches = []
     for i in range(a.distinct_batches):           # word ids follow a Zipf law like real corpora
@@ -71,7 +86,7 @@ def main():
     emit(rank, {"metric": "mini-batches/sec (whole box, device-timed, max over ranks), LDA", "value": round(world * a.steps / (ms / 1e3), 2),
                 "unit": "mini-batches/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": round(ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "dtype": "int32/fp32",
-                "data": "synthetic", "gpu_launches": ops.launches(),
+                "data": "synthetic", "gpu_launches": ops.launches(), "impl": a.impl,
                 "tokens_per_sec_whole_box": round(world * ntok_batch / (ms / a.steps / 1e3), 0),
                 "pull_bytes_per_step_per_gpu": uvoc * table.row_stride * 4,
                 "config": {"model": f"LDA {V}-vocab x {K}-topic (int32 table {(V + 1) * table.row_stride * 4 / 2**30:.2f} GiB sharded)",

@@ -111,7 +111,9 @@ class LassoTrainer(Trainer):
 def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:
     f = int(conf["features"])
     fpp = int(conf.get("features_per_partition", 0) or f)
+    backend = conf.get("backend", "host")
     return TableConfiguration(table_id=table_id, dense=True, capacity=f // fpp, row_dim=fpp,
+                              backend=backend if backend in ("host", "device") else "host",
                               update_function={"name": "add", "params": {"init": "gaussian", "mean": 0.0,
                                                                          "std": float(conf.get("model_gaussian", 0.001)),
                                                                          "seed": 0}})

@@ -47,6 +47,7 @@ class LDADeviceModel:
         self.z = torch.zeros(max(1, n_local_tokens), dtype=torch.int32, device=self.device)
         self.sum_delta = torch.zeros(num_topics, dtype=torch.int32, device=self.device)
         self._iter = 0
+        self.exchange = None       # optional hook (ok, ot, od, sum_delta) -> same, e.g. an all-gather for replicated tables
         self._rows = None
         self._out = None
 
@@ -75,9 +76,12 @@ class LDADeviceModel:
         self._n.lda_sample(b.doc_ptr, b.tok_slot, b.vocab, z_view, rows, nk, self.K, self.alpha, self.beta, self.V,
                            self.seed + 7919 * self._iter, b.tok_lo, ok, ot, od, self.sum_delta, init_mode)
         count_launch()
+        sum_delta = self.sum_delta
+        if self.exchange is not None:
+            ok, ot, od, sum_delta = self.exchange(ok, ot, od, sum_delta)
         self.table.push_sparse_i32(ok, ot, od)                          # word-topic deltas -> owners
         kk = torch.full((self.K,), self.V, dtype=torch.int64, device=self.device)
-        self.table.push_sparse_i32(kk, torch.arange(self.K, dtype=torch.int32, device=self.device), self.sum_delta)
+        self.table.push_sparse_i32(kk, torch.arange(self.K, dtype=torch.int32, device=self.device), sum_delta)
 
     def doc_topic_counts(self, b: LDABatch) -> torch.Tensor:
         nd = b.doc_ptr.numel() - 1

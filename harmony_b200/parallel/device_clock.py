@@ -32,7 +32,7 @@ class DeviceClock:
         self.clocks = arena.tensor(self._ptr, [self.world], torch.int32)
         self.clocks.zero_()
         torch.cuda.synchronize(self.device)
-        infos = self.group.all_gather_object((self.rank, si, off, arena.segment_handle(si)))
+        infos = self.group.all_gather_object((self.rank, si, off, arena.segment_info(si)))
         ptrs = [0] * self.world
         for r, s, o, h in infos:
             arena.map_peer(r, s, h)
