@@ -4,44 +4,8 @@ import os
 import numpy as np
 
 
-def write_mlr_sample(path, n=200, features=64, classes=4, nnz=8, seed=0):
-    rng = np.random.default_rng(seed)
-    Wtrue = rng.standard_normal((features, classes))
-    with open(path, "w") as f:
-        f.write("# synthetic mlr sample\n")
-        for _ in range(n):
-            idx = np.sort(rng.choice(features, nnz, replace=False))
-            val = rng.random(nnz).astype(np.float32) + 0.5
-            label = int(np.argmax(val @ Wtrue[idx]))
-            f.write(str(label) + " " + " ".join(f"{i}:{v:.4f}" for i, v in zip(idx, val)) + "\n")
-    return path
-
-
-def write_nmf_sample(path, rows=60, cols=40, rank=4, density=0.3, seed=0):
-    rng = np.random.default_rng(seed)
-    L, R = rng.random((rows, rank)), rng.random((rank, cols))
-    D = L @ R
-    with open(path, "w") as f:
-        f.write("# synthetic nmf sample\n")
-        for i in range(rows):
-            cs = np.flatnonzero(rng.random(cols) < density)
-            if len(cs) == 0:
-                cs = np.array([rng.integers(cols)])
-            f.write(f"{i + 1}: " + " ".join(f"{c + 1},{D[i, c]:.4f}" for c in cs) + "\n")
-    return path
-
-
-def write_lda_sample(path, docs=60, vocab=50, topics=3, doc_len=30, seed=0):
-    rng = np.random.default_rng(seed)
-    phi = rng.dirichlet(np.full(vocab, 0.05), topics)
-    with open(path, "w") as f:
-        f.write("# synthetic lda sample\n")
-        for _ in range(docs):
-            theta = rng.dirichlet(np.full(topics, 0.3))
-            z = rng.choice(topics, doc_len, p=theta)
-            ws = [rng.choice(vocab, p=phi[t]) for t in z]
-            f.write(" ".join(str(w) for w in ws) + "\n")
-    return path
+from harmony_b200.common.samples import (write_gbt_sample, write_lasso_sample, write_lda_sample,  # noqa: F401,E402
+                                         write_mlr_sample, write_nmf_sample)
 
 
 class FailingTrainer:

@@ -1,5 +1,6 @@
 """Utility layer (reference: utils/src/test DAGImplTest, LongRangeUtilsTest; StateMachine; Tang flags)."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -109,3 +110,24 @@ def test_linalg_vector_matrix_api():
     assert sp.transpose().mmul(vf.create_dense([1, 1, 1])).t.tolist() == [4, 4]
     m.put_row(0, vf.create_dense([0, 0, 0])); m.addi(1).muli(2)
     assert m.t.tolist() == [[2, 2, 2], [6, 10, 14]]
+
+
+def test_sample_generator_writes_every_launch_script_input(tmp_path):
+    """bin/make_samples.sh equivalents of the reference's sample files, parseable by the registered parsers."""
+    from harmony_b200.common.dataloader import make_parser
+    from harmony_b200.common.samples import write_all
+    import harmony_b200.mlapps.gbt, harmony_b200.mlapps.lasso, harmony_b200.mlapps.lda  # noqa: F401,E401
+    import harmony_b200.mlapps.mlr, harmony_b200.mlapps.nmf, harmony_b200.pregel.graph  # noqa: F401,E401
+    d = write_all(str(tmp_path))
+    for name, parser, n in [("sample_mlr", "mlr", 1000), ("sample_mlr_test", "mlr", 200), ("sample_nmf", "nmf", 250),
+                            ("sample_lda", "lda", 200), ("sample_lasso", "lasso", 200), ("sample_gbt", "gbt", 160),
+                            ("inputs/adj_list", "graph_none_edge_value", 40), ("inputs/shortest_path", "graph", 40)]:
+        p = make_parser(parser)
+        with open(os.path.join(d, name)) as f:
+            recs = [p.parse_line(ln) for ln in f if ln.strip() and not ln.startswith("#")]
+        assert len(recs) == n, name
+    from harmony_b200.mlapps.gbt import read_metadata
+    types, ytype = read_metadata(os.path.join(d, "sample_gbt.meta"), 784)
+    assert ytype == 0 and len(types) == 784
+    from harmony_b200.dolphin.optimizer import parse_host_to_value_file
+    assert parse_host_to_value_file(os.path.join(d, "sample_host_to_bandwidth"))["localhost"] > 1e12
