@@ -102,7 +102,7 @@ class TaskletRuntime:
     def _run(self, tasklet_id: str, tasklet: Tasklet) -> None:
         self._status(tasklet_id, "Running")
         try:
-            result = tasklet.run()
+            result = self._run_on_device_stream(tasklet)
             self._status(tasklet_id, "Done", result=result)
         except BaseException as e:  # noqa: BLE001
             LOG.error("tasklet %s failed:\n%s", tasklet_id, traceback.format_exc())
@@ -110,6 +110,18 @@ class TaskletRuntime:
         finally:
             with self._lock:
                 self._tasklets.pop(tasklet_id, None)
+
+    def _run_on_device_stream(self, tasklet: Tasklet) -> Any:
+        ctx = getattr(self._ex, "device_ctx", None)
+        if ctx is None:
+            return tasklet.run()
+        import torch
+        stream = ctx.tasklet_stream()
+        with torch.cuda.device(ctx.device), torch.cuda.stream(stream):
+            try:
+                return tasklet.run()
+            finally:
+                stream.synchronize()
 
     def stop_tasklet(self, tasklet_id: str) -> None:
         with self._lock:

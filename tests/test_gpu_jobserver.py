@@ -174,7 +174,7 @@ def test_mlr_ship_mode_inside_job_server():
                     "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
                     "-mlr_mode", mode, "-port", str(port)]
             assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
-            ok, result = js.driver.wait_job(f"MLR-{i}", timeout=120)
+            ok, result = js.driver.wait_job(f"MLR-{i}", timeout=60)
             assert ok, result
             losses[mode] = np.mean([r["last_batch_loss"] / 64.0 for r in result])
         assert losses["ship"] < 1.30 and abs(losses["ship"] - losses["pull"]) < 0.25, losses
