@@ -17,6 +17,7 @@
 namespace hb {
 
 static constexpr int LDA_WARPS = 4;
+static constexpr int LDA_UNROLL = 4;      // 128-bit row loads in flight per lane
 
 __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
     const int* __restrict__ doc_ptr, const int* __restrict__ tok_slot, const long long* __restrict__ slot_key,
@@ -26,11 +27,13 @@ __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
     int* __restrict__ sum_delta, int init_mode) {
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int* ndk = reinterpret_cast<int*>(smem_raw) + (size_t)wid * K;
-  float* pk = reinterpret_cast<float*>(smem_raw + (size_t)LDA_WARPS * K * sizeof(int)) + (size_t)wid * K;
+  const int Kp = (K + 3) & ~3;             // per-warp arrays padded to whole 128-bit groups
+  const int K4 = Kp >> 2;
+  int* ndk = reinterpret_cast<int*>(smem_raw) + (size_t)wid * Kp;
+  float* pk = reinterpret_cast<float*>(smem_raw + (size_t)LDA_WARPS * Kp * sizeof(int)) + (size_t)wid * Kp;
   for (int d = blockIdx.x * LDA_WARPS + wid; d < n_docs; d += gridDim.x * LDA_WARPS) {
     const int beg = doc_ptr[d], end = doc_ptr[d + 1];
-    for (int k = lane; k < K; k += 32) ndk[k] = 0;
+    for (int k = lane; k < Kp; k += 32) ndk[k] = 0;
     __syncwarp();
     if (!init_mode) {
       for (int t = beg + lane; t < end; t += 32) atomicAdd(&ndk[z[t]], 1);
@@ -47,17 +50,46 @@ __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
         old = z[t];
         if (lane == 0) ndk[old] -= 1;
         __syncwarp();
+        // Every lane owns the topic groups g = lane, lane + 32, ... (4 consecutive topics per 128-bit load).  The loads
+        // of LDA_UNROLL groups are issued before any of them is consumed: the row comes from L2 / HBM (the batch
+        // staging buffer), so memory-level parallelism -- not arithmetic -- bounds the per-token latency.
         float lsum = 0.f;
-        for (int k = lane; k < K; k += 32) {
-          const int own = (k == old) ? 1 : 0;
-          const float a = (float)ndk[k] + alpha;
-          const float b = (float)max(row[k] - own, 0) + beta;
-          const float c = (float)max(nk[k] - own, 0) + vbeta;
-          const float p = a * b / c;
-          pk[k] = p;
-          lsum += p;
+        const int4* row4 = reinterpret_cast<const int4*>(row);
+        const int4* nk4 = reinterpret_cast<const int4*>(nk);
+        const int4* ndk4 = reinterpret_cast<const int4*>(ndk);
+        float4* pk4 = reinterpret_cast<float4*>(pk);
+        for (int g0 = lane; g0 < K4; g0 += 32 * LDA_UNROLL) {
+          int4 r[LDA_UNROLL], n[LDA_UNROLL];
+#pragma unroll
+          for (int u = 0; u < LDA_UNROLL; ++u) {
+            const int g = g0 + 32 * u;
+            if (g < K4) { r[u] = row4[g]; n[u] = nk4[g]; }
+          }
+#pragma unroll
+          for (int u = 0; u < LDA_UNROLL; ++u) {
+            const int g = g0 + 32 * u;
+            if (g < K4) {
+              const int4 dk = ndk4[g];
+              const int k0 = 4 * g;
+              const int rr[4] = {r[u].x, r[u].y, r[u].z, r[u].w};
+              const int nn[4] = {n[u].x, n[u].y, n[u].z, n[u].w};
+              const int dd[4] = {dk.x, dk.y, dk.z, dk.w};
+              float pp[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j;
+                const int own = (k == old) ? 1 : 0;
+                const float a = (float)dd[j] + alpha;
+                const float b = (float)max(rr[j] - own, 0) + beta;
+                const float c = (float)max(nn[j] - own, 0) + vbeta;
+                pp[j] = (k < K) ? __fdividef(a * b, c) : 0.f;
+                lsum += pp[j];
+              }
+              pk4[g] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+            }
+          }
         }
-        // inclusive scan of the lane sums (lane-major topic order)
+        // inclusive scan of the lane sums (lane-major group order)
         float incl = lsum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -72,10 +104,18 @@ __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
         if (lane == src_lane) {
           float acc = incl - lsum;
           cand = -1;
-          for (int k = lane; k < K; k += 32) {
-            acc += pk[k];
-            cand = k;
-            if (acc > u) break;
+          bool done = false;
+          for (int g = lane; g < K4 && !done; g += 32) {
+            const float4 q = pk4[g];
+            const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!done) {
+                acc += qq[j];
+                if (qq[j] > 0.f) cand = 4 * g + j;      // never land on a zero-probability (or padding) topic
+                if (acc > u) done = true;
+              }
+            }
           }
           if (cand < 0) cand = old;
         }
@@ -111,7 +151,10 @@ void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at
   TORCH_CHECK(doc_ptr.scalar_type() == at::kInt && tok_slot.scalar_type() == at::kInt && z.scalar_type() == at::kInt);
   TORCH_CHECK(slot_key.scalar_type() == at::kLong && out_keys.scalar_type() == at::kLong);
   TORCH_CHECK(nwk.scalar_type() == at::kInt && nk.scalar_type() == at::kInt && nwk.stride(1) == 1);
-  const size_t smem = (size_t)LDA_WARPS * K * (sizeof(int) + sizeof(float));
+  const size_t smem = (size_t)LDA_WARPS * ((K + 3) & ~3) * (sizeof(int) + sizeof(float));
+  TORCH_CHECK(nwk.stride(0) % 4 == 0 && reinterpret_cast<uintptr_t>(nwk.data_ptr<int>()) % 16 == 0 &&
+              reinterpret_cast<uintptr_t>(nk.data_ptr<int>()) % 16 == 0 && nwk.stride(0) >= ((K + 3) & ~3),
+              "lda_sample: count rows must be 16-byte aligned and padded to whole int4 groups");
   TORCH_CHECK(smem <= 200 * 1024, "num_topics too large for the shared-memory sampler");
   // per-device attribute: set on every launch (executors of one process may drive different GPUs)
   cudaFuncSetAttribute(lda_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
