@@ -17,7 +17,7 @@
 namespace hb {
 
 static constexpr int LDA_WARPS = 4;
-static constexpr int LDA_UNROLL = 4;      // 128-bit row loads in flight per lane
+static constexpr int LDA_UNROLL = 8;      // 128-bit row loads in flight per lane
 
 __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
     const int* __restrict__ doc_ptr, const int* __restrict__ tok_slot, const long long* __restrict__ slot_key,
@@ -39,15 +39,35 @@ __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
       for (int t = beg + lane; t < end; t += 32) atomicAdd(&ndk[z[t]], 1);
     }
     __syncwarp();
-    for (int t = beg; t < end; ++t) {
-      const int slot = tok_slot[t];
+    // Tokens are processed in chunks of 32: lane l fetches the slot / old topic / key of token cb + l up front (one
+    // round of global latency per 32 tokens instead of three dependent loads per token), the per-token loop gets them
+    // by shuffle, prefetches the NEXT token's count row into L2 (one 128 B line per lane) and the chunk's outputs are
+    // written back coalesced, one token per lane.
+    for (int cb = beg; cb < end; cb += 32) {
+     const int tl = cb + lane;
+     int slot_l = 0, old_l = -1, nw_l = 0;
+     long long key_l = 0;
+     if (tl < end) {
+       slot_l = tok_slot[tl];
+       key_l = slot_key[slot_l];
+       if (!init_mode) old_l = z[tl];
+     }
+     const int cnt = min(32, end - cb);
+     for (int i = 0; i < cnt; ++i) {
+      const int t = cb + i;
+      const int slot = __shfl_sync(0xffffffffu, slot_l, i);
       const int* row = nwk + (size_t)slot * nwk_stride;
+      if (!init_mode && i + 1 < cnt) {
+        const int ns = __shfl_sync(0xffffffffu, slot_l, i + 1);
+        if (lane * 32 < nwk_stride)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nwk + (size_t)ns * nwk_stride + lane * 32));
+      }
       int old = -1, nw;
       if (init_mode) {
         // initial uniformly random assignment
         nw = (int)(rng_u32(seed, (unsigned long long)(tok_base + t)) % (unsigned)K);
       } else {
-        old = z[t];
+        old = __shfl_sync(0xffffffffu, old_l, i);
         if (lane == 0) ndk[old] -= 1;
         __syncwarp();
         // Every lane owns the topic groups g = lane, lane + 32, ... (4 consecutive topics per 128-bit load).  The loads
@@ -121,21 +141,22 @@ __global__ void __launch_bounds__(LDA_WARPS * 32) lda_sample_kernel(
         }
         nw = __shfl_sync(0xffffffffu, cand, src_lane);
       }
-      if (lane == 0) {
-        ndk[nw] += 1;
-        z[t] = nw;
-        const long long key = slot_key[slot];
-        const int changed = (nw != old) ? 1 : 0;
-        out_keys[2 * (size_t)t] = key;      out_topics[2 * (size_t)t] = (old >= 0) ? old : 0;
-        out_deltas[2 * (size_t)t] = (old >= 0 && changed) ? -1 : 0;
-        out_keys[2 * (size_t)t + 1] = key;  out_topics[2 * (size_t)t + 1] = nw;
-        out_deltas[2 * (size_t)t + 1] = changed;
-        if (changed) {
-          if (old >= 0) atomicAdd(sum_delta + old, -1);
-          atomicAdd(sum_delta + nw, 1);
-        }
-      }
+      if (lane == 0) ndk[nw] += 1;
+      if (lane == i) nw_l = nw;
       __syncwarp();
+     }
+     if (tl < end) {
+       const int changed = (nw_l != old_l) ? 1 : 0;
+       z[tl] = nw_l;
+       out_keys[2 * (size_t)tl] = key_l;      out_topics[2 * (size_t)tl] = (old_l >= 0) ? old_l : 0;
+       out_deltas[2 * (size_t)tl] = (old_l >= 0 && changed) ? -1 : 0;
+       out_keys[2 * (size_t)tl + 1] = key_l;  out_topics[2 * (size_t)tl + 1] = nw_l;
+       out_deltas[2 * (size_t)tl + 1] = changed;
+       if (changed) {
+         if (old_l >= 0) atomicAdd(sum_delta + old_l, -1);
+         atomicAdd(sum_delta + nw_l, 1);
+       }
+     }
     }
   }
 }
