@@ -81,6 +81,27 @@ def get_splits(path: str, num_splits: int) -> List[SplitInfo]:
     return splits
 
 
+NATIVE_PARSE_MIN_BYTES = 1 << 12
+
+
+def read_split_bytes(split: SplitInfo) -> bytes:
+    """The bytes of the lines whose FIRST byte lies inside [start, start+length)."""
+    if split.length == 0:
+        return b""
+    with open(strip_scheme(split.path), "rb") as f:
+        end = split.start + split.length
+        if split.start > 0:
+            f.seek(split.start - 1)
+            f.readline()
+        pos = f.tell()
+        if pos >= end:
+            return b""
+        data = f.read(end - pos)
+        if not data.endswith(b"\n"):
+            data += f.readline()          # the last line starts inside the split: it belongs to it entirely
+        return data
+
+
 def read_split(split: SplitInfo) -> Iterator[str]:
     """Lines whose FIRST byte lies inside [start, start+length) (Hadoop line-record semantics)."""
     if split.length == 0:
@@ -104,9 +125,28 @@ def read_split(split: SplitInfo) -> Iterator[str]:
 # ------------------------------------------------------------------------------------------
 class DataParser:
     has_key = False
+    native_mode: Optional[int] = None      # ops/csrc/loader.cpp format id (0 `y i:v`, 1 `r: c,v`, 2 `w w w`)
 
     def __init__(self, **params: Any) -> None:
         self.params = params
+
+    def parse_bytes(self, data: bytes) -> List[Any]:
+        """Parse a whole byte range.  Sparse text formats go through the multi-threaded native parser
+        (ops/csrc/loader.cpp) when the extension is built; otherwise line by line in Python."""
+        if self.native_mode is not None and len(data) >= NATIVE_PARSE_MIN_BYTES:
+            from ..ops import native_or_none
+            nat = native_or_none()
+            if nat is not None:
+                try:
+                    head, ptr, idx, val = nat.parse_sparse_text(data, self.native_mode, os.cpu_count() or 4)
+                except ValueError as e:
+                    raise ValueError(f"{type(self).__name__}: {e}") from None
+                return self.from_arrays(head.numpy(), ptr.numpy(), idx.numpy(), val.numpy())
+        return self.parse(data.decode("utf-8", errors="replace").splitlines())
+
+    def from_arrays(self, head, ptr, idx, val) -> List[Any]:
+        """Records from the native parser's (head[n], ptr[n+1], idx[nnz], val[nnz]) arrays."""
+        raise NotImplementedError
 
     def parse(self, lines: Iterable[str]) -> List[Any]:
         out = []
@@ -198,7 +238,7 @@ def run_bulk_load(executor, table_id: str, file_splits: Sequence[Dict[str, Any]]
     total = 0
     keygen = LocalKeyGenerator(comps)
     for sd in file_splits:
-        records = parser.parse(read_split(SplitInfo.from_dict(sd)))
+        records = parser.parse_bytes(read_split_bytes(SplitInfo.from_dict(sd)))
         if not records:
             continue
         if comps.conf.bulk_loader == "exist_key" or parser.has_key:

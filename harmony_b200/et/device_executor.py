@@ -40,9 +40,10 @@ class DeviceContext:
         import torch
         from ..parallel.peer import PeerArena, PeerGroup
         self.device = int(device)
-        torch.cuda.set_device(self.device)
-        self.arena = PeerArena(self.device, PeerGroup(), segment_bytes=segment_bytes, self_key=executor_id)
-        self.side_stream = torch.cuda.Stream(device=self.device)
+        # scoped: the creating thread (a launcher / test thread that also drives other GPUs) keeps its own device
+        with torch.cuda.device(self.device):
+            self.arena = PeerArena(self.device, PeerGroup(), segment_bytes=segment_bytes, self_key=executor_id)
+            self.side_stream = torch.cuda.Stream(device=self.device)
         self.torch_device = torch.device("cuda", self.device)
 
     def tasklet_stream(self):

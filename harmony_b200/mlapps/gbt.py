@@ -26,6 +26,11 @@ from ..utils.flags import Configuration
 
 
 class GBTDataParser(DataParser):
+    native_mode = 0
+
+    def from_arrays(self, head, ptr, idx, val):
+        return [(idx[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]], float(head[i])) for i in range(len(head))]
+
     def parse_line(self, line: str):
         toks = line.replace(":", " ").split()
         y = float(toks[0])

@@ -23,6 +23,11 @@ CLOSE_TO_ZERO = 1e-9
 
 
 class LassoDataParser(DataParser):
+    native_mode = 0
+
+    def from_arrays(self, head, ptr, idx, val):
+        return [(idx[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]], float(head[i])) for i in range(len(head))]
+
     def parse_line(self, line: str):
         parts = line.split()
         y = float(parts[0])

@@ -29,6 +29,11 @@ LOG = logging.getLogger(__name__)
 
 
 class LDADataParser(DataParser):
+    native_mode = 2
+
+    def from_arrays(self, head, ptr, idx, val):
+        return [idx[ptr[i]:ptr[i + 1]] for i in range(len(head))]
+
     def parse_line(self, line: str):
         return np.asarray([int(t) for t in line.split()], dtype=np.int32)
 

@@ -32,6 +32,15 @@ ZERO_THRESHOLD = 1e-7
 
 class MLRDataParser(DataParser):
     """`label idx:val idx:val ...` -> (idx int32[], val float32[], label)."""
+    native_mode = 0
+
+    def from_arrays(self, head, ptr, idx, val):
+        labels = head.astype(np.int64)
+        nc = self.params.get("classes")
+        bad = (labels < 0) | ((labels >= int(nc)) if nc else False)
+        if np.any(bad):
+            raise ValueError(f"label {int(labels[np.argmax(bad)])} out of range")
+        return [(idx[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]], int(labels[i])) for i in range(len(labels))]
 
     def parse_line(self, line: str):
         parts = line.split()

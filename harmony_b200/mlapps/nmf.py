@@ -29,6 +29,11 @@ LOG = logging.getLogger(__name__)
 
 class NMFDataParser(DataParser):
     """`rowIdx: col,val col,val ...` (1-based) -> (row, cols int32 0-based, vals float32)."""
+    native_mode = 1
+
+    def from_arrays(self, head, ptr, idx, val):
+        rows = head.astype(np.int64) - 1
+        return [(int(rows[i]), idx[ptr[i]:ptr[i + 1]], val[ptr[i]:ptr[i + 1]]) for i in range(len(rows))]
 
     def parse_line(self, line: str):
         head, _, rest = line.partition(":")

@@ -26,6 +26,8 @@ class DeviceTreeBuilder:
         from ..ops import native
         self._n = native()
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.F, self.max_depth, self.leaf_min = int(num_features), int(max_depth), int(leaf_min)
         self.lam, self.gamma = float(lam), float(gamma)
         if any(v > 63 for v in types.values()):
@@ -34,12 +36,20 @@ class DeviceTreeBuilder:
                                   device=self.device)
         self.nodes = 2 ** (self.max_depth + 1) - 1
 
+    def _check(self, *tensors: torch.Tensor) -> None:
+        for t in tensors:
+            if t.device != self.device:
+                raise ValueError(f"tensor on {t.device}, builder on {self.device}: kernels of one tree must run on "
+                                 "one GPU's stream")
+
     def presort(self, X: torch.Tensor) -> torch.Tensor:
         """X [n, F] float32 on the device -> per-feature stable argsort [F, n] int32."""
+        self._check(X)
         return torch.sort(X, dim=0, stable=True).indices.t().contiguous().to(torch.int32)
 
     def build(self, X: torch.Tensor, order: torch.Tensor, g: torch.Tensor, step: float) -> Dict[str, torch.Tensor]:
         """Grow one tree on residuals g [n] float64.  Returns the tree arrays (device tensors, complete-tree ids)."""
+        self._check(X, order, g)
         n = X.shape[0]
         dev = self.device
         t = {"feature": torch.full((self.nodes,), -1, dtype=torch.int32, device=dev),
@@ -56,6 +66,7 @@ class DeviceTreeBuilder:
 
     def predict(self, X: torch.Tensor, forest: Dict[str, torch.Tensor]) -> torch.Tensor:
         """forest: stacked [T, nodes] arrays -> float64 [n] sum of the trees' leaf values."""
+        self._check(X)
         out = torch.zeros(X.shape[0], dtype=torch.float64, device=self.device)
         if forest["feature"].numel():
             self._n.gbt_predict(X, forest["feature"], forest["thr"], forest["mask"], forest["value"],

@@ -61,6 +61,13 @@ def build_batch(csr_ptr: np.ndarray, csr_col: np.ndarray, csr_val: np.ndarray, l
     csr_col = np.asarray(csr_col, dtype=np.int32)
     csr_val = np.asarray(csr_val, dtype=np.float32)
     labels = np.asarray(labels, dtype=np.int32)
+    t = torch.from_numpy
+    from ..ops import native_or_none
+    nat = native_or_none()
+    if nat is not None:        # counting sort in the native runtime (ops/csrc/loader.cpp); NumPy twin below
+        uniq, feat_ptr, samp, xval = nat.group_by_feature(t(np.ascontiguousarray(csr_ptr)), t(np.ascontiguousarray(csr_col)),
+                                                          t(np.ascontiguousarray(csr_val)))
+        return MLRBatch(t(csr_ptr), t(csr_col), t(csr_val), t(labels), uniq, feat_ptr, samp, xval)
     B = len(labels)
     rows = np.repeat(np.arange(B, dtype=np.int32), np.diff(csr_ptr))
     order = np.argsort(csr_col, kind="stable")

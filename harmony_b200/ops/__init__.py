@@ -18,6 +18,17 @@ def native_available() -> bool:
     return _build.available()
 
 
+def native_or_none():
+    """The extension if it is built and loadable, else None -- for the HOST-side helpers (text parsers, batch
+    grouping) that have a NumPy twin.  The device data plane uses `native()` and never falls back."""
+    if not _build.available():
+        return None
+    try:
+        return _build.load()
+    except (ImportError, OSError):
+        return None
+
+
 def count_launch(n: int = 1) -> None:
     global _LAUNCHES
     _LAUNCHES += n

@@ -33,6 +33,21 @@ struct Arena {
   std::mutex mu;
 };
 
+// Switch the calling thread to `device` for one scope and put it back afterwards: these entry points are called
+// from threads that drive OTHER GPUs too (in-process executors, tests), and a leaked cudaSetDevice silently
+// redirects the caller's later `.cuda()` allocations and raw-pointer launches to the wrong GPU.
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device) {
+    cudaGetDevice(&prev);
+    if (prev != device) HB_CUDA_CHECK(cudaSetDevice(device));
+    else prev = -1;
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 static std::map<int64_t, Arena*> g_arenas;
 static std::mutex g_mu;
 
@@ -41,7 +56,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int64_t arena_create(int64_t device, int64_t bytes) {
   auto* a = new Arena();
   a->device = (int)device;
-  HB_CUDA_CHECK(cudaSetDevice((int)device));
+  DeviceScope scope((int)device);
   a->capacity = align_up((size_t)bytes, 2u << 20);
   HB_CUDA_CHECK(cudaMalloc((void**)&a->base, a->capacity));
   std::lock_guard<std::mutex> g(g_mu);
@@ -108,8 +123,10 @@ void arena_destroy(int64_t id) {
     a = it->second;
     g_arenas.erase(it);
   }
-  cudaSetDevice(a->device);
-  cudaFree(a->base);
+  {
+    DeviceScope scope(a->device);
+    cudaFree(a->base);
+  }
   delete a;
 }
 
@@ -124,7 +141,7 @@ int64_t ipc_open(std::string handle_bytes, int64_t device) {
   TORCH_CHECK(handle_bytes.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle_bytes.data(), sizeof(h));
-  HB_CUDA_CHECK(cudaSetDevice((int)device));
+  DeviceScope scope((int)device);
   void* p = nullptr;
   HB_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
   return reinterpret_cast<int64_t>(p);
@@ -138,7 +155,7 @@ bool enable_peer_access(int64_t device, int64_t peer) {
   int can = 0;
   HB_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, (int)device, (int)peer));
   if (!can) return false;
-  HB_CUDA_CHECK(cudaSetDevice((int)device));
+  DeviceScope scope((int)device);
   cudaError_t e = cudaDeviceEnablePeerAccess((int)peer, 0);
   if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return true; }
   HB_CUDA_CHECK(e);

@@ -71,6 +71,11 @@ void gbt_level(at::Tensor X, at::Tensor order, at::Tensor ftype, at::Tensor node
 void gbt_predict(at::Tensor X, at::Tensor t_feature, at::Tensor t_thr, at::Tensor t_mask, at::Tensor t_value,
                  at::Tensor t_leaf, at::Tensor out);
 double lgamma_sum_i32(at::Tensor x, int64_t cols, double c);
+// loader.cpp (host runtime)
+std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> parse_sparse_text(const std::string& text, int64_t mode,
+                                                                              int64_t threads);
+std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> group_by_feature(at::Tensor csr_ptr, at::Tensor csr_col,
+                                                                             at::Tensor csr_val);
 }  // namespace hb
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -114,4 +119,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gbt_level", &hb::gbt_level);
   m.def("gbt_predict", &hb::gbt_predict);
   m.def("lgamma_sum_i32", &hb::lgamma_sum_i32);
+  m.def("parse_sparse_text", &hb::parse_sparse_text, py::arg("text"), py::arg("mode"), py::arg("threads") = 8);
+  m.def("group_by_feature", &hb::group_by_feature);
 }

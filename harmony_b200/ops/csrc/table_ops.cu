@@ -333,8 +333,18 @@ void table_push_scalar_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// Raw-pointer entry points launch on the GPU that OWNS the memory, not on whatever device the calling thread
+// happens to be on (a peer GPU could write it over NVLink, but un-ordered with the owner's streams).
+static c10::DeviceIndex device_of_ptr(int64_t ptr) {
+  cudaPointerAttributes attr;
+  C10_CUDA_CHECK(cudaPointerGetAttributes(&attr, reinterpret_cast<const void*>(ptr)));
+  TORCH_CHECK(attr.type == cudaMemoryTypeDevice, "expected a device pointer");
+  return (c10::DeviceIndex)attr.device;
+}
+
 void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_dim, int64_t kind, double a,
                double b, int64_t seed, int64_t row_key_base, int64_t key_stride) {
+  c10::cuda::CUDAGuard guard(device_of_ptr(slab_ptr));
   auto stream = at::cuda::getCurrentCUDAStream();
   long long total = rows * row_stride;
   if (total == 0) return;
@@ -346,6 +356,7 @@ void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_d
 }
 
 void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes) {
+  c10::cuda::CUDAGuard guard(device_of_ptr(dst_ptr));      // the receiver pulls the block over NVLink
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(nbytes % 16 == 0 && src_ptr % 16 == 0 && dst_ptr % 16 == 0, "migration needs 16B alignment");
   long long n_vec = nbytes / 16;

@@ -27,3 +27,14 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip_gpu)
         if "multigpu" in item.keywords and n_gpu < 2:
             item.add_marker(skip_multi)
+
+
+@pytest.fixture(autouse=True)
+def _gpu_test_starts_on_device0(request):
+    """GPU tests build tensors with `device="cuda"`: start every one of them on device 0 whatever a previous test
+    (multi-executor jobs drive several GPUs from this process) left as the thread's current device."""
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(0)
+    yield

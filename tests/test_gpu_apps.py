@@ -173,9 +173,10 @@ def test_lasso_cd_kernel_matches_float64_coordinate_descent(arena):
         pre -= col * w[j]
         w[j] = sthresh(float(col @ (y - pre)) / nrm, lam, nrm)
         pre += col * w[j]
-    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
-    w_new = torch.zeros(F, device="cuda"); w_old = torch.zeros(F, device="cuda"); stats = torch.zeros(4, device="cuda")
-    native().lasso_cd(*t.view(), Xt, torch.from_numpy(y).cuda(), lam, step, w_new, w_old, stats)
+    dev = t.device
+    Xt = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+    w_new = torch.zeros(F, device=dev); w_old = torch.zeros(F, device=dev); stats = torch.zeros(4, device=dev)
+    native().lasso_cd(*t.view(), Xt, torch.from_numpy(y).to(dev), lam, step, w_new, w_old, stats)
     torch.cuda.synchronize()
     np.testing.assert_allclose(w_new.cpu().numpy(), w, rtol=2e-3, atol=2e-4)
     np.testing.assert_allclose(w_old.cpu().numpy(), w0, rtol=1e-6, atol=1e-7)
@@ -204,8 +205,8 @@ def test_gbt_device_tree_matches_cpu_builder(depth, leaf_min, lam, gamma):
     cpu.max_depth, cpu.leaf_min, cpu.step = depth, leaf_min, 0.5
     ref = cpu._build(X, y)
     b = DeviceTreeBuilder("cuda:0", 5, types, depth, leaf_min, lam, gamma)
-    Xd = torch.from_numpy(X).cuda()
-    t = b.build(Xd, b.presort(Xd), torch.from_numpy(y).cuda(), 0.5)
+    Xd = torch.from_numpy(X).to("cuda:0")
+    t = b.build(Xd, b.presort(Xd), torch.from_numpy(y).to("cuda:0"), 0.5)
     got = b.to_host_tree(t)
     np.testing.assert_array_equal(got.is_leaf, ref.is_leaf)
     np.testing.assert_array_equal(got.feature, ref.feature)
@@ -222,7 +223,7 @@ def test_gbt_device_tree_matches_cpu_builder(depth, leaf_min, lam, gamma):
 def test_lgamma_sum_kernel():
     from scipy.special import gammaln
     from harmony_b200.ops import native
-    x = torch.randint(-3, 500, (777, 40), dtype=torch.int32, device="cuda")
+    x = torch.randint(-3, 500, (777, 40), dtype=torch.int32, device="cuda:0")
     got = native().lgamma_sum_i32(x, 33, 0.1)
     ref = float(gammaln(np.maximum(x[:, :33].cpu().numpy(), 0) + 0.1).sum())
     assert abs(got - ref) < 1e-6 * abs(ref)

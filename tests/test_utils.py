@@ -131,3 +131,49 @@ def test_sample_generator_writes_every_launch_script_input(tmp_path):
     assert ytype == 0 and len(types) == 784
     from harmony_b200.dolphin.optimizer import parse_host_to_value_file
     assert parse_host_to_value_file(os.path.join(d, "sample_host_to_bandwidth"))["localhost"] > 1e12
+
+
+def test_native_loader_matches_python_parsers(tmp_path):
+    """ops/csrc/loader.cpp (multi-threaded text parsers, counting-sort batch grouping) against the Python / NumPy
+    twins; skipped when the extension has not been built."""
+    from harmony_b200.ops import native_or_none
+    nat = native_or_none()
+    if nat is None:
+        pytest.skip("native extension not built")
+    from harmony_b200.common import dataloader as dl
+    from harmony_b200.common.samples import write_all
+    d = write_all(str(tmp_path))
+    for name, parser in [("sample_mlr", "mlr"), ("sample_nmf", "nmf"), ("sample_lda", "lda"),
+                         ("sample_lasso", "lasso"), ("sample_gbt", "gbt")]:
+        p = dl.make_parser(parser)
+        data = open(os.path.join(d, name), "rb").read()
+        assert len(data) >= dl.NATIVE_PARSE_MIN_BYTES
+        fast = p.parse_bytes(data)
+        slow = p.parse(data.decode().splitlines())
+        assert len(fast) == len(slow) > 0, name
+        for a, b in zip(fast, slow):
+            a = a if isinstance(a, tuple) else (a,)
+            b = b if isinstance(b, tuple) else (b,)
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=name)
+    # byte-range splits: every line lands in exactly one split, same as the line reader
+    path = os.path.join(d, "sample_mlr")
+    for k in (1, 3, 7):
+        splits = dl.get_splits(path, k)
+        by_bytes = b"".join(dl.read_split_bytes(s) for s in splits).decode().splitlines()
+        by_lines = [ln for s in splits for ln in dl.read_split(s)]
+        assert by_bytes == by_lines and len(by_lines) == 1001          # 1000 records + the comment line
+    with pytest.raises(ValueError):
+        dl.make_parser("nmf").parse_bytes(b"0: 1,2\n" * 1000)           # row index must be positive
+    # feature grouping == stable argsort
+    import torch
+    from harmony_b200.models.mlr import synthetic_batch
+    b = synthetic_batch(257, 5000, 10, 13, seed=4)
+    col, val, ptr = b.csr_col.numpy(), b.csr_val.numpy(), b.csr_ptr.numpy()
+    order = np.argsort(col, kind="stable")
+    rows = np.repeat(np.arange(257, dtype=np.int32), np.diff(ptr))
+    uniq, fptr, samp, xval = nat.group_by_feature(torch.from_numpy(ptr), torch.from_numpy(col), torch.from_numpy(val))
+    np.testing.assert_array_equal(samp.numpy(), rows[order])
+    np.testing.assert_array_equal(xval.numpy(), val[order])
+    np.testing.assert_array_equal(uniq.numpy(), np.unique(col))
+    assert fptr[0] == 0 and fptr[-1] == len(col) and np.all(np.diff(fptr.numpy()) > 0)
