@@ -118,7 +118,7 @@ def write_all(dir_path: str, force: bool = False) -> str:
     if need("sample_lda"):
         write_lda_sample(p("sample_lda"), docs=200, vocab=17935, topics=10, doc_len=60, seed=0)
     if need("sample_lasso"):
-        write_lasso_sample(p("sample_lasso"), n=200, features=10, seed=0)
+        write_lasso_sample(p("sample_lasso"), n=256, features=10, seed=0)
     if need("sample_lasso_test"):
         write_lasso_sample(p("sample_lasso_test"), n=50, features=10, seed=0, noise=0.02)
     if need("sample_gbt") or need("sample_gbt.meta"):

@@ -239,8 +239,8 @@ def test_lasso_and_gbt_jobs_on_device_backend():
     w = np.zeros(F); w[[1, 5, 9]] = [2.0, -3.0, 1.5]
     path = os.path.join(tmp, "sample_lasso")
     with open(path, "w") as f:
-        for _ in range(200):
-            x = rng.standard_normal(F)
+        for _ in range(256):          # 4 even blocks of 64 (> F): a tiny first batch could zero a support
+            x = rng.standard_normal(F)     # weight, which the reference's skip-zero rule then never revisits
             f.write(f"{x @ w + 0.01 * rng.standard_normal():.5f} " + " ".join(f"{i}:{v:.5f}" for i, v in enumerate(x)) + "\n")
     res = ETDolphinLauncher.launch(lasso.APP, ["-input", path, "-max_num_epochs", "10", "-num_mini_batches", "4",
                                                "-num_worker_blocks", "4", "-num_server_blocks", "2", "-features", str(F),

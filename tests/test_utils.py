@@ -120,7 +120,7 @@ def test_sample_generator_writes_every_launch_script_input(tmp_path):
     import harmony_b200.mlapps.mlr, harmony_b200.mlapps.nmf, harmony_b200.pregel.graph  # noqa: F401,E401
     d = write_all(str(tmp_path))
     for name, parser, n in [("sample_mlr", "mlr", 1000), ("sample_mlr_test", "mlr", 200), ("sample_nmf", "nmf", 250),
-                            ("sample_lda", "lda", 200), ("sample_lasso", "lasso", 200), ("sample_gbt", "gbt", 160),
+                            ("sample_lda", "lda", 200), ("sample_lasso", "lasso", 256), ("sample_gbt", "gbt", 160),
                             ("inputs/adj_list", "graph_none_edge_value", 40), ("inputs/shortest_path", "graph", 40)]:
         p = make_parser(parser)
         with open(os.path.join(d, name)) as f:
