@@ -64,18 +64,54 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    # NVML bit masks of nvmlDeviceGetCurrentClocksEventReasons (nvml.h)
+    NVML_REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def _nvml_sampler(self):
+        """Fast path: in-process NVML queries (~0.1 ms each) so even a 15 ms timed region gets several samples.
+        Returns a zero-argument callable producing one sample in the nvidia-smi column layout, or None."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+
+            def sample():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = int(get_reasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:  # noqa: BLE001
+                    pw = 0.0
+                flag = lambda nm: "Active" if mask & self.NVML_REASONS[nm] else "Not Active"  # noqa: E731
+                return [str(sm), str(mx), f"{pw:.1f}", flag("hw_slowdown"), flag("hw_thermal_slowdown"),
+                        flag("sw_thermal_slowdown"), flag("sw_power_cap")]
+            sample()                      # fail here, not in the loop
+            return sample
+        except Exception:  # noqa: BLE001
+            return None
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        return parts if len(parts) >= 7 else None
+
     def start(self):
+        fast = self._nvml_sampler()
+        self.source = "nvml" if fast else "nvidia-smi"
+
         def run():
             while not self._stop.is_set():
                 try:
-                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                    parts = [p.strip() for p in out.strip().split(",")]
-                    if len(parts) >= 7:
+                    parts = fast() if fast else self._smi_sample()
+                    if parts:
                         self.samples.append(parts)
                 except Exception:  # noqa: BLE001
                     pass
-                self._stop.wait(0.1)
+                self._stop.wait(0.003 if fast else 0.1)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
@@ -92,7 +128,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": getattr(self, "source", None)}
 
 
 def reference_arm(args):
