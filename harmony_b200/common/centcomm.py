@@ -8,7 +8,7 @@ ns/CentCommMsgHandler.java:40-86 (route by client class name), common/src/main/a
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict
+from typing import Any, Callable
 
 Handler = Callable[[str, Any], None]     # (source id, data)
 

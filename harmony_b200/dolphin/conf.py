@@ -8,7 +8,7 @@ values); the table *shape* of a model is described by callables of the parsed fl
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Callable, List, Optional
 
 from ..et.config import TableConfiguration
 from ..utils.flags import Configuration, Param

@@ -12,9 +12,6 @@
 from __future__ import annotations
 
 import logging
-import sys
-import threading
-import time
 from typing import Any, Dict, List, Optional, Sequence
 
 from ..et import ExecutorConfiguration, LocalTransport

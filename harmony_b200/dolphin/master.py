@@ -16,7 +16,7 @@ import time
 from typing import Any, Callable, Dict, List, Optional, Sequence, Set
 
 from ..et.config import TaskletConfiguration
-from ..et.driver import AllocatedExecutor, AllocatedTable, ETMaster, MetricReceiver, RunningTasklet
+from ..et.driver import AllocatedExecutor, ETMaster, MetricReceiver, RunningTasklet
 from ..utils.concurrent import CountDownLatch
 from ..utils.state_machine import StateMachine
 from .metrics import DolphinMetricManager, ServerMetrics

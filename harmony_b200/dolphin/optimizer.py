@@ -18,13 +18,12 @@ from __future__ import annotations
 import heapq
 import logging
 import threading
-import time
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Set, Tuple
 
 from ..et.config import TaskletConfiguration
 from ..et.driver import AllocatedExecutor, ETMaster
-from ..et.plan import ETPlan, LoggingPlanExecutor, PlanExecutor
+from ..et.plan import LoggingPlanExecutor, PlanExecutor
 from .master import SERVER_TASKLET, WORKER_TASKLET, DolphinMaster
 from .plan import (HOMOGENEOUS, NAMESPACE_SERVER, NAMESPACE_WORKER, Plan, PlanCompiler, TransferStep, empty_plan)
 

@@ -9,7 +9,7 @@ short), :474-523 (move ops + their dependencies).
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional, Tuple
+from typing import Any, Callable, Dict, List, Optional
 
 from ..et.config import ExecutorConfiguration, TaskletConfiguration
 from ..et.plan import (AllocateOp, AssociateOp, DeallocateOp, ETPlan, MoveOp, StartOp, StopOp, SubscribeOp,

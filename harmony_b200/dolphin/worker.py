@@ -16,9 +16,9 @@ import logging
 import random
 import threading
 import time
-from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Sequence, Tuple
 
-from ..et.tasklet import CPU, NET, VOID, TaskUnitInfo, Tasklet, load_class
+from ..et.tasklet import CPU, NET, TaskUnitInfo, Tasklet, load_class
 from ..utils import trace
 from .metrics import BatchMetrics, EpochMetrics
 

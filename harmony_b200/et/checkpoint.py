@@ -20,14 +20,11 @@ import pickle
 import random
 import shutil
 import threading
-import time
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ..utils.concurrent import AggregateFuture, ResultFuture
 from .config import TableConfiguration
-from .exceptions import ChkpNotExistError
 
 LOG = logging.getLogger(__name__)
 MAGIC = b"HBCK"

@@ -25,7 +25,6 @@ from __future__ import annotations
 import itertools
 import logging
 import os
-import random
 import threading
 import time
 from typing import Any, Callable, Dict, List, Optional, Sequence, Set, Tuple
@@ -34,8 +33,7 @@ from ..utils.concurrent import AggregateFuture, CompletedFuture, ResultFuture, n
 from ..utils.state_machine import StateMachine
 from . import checkpoint as chk
 from .config import ExecutorConfiguration, TableConfiguration, TaskletConfiguration
-from .exceptions import (AlreadyAssociatedError, ChkpNotExistError, ExecutorNotExistError, NotAssociatedError,
-                         TableNotExistError, TaskletFailedError)
+from .exceptions import (AlreadyAssociatedError, ChkpNotExistError, ExecutorNotExistError, NotAssociatedError, TableNotExistError)
 from .transport import NetworkError, Transport
 
 LOG = logging.getLogger(__name__)

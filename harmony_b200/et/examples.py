@@ -12,7 +12,6 @@ import threading
 import time
 from typing import Any, Dict, List
 
-import numpy as np
 
 from . import ExecutorConfiguration, TableConfiguration, local_cluster
 from .config import TaskletConfiguration

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import logging
 import threading
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 from ..utils.concurrent import new_fixed_thread_pool
 from .checkpoint import ChkpManagerSlave

@@ -13,7 +13,7 @@ import os
 import subprocess
 import sys
 import threading
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Dict, Tuple
 
 from .config import ExecutorConfiguration
 from .driver import ExecutorLauncher

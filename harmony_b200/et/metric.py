@@ -7,7 +7,7 @@ MetricManager.java:46-56 (driver start/stop), driver/api/MetricReceiver.java:26-
 from __future__ import annotations
 
 import threading
-from typing import Any, Dict, List, Optional
+from typing import Any, List, Optional
 
 from ..utils.misc import resolve_hostname
 

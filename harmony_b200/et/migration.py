@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import logging
 import threading
-from typing import Any, Dict, List, Tuple
+from typing import Any, Dict, Tuple
 
 LOG = logging.getLogger(__name__)
 MAX_CONCURRENT_MIGRATIONS = 4

@@ -13,7 +13,7 @@ tables accept arbitrary hashable keys through murmur3.
 from __future__ import annotations
 
 import pickle
-from typing import Any, List, Sequence, Tuple
+from typing import Any, Sequence, Tuple
 
 import numpy as np
 

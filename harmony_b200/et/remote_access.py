@@ -26,7 +26,7 @@ import numpy as np
 
 from ..utils.concurrent import ResultFuture
 from ..utils.state_machine import StateMachine
-from .exceptions import DataAccessFailedError, TableNotExistError
+from .exceptions import DataAccessFailedError
 from .transport import NetworkError
 
 LOG = logging.getLogger(__name__)

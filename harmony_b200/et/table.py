@@ -14,15 +14,14 @@ from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
 
-from ..utils.concurrent import CompletedFuture, ResultFuture
+from ..utils.concurrent import ResultFuture
 from .block_store import BlockStore, DenseBlock, DictBlock, Tablet
 from .config import TableConfiguration
 from .exceptions import TableNotExistError
 from .ownership import OwnershipCache
 from .partitioner import (DenseHashedPartitioner, DenseOrderedPartitioner, HashBasedBlockPartitioner,
                           OrderingBasedBlockPartitioner)
-from .remote_access import (GET, GET_OR_INIT, PUT, PUT_IF_ABSENT, REMOVE, UPDATE, MultiKeyDataOpResult,
-                            RemoteDataOp, SingleKeyDataOpResult, execute_on_block)
+from .remote_access import (GET, GET_OR_INIT, PUT, PUT_IF_ABSENT, REMOVE, UPDATE, MultiKeyDataOpResult, RemoteDataOp, SingleKeyDataOpResult)
 from .update_function import make_update_function
 
 LOG = logging.getLogger(__name__)

@@ -16,9 +16,8 @@ import logging
 import threading
 import traceback
 from dataclasses import dataclass
-from typing import Any, Callable, Dict, Optional
+from typing import Any, Dict, Optional
 
-from ..utils.concurrent import new_fixed_thread_pool
 from .config import TaskletConfiguration
 
 LOG = logging.getLogger(__name__)

@@ -8,13 +8,11 @@ DriverLauncher.java:162-183.  The wire protocol is kept: a line-oriented TCP soc
 from __future__ import annotations
 
 import logging
-import os
 import socket
 import socketserver
 import sys
 import threading
-import time
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 from ..dolphin import params as P
 from ..et.driver import ETMaster, InProcessLauncher

@@ -13,7 +13,7 @@ regression, k = k-class classification).  Input: `y idx:val ...`.
 from __future__ import annotations
 
 import random
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, Tuple
 
 import numpy as np
 

@@ -1,12 +1,11 @@
 """GPU-resident LDA trainer (Dolphin Trainer SPI over ops/csrc/lda_ops.cu + the table kernels)."""
 from __future__ import annotations
 
-from typing import Any, Dict, List
+from typing import Any, Dict
 
 import numpy as np
 
 from ..dolphin.worker import Trainer
-from .lda import doc_llh, word_llh
 
 
 class LDADeviceTrainer(Trainer):

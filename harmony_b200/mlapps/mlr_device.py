@@ -8,7 +8,7 @@ Input blocks are converted once into device-resident CSR/CSC tensors (the input 
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict, Optional
+from typing import Any, Dict
 
 import numpy as np
 

@@ -13,7 +13,7 @@ table (required by the device backend); without it R is a generic KV table on th
 from __future__ import annotations
 
 import logging
-from typing import Any, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Sequence, Tuple
 
 import numpy as np
 

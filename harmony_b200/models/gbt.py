@@ -8,7 +8,7 @@ argsorted once per mini-batch.  Reference behaviour: GBTTrainer.java:327-531 (sp
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 import torch

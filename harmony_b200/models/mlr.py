@@ -12,7 +12,7 @@ The L2 term is applied at the owner (`scale_local`): every worker's mini-batch c
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch

@@ -12,7 +12,7 @@ local HBM.  Same arithmetic as the pull/push mode; clock_slack is 0 by construct
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

@@ -3,7 +3,7 @@ push fused with SGD+clamp at the owners (K2+K4).  See ops/csrc/nmf_ops.cu."""
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 import torch

@@ -5,8 +5,7 @@ pregel/graphapps/shortestpath/ShortestPathComputation.java:42-66, SourceId.java.
 """
 from __future__ import annotations
 
-import sys
-from typing import Any, Iterable, List
+from typing import Iterable, List
 
 from ..dolphin import params as P
 from .graph import Computation, Vertex

@@ -12,7 +12,7 @@ SPMD: rank r owns the vertices whose id % world == r (their adjacency lists and 
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 import torch

@@ -11,7 +11,7 @@ combiner/*.java, common/{DefaultGraphParser,NoneEdgeValueGraphParser}.java (`v t
 from __future__ import annotations
 
 import threading
-from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple
+from typing import Any, Dict, Iterable, List, Optional
 
 from ..common.dataloader import DataParser, register_parser
 

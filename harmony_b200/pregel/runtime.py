@@ -18,7 +18,7 @@ from ..dolphin import params as P
 from ..et import ExecutorConfiguration, LocalTransport, TableConfiguration
 from ..et.config import TaskletConfiguration
 from ..et.driver import AllocatedExecutor, ETMaster, InProcessLauncher
-from ..et.tasklet import CPU, NET, VOID, TaskUnitInfo, Tasklet, load_class
+from ..et.tasklet import CPU, NET, TaskUnitInfo, Tasklet, load_class
 from ..jobserver.client import CommandSender, DEFAULT_PORT
 from ..jobserver.driver import JobEntity, JobMaster, JobServerDriver
 from ..utils.concurrent import CountDownLatch
