@@ -29,7 +29,9 @@ class BatchMetrics:
     kind: str = "batch"
 
     def to_dict(self) -> Dict[str, Any]:
-        return asdict(self)
+        d = dict(self.__dict__)                  # flat record: one shallow copy per mini-batch (asdict recurses)
+        d["batch_custom_metrics"] = dict(self.batch_custom_metrics)
+        return d
 
 
 @dataclass

@@ -301,6 +301,32 @@ class RemoteAccessOpHandler:
         op.is_local = True
         self._enqueue(op)
 
+    def execute_local(self, op: RemoteDataOp, comps) -> None:
+        """Run an op on a LOCAL block in the caller's thread.  The caller holds the block's ownership read lock
+        (TableImpl resolved the owner with it), so the block cannot migrate away underneath; blocks serialise
+        their own mutations.  This is the reference's local path (TableImpl.java:366-408 calls the tablet directly);
+        only requests that arrive over the network go through the per-block comm threads."""
+        op.is_local = True
+        tr = self._tracker(op.table_id)
+        with tr.cond:
+            if tr.sm.current_state != "PROCESSING":
+                self._redirect_to_driver(op)
+                return
+            tr.in_flight += 1
+        try:
+            try:
+                block = comps.block_store.get(op.block_id)
+                result = execute_on_block(block, op.op_type, op.keys, op.values, op.single)
+                ok = True
+            except Exception:  # noqa: BLE001
+                LOG.exception("local op %s on table %s failed", op.op_type, op.table_id)
+                result, ok = None, False
+            self._ex.sender.complete_local(op, result, ok)
+        finally:
+            with tr.cond:
+                tr.in_flight -= 1
+                tr.cond.notify_all()
+
     def _enqueue(self, op: RemoteDataOp) -> None:
         tr = self._tracker(op.table_id)
         with tr.cond:

@@ -85,7 +85,7 @@ class TableImpl:
         owner, unlock = self._c.ownership.resolve_executor_with_lock(block_id)
         try:
             if owner is None:
-                self._ex.handler.enqueue_local(op)
+                self._ex.handler.execute_local(op, self._c)      # inline, under the ownership read lock
             else:
                 self._ex.sender.send_op(op, owner)
         finally:
@@ -128,7 +128,7 @@ class TableImpl:
             owner, unlock = self._c.ownership.resolve_executor_with_lock(block_id)
             try:
                 if owner is None:
-                    self._ex.handler.enqueue_local(op)
+                    self._ex.handler.execute_local(op, self._c)  # inline, under the ownership read lock
                 else:
                     self._ex.sender.send_op(op, owner)
             finally:

@@ -51,11 +51,18 @@ def device_memory_mb() -> float:
     return 0.0
 
 
+_HOSTNAME = None
+
+
 def resolve_hostname() -> str:
-    try:
-        return socket.gethostname()
-    except Exception:  # noqa: BLE001
-        return "localhost"
+    """Cached: the metric collector stamps every per-mini-batch report with it."""
+    global _HOSTNAME
+    if _HOSTNAME is None:
+        try:
+            _HOSTNAME = socket.gethostname()
+        except Exception:  # noqa: BLE001
+            _HOSTNAME = "localhost"
+    return _HOSTNAME
 
 
 def murmur3_32(data: bytes, seed: int = 0) -> int:
