@@ -177,3 +177,18 @@ def test_native_loader_matches_python_parsers(tmp_path):
     np.testing.assert_array_equal(xval.numpy(), val[order])
     np.testing.assert_array_equal(uniq.numpy(), np.unique(col))
     assert fptr[0] == 0 and fptr[-1] == len(col) and np.all(np.diff(fptr.numpy()) > 0)
+
+
+def test_unified_cli_and_flag_reference(tmp_path, capsys):
+    """`python -m harmony_b200 ...`: sample generation, flag listing (docs/FLAGS.md is generated from it) and an
+    ET example through the same dispatcher the bin/ scripts use."""
+    from harmony_b200.__main__ import all_flags, flags_markdown, main
+    assert main(["samples", str(tmp_path)]) == 0 and os.path.exists(tmp_path / "sample_mlr")
+    names = [p.name for _, p in all_flags()]
+    for must in ("num_executors", "scheduler", "max_num_epochs", "num_mini_batches", "clock_slack", "optimizer",
+                 "features_per_partition", "num_topics", "max_depth_of_tree", "num_pregel_workers", "mlr_mode"):
+        assert must in names
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert open(os.path.join(root, "docs", "FLAGS.md")).read() == flags_markdown()     # regenerate when flags change
+    assert main(["et-example", "simple"]) == 0
+    assert main(["run", "nosuchapp"]) == 2 and main(["frobnicate"]) == 2
