@@ -289,6 +289,13 @@ class TableControlAgent:
                 with self._lock:
                     self._futs.pop(op_id, None)
 
+    def on_failed(self, op_id: int, error: str) -> None:
+        """An executor could not perform its part of control op `op_id`: fail the whole fan-out."""
+        with self._lock:
+            fut = self._futs.pop(op_id, None)
+        if fut is not None:
+            fut.on_failed(RuntimeError(error))
+
     def init_table(self, conf: TableConfiguration, executor_ids: Set[str], owners: List[str]) -> AggregateFuture:
         op, fut = self._new(len(executor_ids))
         for e in executor_ids:
@@ -298,7 +305,12 @@ class TableControlAgent:
     def load(self, table_id: str, executor_ids: Set[str], input_path: str) -> AggregateFuture:
         from ..common.dataloader import get_splits
         ids = sorted(executor_ids)
-        splits = get_splits(input_path, NUM_SPLITS_PER_EXECUTOR * len(ids))
+        try:
+            splits = get_splits(input_path, NUM_SPLITS_PER_EXECUTOR * len(ids))
+        except OSError as e:
+            failed: AggregateFuture = AggregateFuture(len(ids))
+            failed.on_failed(RuntimeError(f"cannot read input '{input_path}' of table {table_id}: {e}"))
+            return failed
         op, fut = self._new(len(ids))
         for i, e in enumerate(ids):
             mine = splits[i * NUM_SPLITS_PER_EXECUTOR:(i + 1) * NUM_SPLITS_PER_EXECUTOR]
@@ -707,18 +719,18 @@ class AllocatedTable:
 
         def after_map(_=None):
             if conf.chkp_path:
-                self._m.chkp_master.load_from_path(conf.chkp_path, self).add_listener(done)
+                self._m.chkp_master.load_from_path(conf.chkp_path, self).chain(fut, done)
             elif conf.input_path:
-                self._m.control.load(conf.table_id, ids, conf.input_path).add_listener(done)
+                self._m.control.load(conf.table_id, ids, conf.input_path).chain(fut, done)
             else:
                 done()
 
         def after_init(acks):
             if self.is_device:
-                self._exchange_peer_map(acks, ids).add_listener(after_map)
+                self._exchange_peer_map(acks, ids).chain(fut, after_map)
             else:
                 after_map()
-        init_fut.add_listener(after_init)
+        init_fut.chain(fut, after_init)
         return fut
 
     def init_from_chkp(self, chkp_id: str, initial_associators: Sequence[AllocatedExecutor],
@@ -743,12 +755,12 @@ class AllocatedTable:
                 fut.on_completed(self)
 
             def load(_=None):
-                self._m.chkp_master.load(chkp_id, self).add_listener(done)
+                self._m.chkp_master.load(chkp_id, self).chain(fut, done)
             if self.is_device:
-                self._exchange_peer_map(acks, ids).add_listener(load)
+                self._exchange_peer_map(acks, ids).chain(fut, load)
             else:
                 load()
-        self._m.control.init_table(conf, ids, self.block_manager.get_ownership_status()).add_listener(after_init)
+        self._m.control.init_table(conf, ids, self.block_manager.get_ownership_status()).chain(fut, after_init)
         return fut
 
     def load(self, executors: Sequence[AllocatedExecutor], input_path: str) -> ResultFuture:
@@ -1029,6 +1041,9 @@ class ETMaster:
         if t in ("TableInitAck", "TableLoadAck", "TableDropAck", "OwnershipSyncAck", "TablePeerMapAck",
                  "TableQuiesceAck", "TableResumeAck", "DeviceMoveRecvAck", "DeviceOwnershipFlipAck"):
             self.control.on_ack(m["op_id"], m)
+        elif t == "ControlOpFailed":
+            LOG.error("control op %s (%s) failed on %s: %s", m["op_id"], m.get("orig_type"), m.get("src"), m["error"])
+            self.control.on_failed(m["op_id"], f"{m.get('orig_type')} failed on {m.get('src')}: {m['error']}")
         elif t == "OwnershipMoved":
             self.pool.submit(self.migrations.on_ownership_moved, m["op_id"], m["block_id"])
         elif t == "DataMoved":

@@ -86,7 +86,22 @@ class Executor:
                     return
                 LOG.warning("[%s] unhandled message type %s", self.executor_id, t)
                 return
-            self.pool.submit(fn, m)
+            self.pool.submit(self._guarded, fn, m)
+
+    # control messages the driver fans out and waits on: a failing handler must fail the driver-side future
+    _CONTROL_OPS = {"TableInit", "TableLoad", "TableDrop", "OwnershipSync", "TablePeerMap", "TableQuiesce",
+                    "TableResume", "DeviceMoveRecv", "DeviceOwnershipFlip"}
+
+    def _guarded(self, fn, m: Dict[str, Any]) -> None:
+        try:
+            fn(m)
+        except Exception as e:  # noqa: BLE001
+            if m.get("type") in self._CONTROL_OPS and "op_id" in m:
+                LOG.exception("[%s] control op %s failed", self.executor_id, m.get("type"))
+                self.send_to_driver({"type": "ControlOpFailed", "op_id": m["op_id"], "orig_type": m["type"],
+                                     "table_id": m.get("table_id"), "error": f"{type(e).__name__}: {e}"})
+            else:
+                raise
 
     # -- table control --
     def _on_TableInit(self, m):

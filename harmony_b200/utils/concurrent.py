@@ -56,6 +56,24 @@ class ResultFuture(Generic[T]):
         cb(self._result)
         return self
 
+    def exception(self) -> Optional[BaseException]:
+        return self._exc
+
+    def chain(self, out: "ResultFuture", cb: Callable[[T], None]) -> "ResultFuture[T]":
+        """Continue an asynchronous sequence: on success run `cb(result)` (an exception in it fails `out`), on
+        failure fail `out` with the same exception -- so an error anywhere in a multi-step control operation
+        (init -> peer map -> load ...) reaches whoever waits on the operation's final future instead of leaving it
+        pending forever."""
+        def step(result):
+            if self._exc is not None:
+                out.on_failed(self._exc)
+                return
+            try:
+                cb(result)
+            except BaseException as e:  # noqa: BLE001
+                out.on_failed(e)
+        return self.add_listener(step)
+
     def done(self) -> bool:
         return self._ev.is_set()
 

@@ -223,3 +223,26 @@ def test_trainer_constructor_can_rendezvous_with_its_peers():
             assert sorted(x[1] for x in r["group"]) == ["executor-0", "executor-1", "executor-2"]
     finally:
         js.stop(kill=True)
+
+
+def test_bad_input_fails_the_job_not_the_server(tmp_path):
+    """A missing input file (driver-side split computation) and a corrupt record (executor-side bulk load) must
+    fail the JOB with the cause; the control-plane future chain propagates the error instead of hanging."""
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port})).start()
+    try:
+        bad = tmp_path / "corrupt"
+        bad.write_text("1 0:0.5 3:1.0\n2 notanumber:1\n" * 40)
+        for i, (inp, needle) in enumerate([("/nonexistent/input", "cannot read input"), (str(bad), "TableLoad failed")]):
+            t0 = time.time()
+            args = ["-input", inp, "-classes", "4", "-features", "8", "-max_num_epochs", "1", "-port", str(port)]
+            assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+            ok, result = js.driver.wait_job(f"MLR-{i}", timeout=30)
+            assert not ok and needle in str(result), result
+            assert time.time() - t0 < 20
+        good = write_mlr_sample(str(tmp_path / "ok"), n=60)
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(good, port, ["-max_num_epochs", "1"]),
+                                             port=port).startswith("true")
+        assert js.driver.wait_job("MLR-2", timeout=120)[0]
+    finally:
+        js.stop(kill=True)
