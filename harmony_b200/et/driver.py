@@ -780,8 +780,8 @@ class AllocatedTable:
                 def fin(_):
                     self._m.subscriptions.finish_subscription_init(op)
                     out.on_completed(None)
-                self._exchange_peer_map(acks, ids).add_listener(fin)
-            fut.add_listener(after)
+                self._exchange_peer_map(acks, ids).chain(out, fin)
+            fut.chain(out, after)
             return out
         fut.add_listener(lambda _: self._m.subscriptions.finish_subscription_init(op))
         return fut
@@ -811,8 +811,8 @@ class AllocatedTable:
                 def fin(_):
                     done(None)
                     out.on_completed(None)
-                self._exchange_peer_map(acks, new_ids).add_listener(fin)
-            fut.add_listener(after)
+                self._exchange_peer_map(acks, new_ids).chain(out, fin)
+            fut.chain(out, after)
             return out
         fut.add_listener(done)
         return fut
@@ -865,8 +865,17 @@ class AllocatedTable:
         ctl = self._m.control
 
         def step_resume(_):
+            ctl.fan_out(subs, {"type": "TableResume", "table_id": self.table_id}).chain(
+                out, lambda _: out.on_completed(MigrationResult(True, "device migration completed", list(blocks))))
+
+        def abort(exc):
+            """A step failed (e.g. the receiver's arena is full): nothing was flipped yet, so release the blocks and
+            let the quiesced accessors continue on the old owner."""
+            LOG.error("device migration of %s blocks %s -> %s failed: %s", self.table_id, src, dst, exc)
+            for b in blocks:
+                self.block_manager.release_block_from_move(b)
             ctl.fan_out(subs, {"type": "TableResume", "table_id": self.table_id}).add_listener(
-                lambda _: out.on_completed(MigrationResult(True, "device migration completed", list(blocks))))
+                lambda _: out.on_failed(exc))
 
         def step_flip(acks):
             locs = acks[0]["locs"]
@@ -880,12 +889,12 @@ class AllocatedTable:
                 di["blocks"][b] = (key, si, off)
                 di["handles"][si] = seg_info
             ctl.fan_out(subs, {"type": "DeviceOwnershipFlip", "table_id": self.table_id, "locs": locs,
-                               "new_owner": dst, "old_owner": src}).add_listener(step_resume)
+                               "new_owner": dst, "old_owner": src}).chain(out, step_resume)
 
         def step_copy(_):
             ctl.fan_out({dst}, {"type": "DeviceMoveRecv", "table_id": self.table_id,
-                                "block_ids": list(blocks)}).add_listener(step_flip)
-        ctl.fan_out(subs, {"type": "TableQuiesce", "table_id": self.table_id}).add_listener(step_copy)
+                                "block_ids": list(blocks)}).chain(out, step_flip, on_error=abort)
+        ctl.fan_out(subs, {"type": "TableQuiesce", "table_id": self.table_id}).chain(out, step_copy, on_error=abort)
         return out
 
     def get_partition_info(self) -> Dict[str, Set[int]]:

@@ -59,19 +59,22 @@ class ResultFuture(Generic[T]):
     def exception(self) -> Optional[BaseException]:
         return self._exc
 
-    def chain(self, out: "ResultFuture", cb: Callable[[T], None]) -> "ResultFuture[T]":
+    def chain(self, out: "ResultFuture", cb: Callable[[T], None],
+              on_error: Optional[Callable[[BaseException], None]] = None) -> "ResultFuture[T]":
         """Continue an asynchronous sequence: on success run `cb(result)` (an exception in it fails `out`), on
         failure fail `out` with the same exception -- so an error anywhere in a multi-step control operation
         (init -> peer map -> load ...) reaches whoever waits on the operation's final future instead of leaving it
-        pending forever."""
+        pending forever.  `on_error` (optional) runs instead of `out.on_failed` to undo partial work first."""
+        fail = on_error or out.on_failed
+
         def step(result):
             if self._exc is not None:
-                out.on_failed(self._exc)
+                fail(self._exc)
                 return
             try:
                 cb(result)
             except BaseException as e:  # noqa: BLE001
-                out.on_failed(e)
+                fail(e)
         return self.add_listener(step)
 
     def done(self) -> bool:
