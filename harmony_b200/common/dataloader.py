@@ -15,6 +15,8 @@ from dataclasses import asdict, dataclass
 from typing import Any, Callable, Dict, Iterable, Iterator, List, Optional, Sequence
 
 
+import numpy as np
+
 from ..et.exceptions import KeyGenerationError
 
 
@@ -140,12 +142,39 @@ class DataParser:
                     head, ptr, idx, val = nat.parse_sparse_text(data, self.native_mode, os.cpu_count() or 4)
                 except ValueError as e:
                     raise ValueError(f"{type(self).__name__}: {e}") from None
-                return self.from_arrays(head.numpy(), ptr.numpy(), idx.numpy(), val.numpy())
+                idx_np = idx.numpy()
+                return self.check_index_bounds(self.from_arrays(head.numpy(), ptr.numpy(), idx_np, val.numpy()), idx_np)
         return self.parse(data.decode("utf-8", errors="replace").splitlines())
 
     def from_arrays(self, head, ptr, idx, val) -> List[Any]:
         """Records from the native parser's (head[n], ptr[n+1], idx[nnz], val[nnz]) arrays."""
         raise NotImplementedError
+
+    index_bound_param: Optional[str] = None     # name of the param bounding the record indices ("features", ...)
+
+    def record_indices(self, record: Any):
+        """The index array of one record (checked against `index_bound_param`); None = nothing to check."""
+        return None
+
+    def check_index_bounds(self, records: List[Any], flat_idx=None) -> List[Any]:
+        """Indices address rows of a dense model table (and raw HBM on the device backend): reject out-of-range
+        input at load time instead of corrupting memory at training time."""
+        bound = self.params.get(self.index_bound_param) if self.index_bound_param else None
+        if not bound:
+            return records
+        bound = int(bound)
+        if flat_idx is not None:
+            bad = flat_idx.size and (int(flat_idx.min()) < 0 or int(flat_idx.max()) >= bound)
+        else:
+            bad = False
+            for r in records:
+                idx = self.record_indices(r)
+                if idx is not None and len(idx) and (int(np.min(idx)) < 0 or int(np.max(idx)) >= bound):
+                    bad = True
+                    break
+        if bad:
+            raise ValueError(f"{type(self).__name__}: index out of range [0, {bound}) (-{self.index_bound_param})")
+        return records
 
     def parse(self, lines: Iterable[str]) -> List[Any]:
         out = []
@@ -156,7 +185,7 @@ class DataParser:
             v = self.parse_line(s)
             if v is not None:
                 out.append(v)
-        return out
+        return self.check_index_bounds(out)
 
     def parse_line(self, line: str) -> Any:
         return line

@@ -47,9 +47,13 @@ def build_tables_confs(app: ETDolphinConfiguration, conf: Configuration, job_cou
             nb -= 1
         server_tc.num_total_blocks = nb
     server_tc.chkp_path = conf.get("model_path") if load_model and conf.get("model_path") else None
+    parser_spec = app.input_parser
+    if isinstance(parser_spec, str):      # the parser validates labels / indices against the job's dimensions
+        bounds = {k: conf[k] for k in ("classes", "features", "num_vocabs") if conf.get(k)}
+        parser_spec = {"name": parser_spec, "params": bounds}
     worker_tc = TableConfiguration(
         table_id=input_id, num_total_blocks=int(conf.get("num_worker_blocks", 1024)), is_mutable=False,
-        is_ordered=True, update_function="void", input_path=input_path or None, data_parser=app.input_parser,
+        is_ordered=True, update_function="void", input_path=input_path or None, data_parser=parser_spec,
         bulk_loader="exist_key" if app.has_input_data_key else "none_key",
         chkp_path=(conf.get("input_chkp_path") or None) if load_model and app.has_local_model_table else None)
     local_tc = None
@@ -119,7 +123,7 @@ class DolphinJobEntity(JobEntity):
                   "device_trainer_host_model": self.app.device_trainer_host_model,
                   "model_table_id": self.server_tc.table_id, "input_table_id": self.worker_tc.table_id,
                   "local_model_table_id": self.local_tc.table_id if self.local_tc else None,
-                  "data_parser": self.app.input_parser, "app_id": self.app.app_id,
+                  "data_parser": self.worker_tc.data_parser, "app_id": self.app.app_id,
                   "num_job_workers": max(1, len(self.executors)),
                   "job_executor_ids": [e.id for e in self.executors]})
         return p

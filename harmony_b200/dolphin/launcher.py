@@ -93,7 +93,7 @@ class ETDolphinLauncher:
                            "device_trainer_host_model": app.device_trainer_host_model,
                            "model_table_id": server_tc.table_id, "input_table_id": worker_tc.table_id,
                            "local_model_table_id": local_tc.table_id if local_tc else None,
-                           "data_parser": app.input_parser, "app_id": app.app_id, "task_units_enabled": False})
+                           "data_parser": worker_tc.data_parser, "app_id": app.app_id, "task_units_enabled": False})
             job_id = f"{app.app_id}-0"
             dm = DolphinMaster(master, job_id, params, report=lambda s: (messages.append(s), LOG.info(s)))
             receiver.register(job_id, dm.metric_manager)

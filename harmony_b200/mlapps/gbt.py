@@ -26,6 +26,11 @@ from ..utils.flags import Configuration
 
 
 class GBTDataParser(DataParser):
+    index_bound_param = "features"
+
+    def record_indices(self, record):
+        return record[0]
+
     native_mode = 0
 
     def from_arrays(self, head, ptr, idx, val):

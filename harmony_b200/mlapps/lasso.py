@@ -23,6 +23,11 @@ CLOSE_TO_ZERO = 1e-9
 
 
 class LassoDataParser(DataParser):
+    index_bound_param = "features"
+
+    def record_indices(self, record):
+        return record[0]
+
     native_mode = 0
 
     def from_arrays(self, head, ptr, idx, val):

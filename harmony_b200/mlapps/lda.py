@@ -29,6 +29,11 @@ LOG = logging.getLogger(__name__)
 
 
 class LDADataParser(DataParser):
+    index_bound_param = "num_vocabs"
+
+    def record_indices(self, record):
+        return record
+
     native_mode = 2
 
     def from_arrays(self, head, ptr, idx, val):

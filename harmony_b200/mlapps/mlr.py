@@ -32,6 +32,11 @@ ZERO_THRESHOLD = 1e-7
 
 class MLRDataParser(DataParser):
     """`label idx:val idx:val ...` -> (idx int32[], val float32[], label)."""
+    index_bound_param = "features"
+
+    def record_indices(self, record):
+        return record[0]
+
     native_mode = 0
 
     def from_arrays(self, head, ptr, idx, val):

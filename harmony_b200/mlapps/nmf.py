@@ -29,6 +29,11 @@ LOG = logging.getLogger(__name__)
 
 class NMFDataParser(DataParser):
     """`rowIdx: col,val col,val ...` (1-based) -> (row, cols int32 0-based, vals float32)."""
+    index_bound_param = "features"
+
+    def record_indices(self, record):
+        return record[1]
+
     native_mode = 1
 
     def from_arrays(self, head, ptr, idx, val):

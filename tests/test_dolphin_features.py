@@ -233,7 +233,9 @@ def test_bad_input_fails_the_job_not_the_server(tmp_path):
     try:
         bad = tmp_path / "corrupt"
         bad.write_text("1 0:0.5 3:1.0\n2 notanumber:1\n" * 40)
-        for i, (inp, needle) in enumerate([("/nonexistent/input", "cannot read input"), (str(bad), "TableLoad failed")]):
+        wide = write_mlr_sample(str(tmp_path / "wide"), n=40, features=64)       # feature ids up to 63, job says 8
+        for i, (inp, needle) in enumerate([("/nonexistent/input", "cannot read input"), (str(bad), "TableLoad failed"),
+                                           (wide, "index out of range")]):
             t0 = time.time()
             args = ["-input", inp, "-classes", "4", "-features", "8", "-max_num_epochs", "1", "-port", str(port)]
             assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
@@ -243,6 +245,6 @@ def test_bad_input_fails_the_job_not_the_server(tmp_path):
         good = write_mlr_sample(str(tmp_path / "ok"), n=60)
         assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(good, port, ["-max_num_epochs", "1"]),
                                              port=port).startswith("true")
-        assert js.driver.wait_job("MLR-2", timeout=120)[0]
+        assert js.driver.wait_job("MLR-3", timeout=120)[0]
     finally:
         js.stop(kill=True)
