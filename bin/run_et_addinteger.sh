@@ -2,4 +2,4 @@
 # Elastic Table example `addinteger` (reference: services/et/bin/run_addinteger.sh)
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
-exec python -c "import sys; from harmony_b200.et.examples import main; sys.exit(main(['addinteger']))"
+exec python -m harmony_b200 et-example addinteger "$@"

@@ -2,4 +2,4 @@
 # Elastic Table example `centcomm` (reference: services/et/bin/run_centcomm.sh)
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
-exec python -c "import sys; from harmony_b200.et.examples import main; sys.exit(main(['centcomm']))"
+exec python -m harmony_b200 et-example centcomm "$@"

@@ -2,4 +2,4 @@
 # Elastic Table example `simple` (reference: services/et/bin/run_simple.sh)
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
-exec python -m harmony_b200 et-example simple "$@"
+exec python -m harmony_b200 et-example linecount "$@"

@@ -92,6 +92,29 @@ PREGEL = [P("num_pregel_workers", int, 1, "", "launcher"), P("pregel_worker_mem_
           P("source", int, 0, "SSSP source vertex", "user")]
 
 
+# ---- ET examples / common services (services/et/.../examples/*, common/datastorer, common/metric, utils/trace) ----
+ET_EXAMPLES = [
+    P("num_workers", int, 2, "addinteger: updater executors", "user"),
+    P("num_updates", int, 128, "addinteger: total updates by each worker", "user"),
+    P("delta_value", int, 1, "addinteger: delta added by each update", "user"),
+    P("coefficient", int, 1, "addinteger: multiplier the update function applies to the delta", "user"),
+    P("metric_flush_period_ms", int, 0, "addinteger: automatic metric flush period (0 = off)", "user"),
+    P("table_input", str, "", "simple: optional input file bulk-loaded into the table", "user"),
+    P("kv_data_path", str, "", "load: `key value` lines for the exist-key loader", "user"),
+    P("none_key_data_path", str, "", "load: value lines for the none-key loader", "user"),
+    P("metric_automatic_flush_period_ms", int, 200, "metric: automatic flush period", "user"),
+    P("metric_manual_flush_period_ms", int, 100, "metric: manual flush period inside the tasklet", "user"),
+    P("custom_metric_record_period_ms", int, 20, "metric: period of the custom timestamp metric", "user"),
+    P("task_duration_ms", int, 400, "metric: tasklet run time", "user"),
+    P("inputs", str, "", "linecount: comma-separated input paths (dataloader example)", "user"),
+    P("base_dir", str, "/tmp/harmony_b200", "datastorer base directory", "driver"),
+    P("memory_measure_interval", int, 1000, "memory metric tracker sampling period (ms)", "worker"),
+    P("htrace_receiver_type", str, "CHROME", "STDOUT | ZIPKIN | CHROME: where trace spans go", "client"),
+    P("htrace_receiver_host", str, "localhost", "span receiver host (ZIPKIN)", "client"),
+    P("htrace_receiver_port", int, 9410, "span receiver port (ZIPKIN)", "client"),
+]
+
+
 def registry(*groups) -> ParamRegistry:
     reg = ParamRegistry()
     for g in groups:

@@ -50,6 +50,8 @@ class DeviceTable:
         self.rank, self.world = self.group.rank, self.group.world
         self.device = torch.device("cuda", arena.device)
         self.update_fn = make_update_function(conf.update_function)
+        if self.update_fn.params.get("coefficient") not in (None, 1):
+            raise ValueError("the device ADD update has no coefficient; scale the deltas or use a host table")
         self.torch_dtype = torch.float32 if conf.dtype == "float32" else torch.int32
         self.num_blocks = conf.num_total_blocks
         self.rows_per_block = max(1, -(-conf.capacity // self.num_blocks))

@@ -52,9 +52,17 @@ class SimpleScanTasklet(Tasklet):
         return t.get_local_tablet().get_num_data_items()
 
 
-def run_simple() -> bool:
-    master, execs, _ = local_cluster(3)
+def run_simple(table_input: str = "") -> bool:
+    master, execs, launcher = local_cluster(3)
     try:
+        if table_input:          # SimpleET -table_input: bulk load a file into an (ordered, immutable) table first
+            master.create_table(TableConfiguration(table_id="simple_input", num_total_blocks=16, is_ordered=True,
+                                                   is_mutable=False, update_function="void", input_path=table_input,
+                                                   data_parser="default"), execs[:2]).get(60)
+            loaded = sum(ex.tables.get_table("simple_input").get_local_tablet().get_num_data_items()
+                         for ex in list(launcher.executors.values())[:2])
+            with open(table_input) as f:
+                assert loaded == sum(1 for ln in f if ln.strip() and not ln.startswith("#")), loaded
         conf = TableConfiguration(table_id="simple", num_total_blocks=16, update_function="void")
         master.create_table(conf, execs[:2]).get(30)
         table = master.get_table("simple")
@@ -76,9 +84,10 @@ class AddIntegerTasklet(Tasklet):
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
-        for _ in range(p["num_updates"]):
-            for k in range(p["num_keys"]):
-                t.update_no_reply(k, p["delta"])
+        if p.get("metric_flush_period_ms"):
+            self.context.metric_collector.start(int(p["metric_flush_period_ms"]))
+        for i in range(p["num_updates"]):          # UpdaterTask: round-robin over [start_key, start_key + num_keys)
+            t.update_no_reply(p["start_key"] + i % p["num_keys"], p["delta"])
         return True
 
 
@@ -86,23 +95,31 @@ class AddIntegerValidateTasklet(Tasklet):
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
-        expected = p["delta"] * p["num_updates"] * p["num_workers"]
+        # ValidatorTask.java:74
+        expected = (p["num_workers"] * p["num_updates"] // p["num_keys"]) * (p["delta"] * p["coefficient"])
         for _ in range(100):
-            vals = t.multi_get_or_init(list(range(p["num_keys"]))).get(30)
+            vals = t.multi_get_or_init([p["start_key"] + k for k in range(p["num_keys"])]).get(30)
             if all(v == expected for v in vals):
                 return True
             time.sleep(0.1)
         raise AssertionError(f"expected {expected}, got {vals}")
 
 
-def run_addinteger(num_workers: int = 2, num_servers: int = 2) -> bool:
+def run_addinteger(num_workers: int = 2, num_servers: int = 2, num_updates: int = 120, num_keys: int = 8,
+                   start_key: int = 0, delta_value: int = 3, coefficient: int = 2,
+                   metric_flush_period_ms: int = 0) -> bool:
+    if num_updates % num_keys:
+        raise ValueError("num_updates must be a multiple of num_keys (every key gets the same number of updates)")
     master, execs, _ = local_cluster(num_workers + num_servers)
     try:
         servers, workers = execs[:num_servers], execs[num_servers:]
-        conf = TableConfiguration(table_id="addint", num_total_blocks=8, update_function="add")
+        conf = TableConfiguration(table_id="addint", num_total_blocks=8,
+                                  update_function={"name": "add", "params": {"coefficient": coefficient}})
         master.create_table(conf, servers).get(30)
         master.get_table("addint").subscribe(workers).get(30)
-        params = {"table_id": "addint", "num_updates": 20, "num_keys": 10, "delta": 3, "num_workers": num_workers}
+        params = {"table_id": "addint", "num_updates": num_updates, "num_keys": num_keys, "start_key": start_key,
+                  "delta": delta_value, "coefficient": coefficient, "num_workers": num_workers,
+                  "metric_flush_period_ms": metric_flush_period_ms}
         _run_tasklets(workers, "AddIntegerTasklet", params)
         _run_tasklets(workers[:1], "AddIntegerValidateTasklet", params)
         return True
@@ -173,21 +190,50 @@ def run_checkpoint() -> bool:
 
 
 # ---- load -----------------------------------------------------------------------------------------
-def run_load() -> bool:
+def run_load(kv_data_path: str = "", none_key_data_path: str = "") -> bool:
+    """LoadET: one table bulk-loaded from `key value` lines (exist-key loader), one from value lines (none-key
+    loader, keys generated from the local blocks' ranges)."""
+    from ..common.dataloader import DataParser, register_parser
+
+    class KVLineParser(DataParser):
+        has_key = True
+
+        def parse_line(self, line: str):
+            k, _, v = line.partition(" ")
+            return int(k), v
+    register_parser("kv_line", KVLineParser)
     tmp = tempfile.mkdtemp(prefix="hbex")
-    path = os.path.join(tmp, "data")
-    with open(path, "w") as f:
-        for i in range(500):
-            f.write(f"line-{i}\n")
+    if not none_key_data_path:
+        none_key_data_path = os.path.join(tmp, "data")
+        with open(none_key_data_path, "w") as f:
+            for i in range(500):
+                f.write(f"line-{i}\n")
+    if not kv_data_path:
+        kv_data_path = os.path.join(tmp, "kv")
+        with open(kv_data_path, "w") as f:
+            for i in range(300):
+                f.write(f"{i * 7} value-{i}\n")
+
+    def lines(path):
+        with open(path) as f:
+            return [ln.rstrip("\n") for ln in f if ln.strip() and not ln.startswith("#")]
     master, execs, launcher = local_cluster(3)
     try:
         conf = TableConfiguration(table_id="load", num_total_blocks=12, is_ordered=True, is_mutable=False,
-                                  update_function="void", input_path=path, data_parser="default")
+                                  update_function="void", input_path=none_key_data_path, data_parser="default")
         master.create_table(conf, execs).get(60)
         vals = []
         for ex in launcher.executors.values():
             vals += [v for _, v in ex.tables.get_table("load").get_local_tablet().get_data_iterator()]
-        assert sorted(vals) == sorted(f"line-{i}" for i in range(500))
+        assert sorted(vals) == sorted(lines(none_key_data_path))
+        kv = TableConfiguration(table_id="load_kv", num_total_blocks=12, update_function="void",
+                                input_path=kv_data_path, data_parser="kv_line", bulk_loader="exist_key")
+        master.create_table(kv, execs).get(60)
+        got = {}
+        for ex in launcher.executors.values():
+            got.update(dict(ex.tables.get_table("load_kv").get_local_tablet().get_data_iterator()))
+        want = dict((int(ln.partition(" ")[0]), ln.partition(" ")[2]) for ln in lines(kv_data_path))
+        assert got == want, (len(got), len(want))
         return True
     finally:
         master.close()
@@ -195,17 +241,33 @@ def run_load() -> bool:
 
 # ---- metric ---------------------------------------------------------------------------------------
 class MetricTasklet(Tasklet):
+    """MetricET's task: record a custom timestamp metric every `record_ms`, flush manually every `manual_ms`,
+    for `duration_ms` (the collector also flushes by itself every automatic period)."""
+
     def run(self):
+        p = self.context.params
         mc = self.context.metric_collector
         t = self.context.table_accessor.get_table("metric")
-        t.put(self.context.params["index"], 1).get(10)
+        t.put(p["index"], 1).get(10)
         t.get(12345).get(10)
-        mc.add_custom_metric({"who": self.context.executor.executor_id, "value": 42})
+        t0 = last_flush = time.time()
+        n = 0
+        while True:
+            mc.add_custom_metric({"who": self.context.executor.executor_id, "value": 42, "timestamp": time.time()})
+            n += 1
+            now = time.time()
+            if (now - last_flush) * 1000.0 >= p["manual_ms"]:
+                mc.flush()
+                last_flush = now
+            if (now - t0) * 1000.0 >= p["duration_ms"]:
+                break
+            time.sleep(p["record_ms"] / 1000.0)
         mc.flush()
-        return True
+        return n
 
 
-def run_metric() -> bool:
+def run_metric(metric_automatic_flush_period_ms: int = 200, metric_manual_flush_period_ms: int = 100,
+               custom_metric_record_period_ms: int = 20, task_duration_ms: int = 400) -> bool:
     from .driver import MetricReceiver
     master, execs, _ = local_cluster(2)
     got: List[Dict[str, Any]] = []
@@ -218,11 +280,16 @@ def run_metric() -> bool:
         master.create_table(TableConfiguration(table_id="metric", num_total_blocks=4, update_function="void"),
                             execs).get(30)
         for e in execs:
-            master.metrics.start_metric_collection(e.id, 0)
-        _run_tasklets(execs, "MetricTasklet", {})
+            master.metrics.start_metric_collection(e.id, metric_automatic_flush_period_ms)
+        recorded = _run_tasklets(execs, "MetricTasklet",
+                                 {"manual_ms": metric_manual_flush_period_ms, "record_ms": custom_metric_record_period_ms,
+                                  "duration_ms": task_duration_ms}, timeout=120 + task_duration_ms / 1000.0)
         time.sleep(0.3)
+        for e in execs:
+            master.metrics.stop_metric_collection(e.id)
         customs = [c for r in got for c in r["custom_metrics"]]
-        assert len(customs) == 2 and all(c["value"] == 42 for c in customs)
+        assert len(customs) == sum(recorded) and all(c["value"] == 42 for c in customs), (len(customs), recorded)
+        assert len(got) >= 2 * len(execs)                       # several flushes per executor
         assert all(r["table_to_num_blocks"]["metric"] == 2 for r in got)
         return True
     finally:
@@ -285,13 +352,43 @@ def run_centcomm() -> bool:
         master.close()
 
 
+def run_linecount(inputs: str = "") -> bool:
+    """The dataloader example (common/dataloader/examples/LineCountingDriver): every executor counts the lines of
+    its exact byte-range splits; the total must equal the number of lines of the inputs."""
+    from ..common.dataloader import get_splits, read_split
+    if not inputs:
+        tmp = tempfile.mkdtemp(prefix="hbex")
+        inputs = os.path.join(tmp, "lines")
+        with open(inputs, "w") as f:
+            for i in range(1234):
+                f.write(f"{i} {'x' * (i % 17)}\n")
+    total = want = 0
+    for path in [p for p in inputs.split(",") if p]:
+        with open(path) as f:
+            want += sum(1 for _ in f)
+        for split in get_splits(path, 7):
+            total += sum(1 for _ in read_split(split))
+    assert total == want, (total, want)
+    print(f"Total {total} lines")
+    return True
+
+
 ALL = {"simple": run_simple, "addinteger": run_addinteger, "tableaccess": run_tableaccess,
        "checkpoint": run_checkpoint, "load": run_load, "metric": run_metric, "plan": run_plan,
-       "centcomm": run_centcomm}
+       "centcomm": run_centcomm, "linecount": run_linecount}
 
 
 def main(argv: List[str]) -> int:
-    name = argv[0] if argv else "simple"
-    ok = ALL[name]()
+    """`<example> [-flag value ...]` with the reference examples' flag names (dolphin/params.py: ET_EXAMPLES)."""
+    import inspect
+    from ..dolphin import params as P
+    name = argv[0] if argv and not argv[0].startswith("-") else "simple"
+    rest = argv[1:] if argv and not argv[0].startswith("-") else argv
+    conf = P.registry(P.ET_EXAMPLES, [p for p in P.EXAMPLES if p.name in ("num_keys", "start_key")],
+                      [p for p in P.DOLPHIN if p.name == "num_servers"]).parse(rest, allow_unknown=False)[0]
+    fn = ALL[name]
+    given = {a.lstrip("-") for a in rest[0::2]}
+    kwargs = {k: conf[k] for k in inspect.signature(fn).parameters if k in given}
+    ok = fn(**kwargs)
     print(f"LauncherStatus: {'COMPLETED' if ok else 'FAILED'}")
     return 0 if ok else 1

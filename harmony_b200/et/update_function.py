@@ -97,10 +97,12 @@ class AddUpdateFunction(UpdateFunction):
         return self.init_rows(np.asarray([key]), int(dim), np.dtype(self.params.get("dtype", "float32")))[0]
 
     def update_value(self, key, old, delta):
-        return old + delta
+        c = self.params.get("coefficient")          # AddIntegerUpdateFunction.java:45: old + delta * coefficient
+        return old + (delta if c is None else delta * c)
 
     def update_rows(self, old, deltas):
-        return old + deltas
+        c = self.params.get("coefficient")
+        return old + (deltas if c is None else deltas * c)
 
 
 class SGDClampUpdateFunction(AddUpdateFunction):
