@@ -134,6 +134,11 @@ def main_submit(app_path: str, app: ETDolphinConfiguration, argv: Sequence[str])
 
 def main_run(app: ETDolphinConfiguration, argv: Sequence[str]) -> int:
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s %(name)s | %(message)s")
+    from ..utils import trace
+    trace.configure(parse_job_conf(app, argv))
     res = ETDolphinLauncher.launch(app, argv)
+    where = trace.flush_to_receiver()
+    if where:
+        print(f"trace spans -> {where}")
     print(f"LauncherStatus: {res.status}")
     return 0 if res.ok else 1

@@ -107,9 +107,13 @@ ET_EXAMPLES = [
     P("custom_metric_record_period_ms", int, 20, "metric: period of the custom timestamp metric", "user"),
     P("task_duration_ms", int, 400, "metric: tasklet run time", "user"),
     P("inputs", str, "", "linecount: comma-separated input paths (dataloader example)", "user"),
-    P("base_dir", str, "/tmp/harmony_b200", "datastorer base directory", "driver"),
+]
+# ---- shared services: trace (utils/trace/parameters), datastorer base dir, memory tracker ----
+SERVICES = [
+    P("base_dir", str, "/tmp/harmony_b200", "datastorer base directory (also receives trace files)", "driver"),
     P("memory_measure_interval", int, 1000, "memory metric tracker sampling period (ms)", "worker"),
-    P("htrace_receiver_type", str, "CHROME", "STDOUT | ZIPKIN | CHROME: where trace spans go", "client"),
+    P("htrace_receiver_type", str, "", "'' = tracing off | STDOUT | CHROME (chrome://tracing JSON under base_dir) | "
+                                       "ZIPKIN (JSON spans POSTed to host:port)", "client"),
     P("htrace_receiver_host", str, "localhost", "span receiver host (ZIPKIN)", "client"),
     P("htrace_receiver_port", int, 9410, "span receiver port (ZIPKIN)", "client"),
 ]
@@ -123,4 +127,4 @@ def registry(*groups) -> ParamRegistry:
 
 
 def dolphin_registry(*app_groups) -> ParamRegistry:
-    return registry(COMMON, JOBSERVER, DOLPHIN, OPTIMIZER, *app_groups)
+    return registry(COMMON, JOBSERVER, DOLPHIN, OPTIMIZER, SERVICES, *app_groups)

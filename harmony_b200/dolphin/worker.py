@@ -357,8 +357,12 @@ class WorkerTasklet(Tasklet):
         stop = False
         total_batches = 0
         epoch = 0
+        from ..common.metric import MemoryMetricTracker
+        # host RSS + HBM sampled every -memory_measure_interval ms; max / mean ride on the epoch metrics
+        mem = MemoryMetricTracker(max(0.01, int(self.context.params.get("memory_measure_interval", 1000)) / 1000.0))
         while not stop and not self._abort.is_set():
             epoch_t0 = time.perf_counter()
+            mem.start()
             self.data_provider.prepare_data_for_epoch()
             n_batches, n_inst = 0, 0
             while True:
@@ -402,7 +406,8 @@ class WorkerTasklet(Tasklet):
                     time.sleep(0.01)
             if not stop:
                 self.trainer.on_epoch_finished(epoch)
-            em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0)
+            em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0,
+                              epoch_custom_metrics=mem.stop())
             self.context.metric_collector.add_custom_metric(em.to_dict())
             self.context.metric_collector.flush()
             epoch += 1

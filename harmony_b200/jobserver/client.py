@@ -133,13 +133,18 @@ class CommandSender:
 def start_jobserver_main(argv: List[str]) -> int:
     """`start_jobserver.sh` entry point."""
     logging.basicConfig(level=logging.INFO, format="%(asctime)s %(levelname)s %(name)s | %(message)s")
-    reg = P.registry(P.COMMON, P.JOBSERVER)
+    reg = P.registry(P.COMMON, P.JOBSERVER, P.SERVICES)
     conf, _ = reg.parse(argv, allow_unknown=True)
+    from ..utils import trace
+    trace.configure(conf)
     server = JobServer(conf).start()
     print(f"Job Server is ready (port {server.port})", flush=True)
     timeout_ms = int(conf.get("timeout", 0))
     server.wait_closed(None if timeout_ms <= 0 else timeout_ms / 1000.0)
     server.stop(kill=True)
+    where = trace.flush_to_receiver()
+    if where:
+        print(f"trace spans -> {where}", flush=True)
     return 0
 
 

@@ -13,6 +13,7 @@ table (required by the device backend); without it R is a generic KV table on th
 from __future__ import annotations
 
 import logging
+import os
 from typing import Any, Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -92,9 +93,11 @@ def nmf_gradients(L: np.ndarray, R: np.ndarray, ptr, slot, vals, lam: float):
 
 
 class NMFTrainer(Trainer):
-    def __init__(self, params: Dict[str, Any], model_accessor, local_model_table=None, **_: Any) -> None:
+    def __init__(self, params: Dict[str, Any], model_accessor, local_model_table=None, context=None,
+                 input_table=None, **_: Any) -> None:
         self.acc = model_accessor
         self.local = local_model_table
+        self._params, self._context, self._input = params, context, input_table
         self.rank = int(params["rank"])
         self.step = float(params["step_size"])
         self.lam = float(params.get("lambda", 0.0))
@@ -138,6 +141,30 @@ class NMFTrainer(Trainer):
 
     def summary(self) -> Dict[str, float]:
         return {"last_batch_loss": self.last_loss}
+
+    def cleanup(self) -> None:
+        """-print_mat true: store this worker's rows of L and the columns of R it used (NMFTrainer.java:263-300 prints
+        them; here they go through the DataStorer under -base_dir)."""
+        if not self.print_mat or self.local is None:
+            return
+        row_of = {k: rec[0] for k, rec in self._input.get_local_tablet().get_data_iterator()} if self._input else {}
+        items = sorted(((row_of.get(k, k), v) for k, v in self.local.get_local_tablet().get_data_iterator()),
+                       key=lambda kv: kv[0])
+        store_matrices(self._params, self._context, [k for k, _ in items],
+                       np.asarray([v for _, v in items], dtype=np.float32))
+
+
+def store_matrices(params, context, row_keys, L, col_keys=None, R=None) -> str:
+    from ..common.datastorer import LocalFSDataStorer
+    ex = getattr(getattr(context, "executor", None), "executor_id", "worker")
+    ds = LocalFSDataStorer(str(params.get("base_dir", "/tmp/harmony_b200")))
+    sub = os.path.join("nmf", str(params.get("job_id", "job")))
+    text = "".join(f"{int(k) + 1}: " + " ".join(f"{x:.6g}" for x in row) + "\n" for k, row in zip(row_keys, L))
+    path = ds.store_data(os.path.join(sub, f"L-{ex}.txt"), text.encode())
+    if R is not None:
+        text = "".join(f"{int(k) + 1}: " + " ".join(f"{x:.6g}" for x in row) + "\n" for k, row in zip(col_keys, R))
+        ds.store_data(os.path.join(sub, f"R-{ex}.txt"), text.encode())
+    return path
 
 
 def model_table_conf(conf: Configuration, table_id: str) -> TableConfiguration:

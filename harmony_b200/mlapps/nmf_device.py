@@ -13,7 +13,8 @@ class NMFDeviceTrainer(Trainer):
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
 
     def __init__(self, params: Dict[str, Any], model_table, local_model_table=None, input_table=None,
-                 **_: Any) -> None:
+                 context=None, **_: Any) -> None:
+        self._params, self._context = params, context
         import torch
         from ..models.nmf import NMFDeviceModel
         self._torch = torch
@@ -22,7 +23,8 @@ class NMFDeviceTrainer(Trainer):
         self.local_table = local_model_table
         self.rank = int(params["rank"])
         # worker-local L lives in HBM: one row per local input record, in key order
-        self._keys = sorted(k for k, _ in input_table.get_local_tablet().get_data_iterator())
+        self._input_rows = list(input_table.get_local_tablet().get_data_iterator())
+        self._keys = sorted(k for k, _ in self._input_rows)
         self._row_of = {k: i for i, k in enumerate(self._keys)}
         self.model = NMFDeviceModel(self.dtable, self.rank, max(1, len(self._keys)), float(params["step_size"]),
                                     float(params.get("lambda", 0.0)), float(params.get("max_val", 1e6)),
@@ -70,3 +72,7 @@ class NMFDeviceTrainer(Trainer):
         if self.local_table is not None and self._keys:
             L = self.model.L.cpu().numpy()
             self.local_table.multi_put(self._keys, list(L)).get(timeout=600)
+            if self._params.get("print_mat"):
+                from .nmf import store_matrices
+                row_of = {k: rec[0] for k, rec in self._input_rows}
+                store_matrices(self._params, self._context, [row_of.get(k, k) for k in self._keys], L[: len(self._keys)])

@@ -67,6 +67,56 @@ def dump(path: str) -> int:
     return len(evs)
 
 
+def configure(conf) -> Optional[str]:
+    """Apply the `-htrace_receiver_type/-host/-port` + `-base_dir` flags (reference: utils/trace/HTraceParameters).
+    Returns the receiver type when tracing got enabled.  The spans are delivered by `flush_to_receiver()` (called
+    by the launchers / the job server at exit)."""
+    global _receiver
+    kind = str(conf.get("htrace_receiver_type", "") or "").upper()
+    if not kind:
+        return None
+    if kind not in ("STDOUT", "CHROME", "ZIPKIN"):
+        raise ValueError(f"unknown -htrace_receiver_type {kind!r} (STDOUT | CHROME | ZIPKIN)")
+    _receiver = {"kind": kind, "host": conf.get("htrace_receiver_host", "localhost"),
+                 "port": int(conf.get("htrace_receiver_port", 9410)),
+                 "dir": conf.get("base_dir", "/tmp/harmony_b200")}
+    enable(True)
+    return kind
+
+
+_receiver: Optional[Dict[str, Any]] = None
+
+
+def flush_to_receiver() -> Optional[str]:
+    """Deliver the recorded spans to the configured receiver; returns where they went."""
+    r = _receiver
+    if r is None:
+        return None
+    with _lock:
+        evs = list(_events)
+        _events.clear()
+    if r["kind"] == "STDOUT":
+        for e in evs:
+            print(json.dumps(e))
+        return "stdout"
+    if r["kind"] == "ZIPKIN":
+        try:
+            import urllib.request
+            spans = [{"name": e["name"], "timestamp": int(e["ts"]), "duration": int(e["dur"]), "tags": e["args"],
+                      "localEndpoint": {"serviceName": f"harmony_b200-{e['pid']}"}} for e in evs]
+            req = urllib.request.Request(f"http://{r['host']}:{r['port']}/api/v2/spans", data=json.dumps(spans).encode(),
+                                         headers={"Content-Type": "application/json"})
+            urllib.request.urlopen(req, timeout=2).read()
+            return f"zipkin://{r['host']}:{r['port']}"
+        except Exception:  # noqa: BLE001  (collector unreachable: keep the spans on disk)
+            pass
+    os.makedirs(r["dir"], exist_ok=True)
+    path = os.path.join(r["dir"], f"trace-{os.getpid()}.json")
+    with open(path, "w") as f:
+        json.dump({"traceEvents": evs}, f)
+    return path
+
+
 def clear() -> None:
     with _lock:
         _events.clear()
