@@ -17,6 +17,7 @@ Table semantics kept from the reference:
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -26,6 +27,8 @@ from ..parallel.peer import PeerArena, PeerGroup
 from .config import TableConfiguration
 from .partitioner import PART_HASHED, PART_ORDERED
 from .update_function import DEV_ADAGRAD, make_update_function
+
+_CHECK_KEYS = bool(os.environ.get("HB_CHECK_KEYS"))
 
 
 def _round_up(x: int, m: int) -> int:
@@ -151,9 +154,18 @@ class DeviceTable:
         return len(self._local_ptr) * self.block_bytes
 
     # ---- data plane ----
+    def _check_keys(self, keys: torch.Tensor) -> None:
+        """HB_CHECK_KEYS=1: validate keys before a kernel turns them into raw HBM addresses (costs a device sync per
+        call; the loaders already reject out-of-range indices, so this is a debugging aid for library users)."""
+        if _CHECK_KEYS and keys.numel():
+            lo, hi = int(keys.min()), int(keys.max())
+            if lo < 0 or hi >= self.conf.capacity:
+                raise IndexError(f"table {self.conf.table_id}: key range [{lo}, {hi}] outside [0, {self.conf.capacity})")
+
     def pull(self, keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """K1: gather rows by key from whichever GPU owns them."""
         from ..ops import count_launch
+        self._check_keys(keys)
         if out is None:
             out = torch.empty((keys.numel(), self.row_dim), dtype=self.torch_dtype, device=self.device)
         self._n.table_pull(*self.view(), keys, out)
@@ -166,17 +178,20 @@ class DeviceTable:
         fn = self.update_fn.device_fn
         assert fn is not None, f"update function {self.update_fn.name} has no device implementation"
         p = self.update_fn.device_params()
+        self._check_keys(keys)
         self._n.table_push(*self.view(), keys, deltas, fn, p["step"], p["lo"], p["hi"], p["eps"])
         count_launch()
 
     def push_sparse_i32(self, keys: torch.Tensor, topics: torch.Tensor, deltas: torch.Tensor) -> None:
         """K2+K5: LDA sparse (row, topic, delta) triples with clamp>=0 and nnz bookkeeping."""
         from ..ops import count_launch
+        self._check_keys(keys)
         self._n.table_push_sparse_i32(*self.view(), keys, topics, deltas, self.row_dim - 1)
         count_launch()
 
     def put_rows(self, keys: torch.Tensor, values: torch.Tensor) -> None:
         from ..ops import count_launch
+        self._check_keys(keys)
         self._n.table_push(*self.view(), keys, values.contiguous(), 3, 0.0, 0.0, 0.0, 0.0)
         count_launch()
 
