@@ -75,6 +75,10 @@ class Executor:
             self.handler.on_table_access_req(m)
         elif t == "TableAccessRes":
             self.sender.on_table_access_res(m)
+        elif t == "TableAccessReqBatch":
+            self.handler.on_table_access_req_batch(m)
+        elif t == "TableAccessResBatch":
+            self.sender.on_table_access_res_batch(m)
         elif t == "TaskUnitReady":
             self.task_unit_scheduler.on_ready(m)
         else:

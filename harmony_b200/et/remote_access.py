@@ -97,13 +97,14 @@ class MultiKeyDataOpResult(ResultFuture):
 class RemoteDataOp:
     """One (table, block) operation travelling between the origin and the owner."""
     __slots__ = ("op_id", "orig_id", "table_id", "op_type", "block_id", "keys", "values", "reply_required",
-                 "single", "callback", "is_local")
+                 "single", "callback", "is_local", "batch")
 
     def __init__(self, op_id, orig_id, table_id, op_type, block_id, keys, values, reply_required, single,
                  callback=None, is_local=False) -> None:
         self.op_id, self.orig_id, self.table_id, self.op_type = op_id, orig_id, table_id, op_type
         self.block_id, self.keys, self.values = block_id, keys, values
         self.reply_required, self.single, self.callback, self.is_local = reply_required, single, callback, is_local
+        self.batch: Optional["_ReplyBatch"] = None      # owner side: replies of one request batch travel together
 
     def to_msg(self) -> Dict[str, Any]:
         return {"type": "TableAccessReq", "op_id": self.op_id, "orig_id": self.orig_id, "table_id": self.table_id,
@@ -114,6 +115,35 @@ class RemoteDataOp:
     def from_msg(m: Dict[str, Any]) -> "RemoteDataOp":
         return RemoteDataOp(m["op_id"], m["orig_id"], m["table_id"], m["op_type"], m["block_id"], m["keys"],
                             m.get("values"), m["reply_required"], m["single"])
+
+
+class _ReplyBatch:
+    """Owner side of a `TableAccessReqBatch`: the block ops of one multi-key request that target this executor were
+    sent in ONE message; their results go back in one `TableAccessResBatch` once the last of them has executed
+    (ops that had to be forwarded to a new owner leave the batch and are answered individually)."""
+
+    def __init__(self, expected: int, orig_id: str, executor) -> None:
+        self._expected, self._orig, self._ex = expected, orig_id, executor
+        self._results: List[Dict[str, Any]] = []
+        self._lock = threading.Lock()
+
+    def _maybe_send(self) -> None:
+        if len(self._results) >= self._expected and self._results:
+            out, self._results = self._results, []
+            try:
+                self._ex.transport.send(self._orig, {"type": "TableAccessResBatch", "results": out})
+            except NetworkError:
+                LOG.warning("origin %s of a request batch is gone", self._orig)
+
+    def add(self, res: Dict[str, Any]) -> None:
+        with self._lock:
+            self._results.append(res)
+            self._maybe_send()
+
+    def drop(self) -> None:
+        with self._lock:
+            self._expected -= 1
+            self._maybe_send()
 
 
 class CommManager:
@@ -206,6 +236,28 @@ class RemoteAccessOpSender:
             self.stat.inc_count_sent_get_req()
         self._send_with_retry(op, target_id)
 
+    def send_ops(self, ops: List[RemoteDataOp], target_id: str) -> None:
+        """All block ops of one multi-key request that live on `target_id`, in one message (the reference sends one
+        message per block: TableImpl.java:460-501; a GPU-era host has far fewer, fatter peers)."""
+        if len(ops) == 1:
+            return self.send_op(ops[0], target_id)
+        with self._lock:
+            for op in ops:
+                if op.reply_required:
+                    self._ongoing[op.op_id] = op
+        if ops[0].op_type in (GET, GET_OR_INIT):
+            self.stat.inc_count_sent_get_req()
+        try:
+            self._ex.transport.send(target_id, {"type": "TableAccessReqBatch", "orig_id": self._ex.executor_id,
+                                                "ops": [op.to_msg() for op in ops]})
+        except NetworkError:
+            for op in ops:                      # stale ownership: fall back to the per-op path (re-resolves owners)
+                self._send_with_retry(op, target_id)
+
+    def on_table_access_res_batch(self, m: Dict[str, Any]) -> None:
+        for res in m["results"]:
+            self.on_table_access_res(res)
+
     def _send_with_retry(self, op: RemoteDataOp, target_id: str, max_retries: int = 100) -> None:
         comps = self._ex.tables.try_get_components(op.table_id)
         for _ in range(max_retries):
@@ -297,6 +349,15 @@ class RemoteAccessOpHandler:
         op = RemoteDataOp.from_msg(m)
         self._enqueue(op)
 
+    def on_table_access_req_batch(self, m: Dict[str, Any]) -> None:
+        subs = m["ops"]
+        batch = _ReplyBatch(sum(1 for s in subs if s["reply_required"]), m["orig_id"], self._ex)
+        for sub in subs:
+            op = RemoteDataOp.from_msg(sub)
+            if op.reply_required:
+                op.batch = batch
+            self._enqueue(op)
+
     def enqueue_local(self, op: RemoteDataOp) -> None:
         op.is_local = True
         self._enqueue(op)
@@ -373,10 +434,13 @@ class RemoteAccessOpHandler:
             return
         if not op.reply_required:
             return
+        res = {"type": "TableAccessRes", "op_id": op.op_id, "table_id": op.table_id, "block_id": op.block_id,
+               "values": result, "success": ok, "single": op.single}
+        if op.batch is not None:
+            op.batch.add(res)
+            return
         try:
-            self._ex.transport.send(op.orig_id, {"type": "TableAccessRes", "op_id": op.op_id, "table_id": op.table_id,
-                                                  "block_id": op.block_id, "values": result, "success": ok,
-                                                  "single": op.single})
+            self._ex.transport.send(op.orig_id, res)
         except NetworkError:
             LOG.warning("origin %s of op %s is gone", op.orig_id, op.op_id)
 
@@ -389,13 +453,20 @@ class RemoteAccessOpHandler:
             return
         self._forward(op, owner)
 
+    def _leave_batch(self, op: RemoteDataOp) -> None:
+        if op.batch is not None:
+            op.batch.drop()
+            op.batch = None
+
     def _forward(self, op: RemoteDataOp, owner: str) -> None:
+        self._leave_batch(op)
         try:
             self._ex.transport.send(owner, op.to_msg())
         except NetworkError:
             self._redirect_to_driver(op)
 
     def _redirect_to_driver(self, op: RemoteDataOp) -> None:
+        self._leave_batch(op)
         msg = op.to_msg()
         msg["fallback"] = True
         if op.is_local:

@@ -111,30 +111,41 @@ class TableImpl:
         fut = MultiKeyDataOpResult(n, len(groups), dense and op_type in (GET_OR_INIT, UPDATE))
         if values is not None and dense:
             values = np.asarray(values)
-        for pos in groups:
-            block_id = int(blocks[pos[0]])
-            if dense:
-                k = keys_arr[pos]
-                v = None if values is None else values[pos]
-            else:
-                k = [keys_arr[i] for i in pos]
-                v = None if values is None else [values[i] for i in pos]
-
-            def cb(vals, ok, _pos=pos):
-                fut.on_block_completed(_pos, vals, ok)
-
-            op = RemoteDataOp(self._ex.sender.next_op_id(), self._ex.executor_id, self.table_id, op_type, block_id,
-                              k, v, reply_required, False, callback=cb if reply_required else None)
-            owner, unlock = self._c.ownership.resolve_executor_with_lock(block_id)
-            try:
-                if owner is None:
-                    self._ex.handler.execute_local(op, self._c)  # inline, under the ownership read lock
+        by_owner: Dict[str, List[RemoteDataOp]] = {}
+        unlocks = []
+        try:
+            for pos in groups:
+                block_id = int(blocks[pos[0]])
+                if dense:
+                    k = keys_arr[pos]
+                    v = None if values is None else values[pos]
                 else:
-                    self._ex.sender.send_op(op, owner)
-            finally:
-                unlock()
-            if not reply_required:
-                fut.on_block_completed(pos, None, True)
+                    k = [keys_arr[i] for i in pos]
+                    v = None if values is None else [values[i] for i in pos]
+
+                def cb(vals, ok, _pos=pos):
+                    fut.on_block_completed(_pos, vals, ok)
+
+                op = RemoteDataOp(self._ex.sender.next_op_id(), self._ex.executor_id, self.table_id, op_type, block_id,
+                                  k, v, reply_required, False, callback=cb if reply_required else None)
+                owner, unlock = self._c.ownership.resolve_executor_with_lock(block_id)
+                if owner is None:
+                    try:
+                        self._ex.handler.execute_local(op, self._c)  # inline, under the ownership read lock
+                    finally:
+                        unlock()
+                else:
+                    # remote block ops are grouped per owner; the blocks' read locks are held until the message
+                    # is on its way (same ordering guarantee vs ownership updates as the per-block send)
+                    unlocks.append(unlock)
+                    by_owner.setdefault(owner, []).append(op)
+                if not reply_required:
+                    fut.on_block_completed(pos, None, True)
+            for owner, ops in by_owner.items():
+                self._ex.sender.send_ops(ops, owner)
+        finally:
+            for u in unlocks:
+                u()
         return fut
 
     # ---- the 17 ops ----
