@@ -101,14 +101,16 @@ def test_dense_input_mlr_job_uses_tensor_core_path():
     port = _free_port()
     js = JobServer(Configuration({"num_executors": 2, "port": port, "backend": "device"})).start()
     try:
-        args = ["-input", data, "-max_num_epochs", "10", "-num_mini_batches", "4", "-num_worker_blocks", "4",
-                "-num_server_blocks", "8", "-step_size", "0.05", "-classes", "4", "-features", "64",
+        # 32 non-zeros per instance: step 0.05 oscillates (host twin: loss 2-5 on some runs), 0.01 x 30 epochs
+        # converges to ~0.17 on every run
+        args = ["-input", data, "-max_num_epochs", "30", "-num_mini_batches", "4", "-num_worker_blocks", "4",
+                "-num_server_blocks", "8", "-step_size", "0.01", "-classes", "4", "-features", "64",
                 "-dense_input", "true", "-port", str(port)]
         assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
         ok, result = js.driver.wait_job("MLR-0", timeout=120)
         assert ok, result
         loss = np.mean([r["last_batch_loss"] / 64.0 for r in result])
-        assert loss < 1.30, loss
+        assert loss < 0.8, loss
     finally:
         js.stop(kill=True)
 
