@@ -1,0 +1,95 @@
+"""Host-side logic of the SPMD paths, testable without a GPU: ship-mode routing (which owner sees which non-zero),
+the PeerGroup bootstrap over gloo with 2 processes, and the control-plane rendezvous group."""
+import os
+import subprocess
+import sys
+import textwrap
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from harmony_b200.et.partitioner import PART_HASHED, PART_ORDERED
+from harmony_b200.models.mlr import synthetic_batch
+from harmony_b200.models.mlr_ship import owner_of_features, route_batches
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _stub_table(mode, F, world, num_blocks):
+    rpb = -(-F // num_blocks)
+    owners = [b % world for b in range(num_blocks)]
+    return SimpleNamespace(mode=mode, rows_per_block=rpb, num_blocks=num_blocks, owners=owners)
+
+
+@pytest.mark.parametrize("mode", [PART_ORDERED, PART_HASHED])
+@pytest.mark.parametrize("world", [2, 3])
+def test_ship_routing_covers_every_nonzero_exactly_once(mode, world):
+    """Sum over owners of the partial logits of the routed slices == X . W of the original batches: every non-zero
+    goes to exactly one owner, rows keep their (worker, instance) identity, values are untouched."""
+    F, C, B, nnz = 500, 7, 33, 9
+    table = _stub_table(mode, F, world, 16)
+    rng = np.random.default_rng(0)
+    W = rng.standard_normal((F, C))
+    batches = [synthetic_batch(B, F, C, nnz, seed=10 + w) for w in range(world)]
+    full = np.zeros((world * B, C))
+    for w, mb in enumerate(batches):
+        ptr, col, val = mb.csr_ptr.numpy(), mb.csr_col.numpy(), mb.csr_val.numpy()
+        rows = np.repeat(np.arange(B), np.diff(ptr))
+        np.add.at(full, w * B + rows, val[:, None] * W[col])
+    partial_sum = np.zeros_like(full)
+    total_nnz = 0
+    for rank in range(world):
+        rb = route_batches(table, batches, rank)
+        r = rb.routed
+        ptr, col, val = r.csr_ptr.numpy(), r.csr_col.numpy(), r.csr_val.numpy()
+        assert len(ptr) == world * B + 1 and ptr[0] == 0 and ptr[-1] == len(col)
+        assert np.all(owner_of_features(table, col) == rank)                 # only features this rank owns
+        rows = np.repeat(np.arange(world * B), np.diff(ptr))
+        np.add.at(partial_sum, rows, val[:, None] * W[col])
+        total_nnz += len(col)
+        np.testing.assert_array_equal(rb.labels.numpy(), batches[rank].labels.numpy())
+        # feature-major grouping of the routed slice (what the owner-side update kernel walks)
+        fp, uf = r.feat_ptr.numpy(), r.uniq_feat.numpy()
+        assert fp[-1] == len(col) and np.all(np.diff(uf) > 0)
+        for j in (0, len(uf) // 2, len(uf) - 1):
+            members = np.sort(r.samp.numpy()[fp[j]:fp[j + 1]])
+            np.testing.assert_array_equal(members, np.sort(rows[col == uf[j]]))
+    assert total_nnz == sum(len(mb.csr_col) for mb in batches)
+    np.testing.assert_allclose(partial_sum, full, rtol=1e-6, atol=1e-6)
+    # executor-id owners (job-server mode) are mapped through owner_ranks
+    table.owners = [f"executor-{b % world}" for b in range(16)]
+    ranks = [b % world for b in range(16)]
+    rb = route_batches(table, batches, 0, ranks)
+    assert np.all(owner_of_features(table, rb.routed.csr_col.numpy(), ranks) == 0)
+
+
+def test_peer_group_bootstrap_over_gloo_two_processes(tmp_path):
+    """`PeerGroup.from_env()` is the only use of torch.distributed in the SPMD path (handle exchange, barriers):
+    run it with the gloo backend on 2 CPU processes (127.0.0.1 rendezvous)."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        from harmony_b200.parallel.peer import PeerGroup
+        g = PeerGroup.from_env()
+        assert (g.rank, g.world) == (int(os.environ["RANK"]), 2)
+        got = g.all_gather_object({{"rank": g.rank, "handle": bytes([g.rank]) * 4}})
+        assert [x["rank"] for x in got] == [0, 1] and got[1]["handle"] == b"\\x01" * 4
+        g.barrier()
+        dist.destroy_process_group()
+        print("ok", g.rank)
+    """))
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert sorted(o.strip().splitlines()[-1] for o in outs) == ["ok 0", "ok 1"]
