@@ -192,3 +192,16 @@ def test_unified_cli_and_flag_reference(tmp_path, capsys):
     assert open(os.path.join(root, "docs", "FLAGS.md")).read() == flags_markdown()     # regenerate when flags change
     assert main(["et-example", "simple"]) == 0
     assert main(["run", "nosuchapp"]) == 2 and main(["frobnicate"]) == 2
+
+
+def test_bench_reference_arm_reports_unavailable():
+    """bench.py --impl reference: the reference is Java/REEF and cannot be installed here; the arm must say so in
+    one JSON line and exit 0 (driver contract)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1",
+                        "--steps", "3", "--warmup", "3"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and isinstance(line["unavailable"], str) and line["unavailable"]
