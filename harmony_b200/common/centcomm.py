@@ -14,6 +14,10 @@ Handler = Callable[[str, Any], None]     # (source id, data)
 
 
 class MasterSideCentComm:
+    """Driver side of the named message channels between the driver and its executors.  Reference:
+    common/src/main/java/edu/snu/cay/common/centcomm/master/MasterSideCentCommMsgSender.java,
+    CentCommConf.java:46-145."""
+
     def __init__(self, et_master) -> None:
         self._m = et_master
 
@@ -26,6 +30,9 @@ class MasterSideCentComm:
 
 
 class SlaveSideCentComm:
+    """Executor side of CentComm.  Reference:
+    common/src/main/java/edu/snu/cay/common/centcomm/slave/SlaveSideCentCommMsgSender.java."""
+
     def __init__(self, executor) -> None:
         self._ex = executor
 

@@ -29,6 +29,9 @@ def strip_scheme(path: str) -> str:
 
 @dataclass
 class SplitInfo:
+    """Serialisable byte-range split of an input file.  Reference:
+    common/src/main/java/edu/snu/cay/common/dataloader/HdfsSplitInfo.java, HdfsSplitManager.java:46-80."""
+
     path: str
     start: int
     length: int
@@ -125,6 +128,11 @@ def read_split(split: SplitInfo) -> Iterator[str]:
 # parsers  (value parsers return `value`; key-value parsers return `(key, value)`)
 # ------------------------------------------------------------------------------------------
 class DataParser:
+    """lines -> records (value parsers) or (key, value) pairs (key-value parsers); sparse text formats have a
+    native multi-threaded twin (ops/csrc/loader.cpp).  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/api/DataParser.java,
+    impl/DefaultDataParser.java."""
+
     has_key = False
     native_mode: Optional[int] = None      # ops/csrc/loader.cpp format id (0 `y i:v`, 1 `r: c,v`, 2 `w w w`)
 
@@ -192,6 +200,9 @@ class DataParser:
 
 
 class DefaultDataParser(DataParser):
+    """Every non-empty, non-comment line is one value.  Reference:
+    services/et/.../evaluator/impl/DefaultDataParser.java."""
+
     pass
 
 

@@ -5,11 +5,17 @@ import os
 
 
 class DataStorer:
+    """Write bytes under a base directory.  Reference:
+    common/src/main/java/edu/snu/cay/common/datastorer/DataStorer.java:24-33."""
+
     def store_data(self, sub_path: str, data: bytes) -> str:
         raise NotImplementedError
 
 
 class LocalFSDataStorer(DataStorer):
+    """DataStorer on the local file system (-base_dir).  Reference:
+    common/src/main/java/edu/snu/cay/common/datastorer/LocalFSDataStorer.java:34-55."""
+
     def __init__(self, base_dir: str) -> None:
         self.base_dir = base_dir
 

@@ -17,6 +17,10 @@ Scalar = Union[int, float]
 
 
 class Vector:
+    """Dense / sparse float vector API (length, get/set, slice, add/sub/scale/div +-in-place, axpy, dot) over torch
+    tensors.  Reference: common/src/main/java/edu/snu/cay/common/math/linalg/Vector.java,
+    breeze/DenseVector.java:288-307."""
+
     def __init__(self, data: torch.Tensor) -> None:
         self.t = data
 
@@ -94,6 +98,9 @@ class Vector:
 
 
 class Matrix:
+    """Dense / CSC float matrix API (rows / columns, transpose, element-wise ops, mmul).  Reference:
+    common/src/main/java/edu/snu/cay/common/math/linalg/Matrix.java, breeze/DenseMatrix.java."""
+
     def __init__(self, data: torch.Tensor) -> None:
         self.t = data
 
@@ -179,6 +186,9 @@ class Matrix:
 
 
 class VectorFactory:
+    """Dense-zeros / dense-from-array / sparse constructors.  Reference:
+    common/src/main/java/edu/snu/cay/common/math/linalg/VectorFactory.java."""
+
     def __init__(self, device: str = "cpu", dtype=torch.float32) -> None:
         self.device, self.dtype = device, dtype
 
@@ -204,6 +214,9 @@ class VectorFactory:
 
 
 class MatrixFactory:
+    """Dense / CSC matrix constructors.  Reference:
+    common/src/main/java/edu/snu/cay/common/math/linalg/MatrixFactory.java."""
+
     def __init__(self, device: str = "cpu", dtype=torch.float32) -> None:
         self.device, self.dtype = device, dtype
 

@@ -16,6 +16,9 @@ from ..utils.misc import device_memory_mb, used_memory_mb
 
 
 class MetricTracker:
+    """start() / stop() -> metric dict SPI of the generic metric framework.  Reference:
+    common/src/main/java/edu/snu/cay/common/metric/MetricTracker.java."""
+
     def start(self) -> None:
         pass
 
@@ -27,6 +30,9 @@ class MetricTracker:
 
 
 class TimeMetricTracker(MetricTracker):
+    """Wall-clock time between start and stop.  Reference:
+    common/src/main/java/edu/snu/cay/common/metric/TimeMetricTracker.java."""
+
     KEY = "METRIC_WALL_TIME_SEC"
 
     def start(self) -> None:
@@ -86,6 +92,9 @@ class DeviceTimeMetricTracker(MetricTracker):
 
 
 class InsertableMetricTracker(MetricTracker):
+    """User-inserted key/value metrics.  Reference:
+    common/src/main/java/edu/snu/cay/common/metric/InsertableMetricTracker.java."""
+
     def __init__(self) -> None:
         self._vals: Dict[str, float] = {}
 
@@ -98,6 +107,9 @@ class InsertableMetricTracker(MetricTracker):
 
 
 class MetricsCollector:
+    """Aggregates the registered trackers' metrics between start() and stop() and hands them to a handler.
+    Reference: common/src/main/java/edu/snu/cay/common/metric/MetricsCollector.java."""
+
     def __init__(self, handler: Optional[Callable[[Dict[str, float]], None]] = None) -> None:
         self._trackers: List[MetricTracker] = []
         self._handler = handler

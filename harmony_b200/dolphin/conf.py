@@ -18,6 +18,10 @@ TableConfFn = Callable[[Configuration, str], TableConfiguration]
 
 @dataclass
 class ETDolphinConfiguration:
+    """App descriptor: trainer, input parser, model / local-model table factories, extra parameters (+ the GPU
+    trainer).  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/client/ETDolphinConfiguration.java:45-64,175-278."""
+
     app_id: str                                   # "MLR", "NMF", ...
     trainer_class: str                            # "module:Class"
     input_parser: Any                             # parser name / spec (common/dataloader.py)

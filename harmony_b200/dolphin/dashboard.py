@@ -22,6 +22,10 @@ LOG = logging.getLogger(__name__)
 
 
 class DashboardServer:
+    """Metric dashboard: HTTP endpoint receiving every metric as form data, sqlite store, plot page.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/dashboard/DashboardConnector.java:112-217,
+    DashboardLauncher.java, jobserver/bin/dashboard.py."""
+
     def __init__(self, port: int = 9005, db_path: str = ":memory:") -> None:
         self.port = port
         self._db = sqlite3.connect(db_path, check_same_thread=False)

@@ -13,6 +13,9 @@ from typing import Any, Callable, Dict, List, Tuple
 
 
 class MasterSideRendezvous:
+    """Master half of the job-level gather used by SPMD-style trainers (ship mode): collects one object per worker
+    and replies to all.  No reference twin (the reference has no peer-to-peer data plane)."""
+
     def __init__(self, send_to_worker: Callable[[str, Dict[str, Any]], None]) -> None:
         self._send = send_to_worker
         self._pending: Dict[Tuple[str, int], Dict[str, Any]] = {}

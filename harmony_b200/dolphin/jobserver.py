@@ -66,6 +66,10 @@ def build_tables_confs(app: ETDolphinConfiguration, conf: Configuration, job_cou
 
 
 class DolphinJobMaster(JobMaster):
+    """JobMaster of a Dolphin job inside the job server: routes tasklet messages to the DolphinMaster, runs it,
+    returns the results.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/jobserver/DolphinJobMaster.java:65-87."""
+
     def __init__(self, entity: "DolphinJobEntity") -> None:
         self.entity = entity
         self.dolphin_master: Optional[DolphinMaster] = None
@@ -102,6 +106,10 @@ class DolphinJobMaster(JobMaster):
 
 
 class DolphinJobEntity(JobEntity):
+    """A submitted Dolphin job: its configuration, executors (co-located workers / servers) and tables (model,
+    local model, input).  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/jobserver/DolphinJobEntity.java:76-121."""
+
     def __init__(self, driver: JobServerDriver, conf: Configuration, app: ETDolphinConfiguration, job_id: str,
                  server_tc: TableConfiguration, worker_tc: TableConfiguration,
                  local_tc: Optional[TableConfiguration]) -> None:

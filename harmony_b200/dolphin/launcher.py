@@ -33,6 +33,10 @@ def parse_job_conf(app: ETDolphinConfiguration, argv: Sequence[str]) -> Configur
 
 
 class DolphinJobLauncher:
+    """Client side of `submit_<app>.sh`: flags -> one serialisable job configuration -> SUBMIT command to the job
+    server.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/jobserver/DolphinJobLauncher.java:75-144,147-196."""
+
     @staticmethod
     def submit_job(app_path: str, app: ETDolphinConfiguration, argv: Sequence[str],
                    port: Optional[int] = None) -> str:
@@ -43,6 +47,8 @@ class DolphinJobLauncher:
 
 
 class LauncherResult:
+    """Outcome of a stand-alone run (`run_<app>.sh`): COMPLETED / FAILED plus the worker results."""
+
     def __init__(self, ok: bool, results: Any, messages: List[str], master: Optional[DolphinMaster]) -> None:
         self.ok, self.results, self.messages, self.dolphin_master = ok, results, messages, master
 
@@ -52,6 +58,11 @@ class LauncherResult:
 
 
 class ETDolphinLauncher:
+    """Stand-alone launcher (own driver per app, `run_<app>.sh`): worker / server executors, tables, bulk load,
+    training, optional optimizer, dashboard and offline evaluation.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/client/ETDolphinLauncher.java:111-211,226-327,
+    core/driver/DolphinDriver.java:97-162,262-346."""
+
     @staticmethod
     def launch(app: ETDolphinConfiguration, argv: Sequence[str],
                extra_conf: Optional[Dict[str, Any]] = None) -> LauncherResult:

@@ -28,6 +28,10 @@ EVAL_TASKLET = "harmony_b200.dolphin.worker:ModelEvaluationTasklet"
 
 
 class MasterSideMsgSender:
+    """Master -> worker Dolphin messages (release, mini-batch control, model-eval answers) wrapped as tasklet
+    custom messages.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/master/MasterSideMsgSender.java:66-111."""
+
     def __init__(self, task_runner: "ETTaskRunner") -> None:
         self._runner = task_runner
 
@@ -49,6 +53,11 @@ class MasterSideMsgSender:
 
 
 class WorkerStateManager:
+    """Global worker barrier FSM INIT -> RUN <-> OPTIMIZE -> RUN_FINISHING -> CLEANUP: workers send SyncMsg(state),
+    the master releases all of them once every running worker is blocked; workers added or deleted by a plan are
+    accounted for.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/master/WorkerStateManager.java:94-116,152-199,204-262,269-346."""
+
     def __init__(self, num_workers: int, sender: MasterSideMsgSender, log: Callable[[str], None] = LOG.info) -> None:
         self.num_workers = num_workers
         self._sender = sender
@@ -207,6 +216,10 @@ class MiniBatchController:
 
 
 class BatchProgressTracker:
+    """Counts ProgressMsgs, prints `Epoch progress: [e / E]` for the client and triggers the per-epoch model
+    checkpoint when -offline_model_eval is on.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/master/BatchProgressTracker.java:84-105."""
+
     def __init__(self, job_id: str, num_epochs: int, num_mini_batches_in_epoch: int,
                  report: Callable[[str], None], on_epoch: Optional[Callable[[int], None]] = None) -> None:
         self.job_id, self.num_epochs, self.per_epoch = job_id, num_epochs, max(1, num_mini_batches_in_epoch)
@@ -265,6 +278,10 @@ class ModelChkpManager:
 
 
 class ETTaskRunner:
+    """Submits the server tasklets (idle latch) and the worker tasklets, waits for the run stage, collects the
+    results and follows executor-set changes made by the optimizer; a failed tasklet fails the job fast.
+    Reference: jobserver/src/main/java/edu/snu/cay/dolphin/core/master/ETTaskRunner.java:82-106,121-172,174-189."""
+
     def __init__(self, master: ETMaster, job_id: str) -> None:
         self._m = master
         self.job_id = job_id

@@ -15,6 +15,9 @@ from typing import Any, Dict, List, Optional
 
 @dataclass
 class BatchMetrics:
+    """Per-mini-batch worker metrics (times, processing rate, custom metrics).  Reference:
+    jobserver/src/main/avro/metrics.avsc (BatchMetrics)."""
+
     job_id: str
     worker_id: str
     epoch_idx: int
@@ -36,6 +39,8 @@ class BatchMetrics:
 
 @dataclass
 class EpochMetrics:
+    """Per-epoch worker metrics.  Reference: jobserver/src/main/avro/metrics.avsc (EpochMetrics)."""
+
     job_id: str
     worker_id: str
     epoch_idx: int
@@ -51,6 +56,10 @@ class EpochMetrics:
 
 @dataclass
 class WorkerMetrics:
+    """Driver-side record of one worker report (what the optimizer consumes).  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/metric/ETDolphinMetricReceiver.java:64-201, metrics.avsc
+    (DolphinWorkerMetrics)."""
+
     worker_id: str
     hostname: str
     num_data_blocks: int
@@ -62,6 +71,9 @@ class WorkerMetrics:
 
 @dataclass
 class ServerMetrics:
+    """Driver-side record of one server report.  Reference: metrics.avsc (ServerMetrics),
+    ETDolphinMetricReceiver.java:64-201."""
+
     server_id: str
     hostname: str
     num_model_blocks: int

@@ -35,6 +35,9 @@ NVLINK_BPS = 770e9 * 8       # measured peer copy bandwidth per direction per GP
 
 @dataclass
 class EvaluatorParameters:
+    """What the optimizer knows about one executor: id, number of blocks, averaged metrics.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/optimizer/api/EvaluatorParameters.java."""
+
     id: str
     num_blocks: int
     metrics: Dict[str, float] = field(default_factory=dict)    # comp_time, pull_time, bytes, ...
@@ -87,12 +90,17 @@ class MetricProcessor:
 
 
 class Optimizer:
+    """SPI: (evaluator parameters, available executors, model parameters) -> Plan.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/optimizer/api/Optimizer.java."""
+
     def optimize(self, eval_params: Dict[str, List[EvaluatorParameters]], available_evaluators: int,
                  model_params: Dict[str, float]) -> Plan:
         raise NotImplementedError
 
 
 class EmptyPlanOptimizer(Optimizer):
+    """Never changes anything (the default -optimizer).  Reference: optimizer/impl/EmptyPlanOptimizer.java."""
+
     def optimize(self, eval_params, available_evaluators, model_params) -> Plan:
         return empty_plan()
 
@@ -107,6 +115,10 @@ class _Summary:
 
 
 class HomogeneousOptimizer(Optimizer):
+    """Cost-model optimizer: picks the worker / server split minimising estimated epoch time = max(compute,
+    communication) with bandwidth-proportional server blocks, then emits add / delete / move steps.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/optimizer/impl/HomogeneousOptimizer.java:127-210,255-289,311-423,461-528."""
+
     def __init__(self, num_total_mini_batches: int, default_bandwidth: float = NVLINK_BPS,
                  opt_benefit_threshold: float = 0.0, host_to_bandwidth: Optional[Dict[str, float]] = None) -> None:
         self.B = num_total_mini_batches
@@ -251,6 +263,9 @@ def _most_blocks(params: List[EvaluatorParameters]) -> EvaluatorParameters:
 
 
 class AddOneServerOptimizer(_OneShot):
+    """Sample optimizer: add one server and give it half of the most loaded server's blocks.  Reference:
+    optimizer/impl/SampleOptimizers.java:100-363."""
+
     def _plan(self, ep, avail):
         p = Plan()
         src = _most_blocks(ep[NAMESPACE_SERVER])
@@ -261,6 +276,9 @@ class AddOneServerOptimizer(_OneShot):
 
 
 class AddOneWorkerOptimizer(_OneShot):
+    """Sample optimizer: add one worker with half of the most loaded worker's input blocks.  Reference:
+    SampleOptimizers.java:100-363."""
+
     def _plan(self, ep, avail):
         p = Plan()
         src = _most_blocks(ep[NAMESPACE_WORKER])
@@ -271,6 +289,9 @@ class AddOneWorkerOptimizer(_OneShot):
 
 
 class DeleteOneServerOptimizer(_OneShot):
+    """Sample optimizer: delete the last server after moving its blocks to the first.  Reference:
+    SampleOptimizers.java:100-363 (used by OwnershipFirstMigrationTest)."""
+
     def _plan(self, ep, avail):
         p = Plan()
         servers = ep[NAMESPACE_SERVER]
@@ -284,6 +305,9 @@ class DeleteOneServerOptimizer(_OneShot):
 
 
 class DeleteOneWorkerOptimizer(_OneShot):
+    """Sample optimizer: delete the last worker after moving its input blocks away.  Reference:
+    SampleOptimizers.java:100-363."""
+
     def _plan(self, ep, avail):
         p = Plan()
         workers = ep[NAMESPACE_WORKER]

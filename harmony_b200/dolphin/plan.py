@@ -21,6 +21,9 @@ HOMOGENEOUS, HETEROGENEOUS = "HOMOGENEOUS", "HETEROGENEOUS"
 
 @dataclass(frozen=True)
 class TransferStep:
+    """Move `num_blocks` blocks from `src` to `dst` inside one namespace.  Reference:
+    dolphin/plan/api/TransferStep.java."""
+
     src_id: str
     dst_id: str
     num_blocks: int
@@ -28,6 +31,9 @@ class TransferStep:
 
 @dataclass
 class Plan:
+    """Optimizer output: evaluators to add / delete and transfer steps per namespace (SERVER / WORKER).  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/plan/impl/PlanImpl.java."""
+
     evaluators_to_add: Dict[str, List[str]] = field(default_factory=lambda: {NAMESPACE_SERVER: [], NAMESPACE_WORKER: []})
     evaluators_to_delete: Dict[str, List[str]] = field(default_factory=lambda: {NAMESPACE_SERVER: [], NAMESPACE_WORKER: []})
     transfer_steps: Dict[str, List[TransferStep]] = field(default_factory=lambda: {NAMESPACE_SERVER: [], NAMESPACE_WORKER: []})
@@ -65,6 +71,10 @@ def empty_plan(optimizer_type: str = HOMOGENEOUS) -> Plan:
 
 
 class PlanCompiler:
+    """Plan -> ETPlan DAG: switch (server <-> worker without reallocation), add, delete, move, with the dependency
+    edges between allocate / associate / subscribe / move / start / stop ops.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/plan/impl/PlanCompiler.java:159-232,234-274,304-380,382-423,425-472,474-523."""
+
     def __init__(self, model_table_id: str, input_table_id: str,
                  worker_tasklet_conf: Callable[[str], TaskletConfiguration],
                  server_tasklet_conf: Callable[[str], TaskletConfiguration],

@@ -61,6 +61,9 @@ class Trainer:
 
 
 class ModelAccessor:
+    """Trainer-facing pull / push SPI over the model table.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/worker/ModelAccessor.java:29-83."""
+
     def push(self, key, delta) -> None: raise NotImplementedError
     def push_many(self, keys, deltas) -> None: raise NotImplementedError
     def pull(self, key): raise NotImplementedError
@@ -157,6 +160,9 @@ class CachedModelAccessor(ETModelAccessor):
 
 
 class TrainingDataProvider:
+    """Mini-batch source SPI.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/core/worker/TrainingDataProvider.java:26-51."""
+
     def prepare_data_for_epoch(self) -> None: raise NotImplementedError
     def get_next_batch_data(self) -> List[Tuple[Any, Any]]: raise NotImplementedError
     def get_epoch_data(self) -> List[Tuple[Any, Any]]: raise NotImplementedError
@@ -199,6 +205,9 @@ class ETTrainingDataProvider(TrainingDataProvider):
 # barriers / messaging
 # ------------------------------------------------------------------------------------------
 class WorkerSideMsgSender:
+    """Worker -> master Dolphin messages (progress, sync, mini-batch sync, model-eval ask, group gather).
+    Reference: jobserver/src/main/java/edu/snu/cay/dolphin/core/worker/WorkerSideMsgSender.java:64-127."""
+
     def __init__(self, context, job_id: str) -> None:
         self._ctx = context
         self.job_id = job_id
@@ -256,6 +265,9 @@ class MiniBatchBarrier:
 
 
 class ModelEvalBarrier:
+    """Worker side of the offline model evaluation loop: asks the master whether another checkpoint is to be
+    evaluated.  Reference: jobserver/src/main/java/edu/snu/cay/dolphin/core/worker/ModelEvaluator.java:69-147."""
+
     def __init__(self, sender: WorkerSideMsgSender) -> None:
         self._sender = sender
         self._ev = threading.Semaphore(0)

@@ -22,10 +22,16 @@ from .update_function import UpdateFunction
 
 
 class BlockNotExistsError(KeyError):
+    """The block is not (or no longer) stored on this executor."""
+
     pass
 
 
 class Block:
+    """One block of a table: per-key ops + bulk export / import for migration and checkpoint.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/BlockImpl.java:65-76,
+    BlockStore.java:55-117."""
+
     block_id: int
 
     def put(self, key, value): raise NotImplementedError
@@ -55,6 +61,8 @@ class Block:
 
 
 class DictBlock(Block):
+    """Generic key-value block (hash map + update function) for non-dense tables."""
+
     def __init__(self, block_id: int, update_fn: UpdateFunction) -> None:
         self.block_id = block_id
         self._fn = update_fn

@@ -66,6 +66,10 @@ def _sample(keys, values, ratio: float):
 
 
 class ChkpManagerSlave:
+    """Executor side of checkpointing: conf + one file per local block (optionally sampled) into the temp dir under
+    the write lock, commit on stop, load with re-blocking.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/ChkpManagerSlave.java:146-201,203-220,226-293,346-455,467-484."""
+
     def __init__(self, executor, temp_path: str, commit_path: str) -> None:
         self._ex = executor
         self.temp_root = os.path.join(temp_path, executor.executor_id)

@@ -20,6 +20,10 @@ NUM_TASKLETS_DEFAULT = 4
 
 @dataclass
 class TableConfiguration:
+    """Everything that defines a table: id, blocks, mutability, ordering, update function, input / checkpoint path,
+    parser, dense row layout, backend.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/configuration/TableConfiguration.java."""
+
     table_id: str
     # --- layout ---
     dense: bool = False               # dense slab table (bounded int key space) vs generic KV table
@@ -56,6 +60,9 @@ class TableConfiguration:
 
 @dataclass
 class ResourceConfiguration:
+    """Cores / memory / node (here: GPU ordinal) of an executor.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/configuration/ResourceConfiguration.java."""
+
     num_cores: int = 1
     mem_size_mb: int = 128
     node_names: List[str] = field(default_factory=list)
@@ -64,6 +71,9 @@ class ResourceConfiguration:
 
 @dataclass
 class RemoteAccessConfiguration:
+    """Queue sizes and thread counts of the remote-access handler / sender.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/configuration/RemoteAccessConfiguration.java."""
+
     handler_queue_size: int = COMM_QUEUE_SIZE_DEFAULT
     sender_queue_size: int = COMM_QUEUE_SIZE_DEFAULT
     num_handler_threads: int = NUM_COMM_THREADS_DEFAULT
@@ -72,6 +82,9 @@ class RemoteAccessConfiguration:
 
 @dataclass
 class ExecutorConfiguration:
+    """Tasklet slots, resources, remote-access configuration, checkpoint paths of an executor.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/configuration/ExecutorConfiguration.java."""
+
     resource: ResourceConfiguration = field(default_factory=ResourceConfiguration)
     remote_access: RemoteAccessConfiguration = field(default_factory=RemoteAccessConfiguration)
     num_tasklets: int = NUM_TASKLETS_DEFAULT
@@ -95,6 +108,9 @@ class ExecutorConfiguration:
 
 @dataclass
 class TaskletConfiguration:
+    """Tasklet id, class, custom message handler, user parameters.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/configuration/TaskletConfiguration.java."""
+
     tasklet_id: str
     tasklet_class: str                # "module:ClassName"
     msg_handler_class: Optional[str] = None

@@ -110,6 +110,9 @@ class DeviceBlock(Block):
 
 
 class DeviceBlockStore(BlockStore):
+    """BlockStore facade over the HBM slabs of a device table (checkpoint, tablet iteration, tests see blocks; the
+    data plane bypasses it)."""
+
     def __init__(self, dtable) -> None:
         super().__init__(lambda b: DeviceBlock(b, dtable))
         self._t = dtable
@@ -126,6 +129,9 @@ class DeviceBlockStore(BlockStore):
 
 
 class DeviceTableComponents(TableComponents):
+    """Per-table state of a device executor: DeviceTable, ownership cache, read/write gate (device twin of the
+    per-block ownership locks), ready event."""
+
     def __init__(self, conf: TableConfiguration, executor: "DeviceExecutor") -> None:
         super().__init__(conf, executor)
         self.dtable = None                    # created in init (needs the block owners)
@@ -230,6 +236,9 @@ class DeviceTableImpl(TableImpl):
 
 
 class DeviceExecutor(Executor):
+    """Executor whose dense `backend=device` tables live in HBM slabs of a CUDA-IPC exported arena; handles the
+    device flavour of table init, peer map, quiesce / resume, migration receive and ownership flip."""
+
     def __init__(self, executor_id: str, transport: Transport, conf: Optional[ExecutorConfiguration] = None,
                  driver_id: str = "driver", device: Optional[int] = None) -> None:
         conf = conf or ExecutorConfiguration()

@@ -189,6 +189,9 @@ class SubscriptionManager:
 # Migration manager
 # ==========================================================================================
 class MigrationResult:
+    """Outcome of a moveBlocks call.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/MigrationResult.java."""
+
     def __init__(self, completed: bool, msg: str, migrated_blocks: List[int]) -> None:
         self.is_completed, self.msg, self.migrated_blocks = completed, msg, migrated_blocks
 
@@ -204,6 +207,10 @@ class _Migration:
 
 
 class MigrationManager:
+    """Driver side of host-table migration: op ids, MoveInit to the sender, ownership / data moved bookkeeping
+    (arrival order fixed per block), broadcast to the other subscribers, completion.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/MigrationManager.java:76-92,101-172."""
+
     def __init__(self, master: "ETMaster") -> None:
         self._m = master
         self._ongoing: Dict[int, _Migration] = {}
@@ -267,6 +274,10 @@ class MigrationManager:
 # Table control agent (fan-out / fan-in)
 # ==========================================================================================
 class TableControlAgent:
+    """Fan-out / fan-in of table control messages (init, load with 32 splits per executor, drop, ownership sync,
+    device peer map / quiesce / flip) with aggregate futures; a failed executor fails the future.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/TableControlAgent.java:43,66-133,163-237."""
+
     def __init__(self, master: "ETMaster") -> None:
         self._m = master
         self._futs: Dict[int, AggregateFuture] = {}
@@ -346,6 +357,10 @@ class TableControlAgent:
 # Checkpoint master
 # ==========================================================================================
 class ChkpManagerMaster:
+    """Checkpoint ids `<tableId>-<ms>`, ChkpStart to the associators, temp vs committed blocks, restore (possibly
+    with a different blocking / executor set) from id or path.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/ChkpManagerMaster.java:142-168,177-206,208-245,250-301,309-418."""
+
     def __init__(self, master: "ETMaster", temp_path: str, commit_path: str) -> None:
         self._m = master
         self.temp_path, self.commit_path = temp_path, commit_path
@@ -550,6 +565,9 @@ class GlobalTaskUnitScheduler:
 # Tasklets (driver view)
 # ==========================================================================================
 class TaskletResult:
+    """Final status + result of a tasklet.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/TaskletResult.java."""
+
     def __init__(self, tasklet_id: str, executor_id: str, status: str, result: Any, error: Optional[str]) -> None:
         self.tasklet_id, self.executor_id, self.status, self.result, self.error = \
             tasklet_id, executor_id, status, result, error
@@ -629,6 +647,9 @@ class InProcessLauncher(ExecutorLauncher):
 
 
 class AllocatedExecutor:
+    """Driver handle of one executor: submit tasklets, close, running tasklets.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/AllocatedExecutorImpl.java:63-121."""
+
     def __init__(self, master: "ETMaster", executor_id: str, conf: ExecutorConfiguration) -> None:
         self._m = master
         self.id = executor_id
@@ -939,6 +960,9 @@ class AllocatedTable:
 
 
 class TableManager:
+    """Driver registry of tables: create (fresh / checkpoint / input), get, drop bookkeeping.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/TableManager.java:75-157."""
+
     def __init__(self, master: "ETMaster") -> None:
         self._m = master
         self._tables: Dict[str, AllocatedTable] = {}
@@ -986,11 +1010,17 @@ class TableManager:
 # Metrics (driver)
 # ==========================================================================================
 class MetricReceiver:
+    """SPI receiving executor metric reports.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/api/MetricReceiver.java:26-34."""
+
     def on_metric_report(self, report: Dict[str, Any]) -> None:   # default: ignore
         pass
 
 
 class MetricManager:
+    """Starts / stops metric collection on executors and forwards reports to the receivers.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/metric/MetricManager.java:46-56."""
+
     def __init__(self, master: "ETMaster") -> None:
         self._m = master
         self.receivers: List[MetricReceiver] = []
@@ -1013,6 +1043,11 @@ class MetricManager:
 # ETMaster
 # ==========================================================================================
 class ETMaster:
+    """Driver entry point of Elastic Table: add executors, create tables, look executors / tables up; owns the
+    managers, the message demux and the failure listeners.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/driver/impl/ETMasterImpl.java:44-88,
+    driver/impl/MessageHandlerImpl.java:109-141,216-232."""
+
     def __init__(self, transport: Transport, launcher: Optional[ExecutorLauncher] = None,
                  driver_id: str = "driver", chkp_temp_path: str = "/tmp/chkp",
                  chkp_commit_path: str = "/tmp/chkp/commit") -> None:

@@ -35,6 +35,8 @@ def _run_tasklets(execs, cls: str, params: Dict[str, Any], timeout: float = 120.
 
 # ---- simple: put / get / scan / migrate / drop ------------------------------------------------
 class SimplePutTasklet(Tasklet):
+    """simple example: every executor puts its share of 100 values."""
+
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
@@ -44,6 +46,8 @@ class SimplePutTasklet(Tasklet):
 
 
 class SimpleScanTasklet(Tasklet):
+    """simple example: count the locally stored values."""
+
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
@@ -81,6 +85,8 @@ def run_simple(table_input: str = "") -> bool:
 
 # ---- addinteger: PS semantics (many workers update the same keys) -----------------------------
 class AddIntegerTasklet(Tasklet):
+    """addinteger example: num_updates round-robin updates of delta (UpdaterTask)."""
+
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
@@ -92,6 +98,8 @@ class AddIntegerTasklet(Tasklet):
 
 
 class AddIntegerValidateTasklet(Tasklet):
+    """addinteger example: waits until every key holds the expected sum (ValidatorTask.java:74)."""
+
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
@@ -129,6 +137,8 @@ def run_addinteger(num_workers: int = 2, num_servers: int = 2, num_updates: int 
 
 # ---- tableaccess: every op x local/remote x ordered/hashed ------------------------------------
 class TableAccessTasklet(Tasklet):
+    """tableaccess example: every op, local and remote, ordered and hashed tables."""
+
     def run(self):
         p = self.context.params
         t = self.context.table_accessor.get_table(p["table_id"])
@@ -330,6 +340,8 @@ def run_plan() -> bool:
 
 # ---- centcomm (user service) --------------------------------------------------------------------------
 class CentCommTasklet(Tasklet):
+    """centcomm example: ping the driver, wait for pong."""
+
     def run(self):
         from ..common.centcomm import SlaveSideCentComm
         cc = SlaveSideCentComm(self.context.executor)

@@ -27,6 +27,11 @@ LOG = logging.getLogger(__name__)
 
 
 class Executor:
+    """One ET executor: table registry, remote-access handler / sender, migration executor, checkpoint slave,
+    tasklet runtime, task-unit scheduler, metric collector, message demux.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/MessageHandlerImpl.java:55-69,106-138,194-289,
+    Tables.java:79-133."""
+
     def __init__(self, executor_id: str, transport: Transport, conf: Optional[ExecutorConfiguration] = None,
                  driver_id: str = "driver") -> None:
         self.executor_id = executor_id

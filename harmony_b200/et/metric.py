@@ -13,6 +13,10 @@ from ..utils.misc import resolve_hostname
 
 
 class MetricCollector:
+    """Executor metric collector: table -> #blocks, GET-response bytes / counts, custom metrics; periodic or manual
+    flush to the driver.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/metric/MetricCollector.java:66-137."""
+
     def __init__(self, executor) -> None:
         self._ex = executor
         self._custom: List[Any] = []

@@ -32,6 +32,10 @@ def _chunks(keys, values, chunk_size: int):
 
 
 class MigrationExecutor:
+    """Executor halves of block migration: sender (<= 4 blocks in flight, ownership-first for mutable tables,
+    chunked data messages) and receiver (install block, update cache, acks).  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/MigrationExecutor.java:107-132,134-198,202-253,255-295,338-414."""
+
     def __init__(self, executor) -> None:
         self._ex = executor
         self._sem = threading.Semaphore(MAX_CONCURRENT_MIGRATIONS)

@@ -16,6 +16,10 @@ from ..utils.concurrent import CountDownLatch, ReadWriteLock
 
 
 class OwnershipCache:
+    """Replicated block -> owner array with a fair read/write lock per block and incoming-block latches; ops
+    resolve the owner under the read lock, ownership updates take the write lock.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/OwnershipCache.java:123-153,195-244,285-318."""
+
     def __init__(self, table_id: str, num_total_blocks: int, local_executor_id: str, driver_id: str = "driver",
                  sync_ack: Optional[Callable[[int, str, str], None]] = None) -> None:
         self.table_id = table_id

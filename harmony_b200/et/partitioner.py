@@ -25,6 +25,10 @@ _LONG_MAX = 2 ** 63 - 1
 
 
 class BlockPartitioner:
+    """key -> block id: range partitioning for ordered tables, hashing otherwise; key ranges of blocks.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/OrderingBasedBlockPartitioner.java,
+    HashBasedBlockPartitioner.java."""
+
     num_blocks: int
 
     def get_block_id(self, key: Any) -> int:

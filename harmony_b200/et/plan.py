@@ -26,6 +26,8 @@ _op_ids = itertools.count()
 
 
 class OpResult:
+    """Result of one plan op.  Reference: services/et/src/main/java/edu/snu/cay/services/et/plan/api/Op.java:35-71."""
+
     def __init__(self, op: "Op", payload: Any = None) -> None:
         self.op, self.payload = op, payload
 
@@ -35,6 +37,9 @@ class OpResult:
 
 
 class Op:
+    """One node of an ETPlan: type, execute(context) -> future, virtual executor ids.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/plan/api/Op.java:35-71."""
+
     op_type = "?"
 
     def __init__(self) -> None:
@@ -65,6 +70,8 @@ def _chain(src: ResultFuture, op: Op, payload_fn: Callable[[Any], Any] = lambda 
 
 
 class AllocateOp(Op):
+    """ALLOCATE an executor (virtual id -> actual id).  Reference: services/et/.../plan/impl/op/AllocateOp.java."""
+
     op_type = ALLOCATE
 
     def __init__(self, virtual_id: str, executor_conf: Optional[ExecutorConfiguration] = None) -> None:
@@ -79,6 +86,8 @@ class AllocateOp(Op):
 
 
 class DeallocateOp(Op):
+    """DEALLOCATE an executor.  Reference: plan/impl/op/DeallocateOp.java."""
+
     op_type = DEALLOCATE
 
     def __init__(self, executor_id: str) -> None:
@@ -90,6 +99,8 @@ class DeallocateOp(Op):
 
 
 class AssociateOp(Op):
+    """ASSOCIATE an executor with a table.  Reference: plan/impl/op/AssociateOp.java."""
+
     op_type = ASSOCIATE
 
     def __init__(self, executor_id: str, table_id: str) -> None:
@@ -102,6 +113,9 @@ class AssociateOp(Op):
 
 
 class UnassociateOp(Op):
+    """UNASSOCIATE an executor from a table (after its blocks moved away).  Reference:
+    plan/impl/op/UnassociateOp.java."""
+
     op_type = UNASSOCIATE
 
     def __init__(self, executor_id: str, table_id: str) -> None:
@@ -113,6 +127,8 @@ class UnassociateOp(Op):
 
 
 class SubscribeOp(Op):
+    """SUBSCRIBE an executor to a table's ownership updates.  Reference: plan/impl/op/SubscribeOp.java."""
+
     op_type = SUBSCRIBE
 
     def __init__(self, executor_id: str, table_id: str) -> None:
@@ -125,6 +141,8 @@ class SubscribeOp(Op):
 
 
 class UnsubscribeOp(Op):
+    """UNSUBSCRIBE.  Reference: plan/impl/op/UnsubscribeOp.java."""
+
     op_type = UNSUBSCRIBE
 
     def __init__(self, executor_id: str, table_id: str) -> None:
@@ -136,6 +154,8 @@ class UnsubscribeOp(Op):
 
 
 class MoveOp(Op):
+    """MOVE n blocks of a table between executors.  Reference: plan/impl/op/MoveOp.java."""
+
     op_type = MOVE
 
     def __init__(self, src_executor_id: str, dst_executor_id: str, table_id: str, num_blocks: int) -> None:
@@ -149,6 +169,8 @@ class MoveOp(Op):
 
 
 class CreateOp(Op):
+    """CREATE a table.  Reference: plan/impl/op/CreateOp.java."""
+
     op_type = CREATE
 
     def __init__(self, executor_ids: List[str], table_conf: TableConfiguration) -> None:
@@ -161,6 +183,8 @@ class CreateOp(Op):
 
 
 class DropOp(Op):
+    """DROP a table.  Reference: plan/impl/op/DropOp.java."""
+
     op_type = DROP
 
     def __init__(self, table_id: str) -> None:
@@ -172,6 +196,8 @@ class DropOp(Op):
 
 
 class StartOp(Op):
+    """START a tasklet on an executor.  Reference: plan/impl/op/StartOp.java."""
+
     op_type = START
 
     def __init__(self, executor_id: str, tasklet_conf: TaskletConfiguration, metric_flush_period_ms: int = 0,
@@ -188,6 +214,8 @@ class StartOp(Op):
 
 
 class StopOp(Op):
+    """STOP a tasklet.  Reference: plan/impl/op/StopOp.java."""
+
     op_type = STOP
 
     def __init__(self, executor_id: str, tasklet_id: Optional[str] = None) -> None:

@@ -61,6 +61,9 @@ class RemoteAccessOpStat:
 
 
 class SingleKeyDataOpResult(ResultFuture):
+    """Future of a single-key op.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/SingleKeyDataOpResult.java."""
+
     pass
 
 

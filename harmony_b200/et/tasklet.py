@@ -28,6 +28,9 @@ SLOTS = {CPU: 1, NET: 2}
 
 @dataclass(frozen=True)
 class TaskUnitInfo:
+    """(job, unit name, resource type, sequence number) of one schedulable phase.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/TaskUnitInfo.java:26-30."""
+
     job_id: str
     unit_name: str        # e.g. PULL / COMP / PUSH / SYNC
     resource: str         # CPU | NET | VOID
@@ -51,6 +54,9 @@ class Tasklet:
 
 
 class TaskletContext:
+    """What a tasklet sees: its id and parameters, the executor's table accessor, metric collector, task-unit
+    scheduler and a channel to the driver."""
+
     def __init__(self, executor, conf: TaskletConfiguration) -> None:
         self.executor = executor
         self.tasklet_id = conf.tasklet_id
@@ -71,6 +77,10 @@ def load_class(path: str):
 
 
 class TaskletRuntime:
+    """Runs tasklets on daemon threads bounded by the tasklet slots (each under its own CUDA stream on a device
+    executor); start / stop by driver messages, status reports, custom message routing.  Reference:
+    services/et/src/main/java/edu/snu/cay/services/et/evaluator/impl/TaskletRuntime.java:69-130."""
+
     def __init__(self, executor, num_tasklets: int) -> None:
         self._ex = executor
         # daemon threads bounded by a semaphore (a parked tasklet must never block interpreter exit)

@@ -53,6 +53,9 @@ class _Inbox:
 
 
 class Transport:
+    """Control-plane transport SPI (register an endpoint handler, send a dict message).  Replaces REEF
+    NetworkConnectionService (services/et/.../common/impl/NetworkConnectionImpl.java:72-95)."""
+
     def register(self, endpoint_id: str, handler: Handler) -> None:
         raise NotImplementedError
 
@@ -67,6 +70,9 @@ class Transport:
 
 
 class LocalTransport(Transport):
+    """In-process transport: one inbox thread per endpoint (drivers, executors of the tests and of `-executor_mode
+    inproc`); has a drop filter for fault injection."""
+
     def __init__(self) -> None:
         self._inboxes: Dict[str, _Inbox] = {}
         self._lock = threading.Lock()

@@ -146,6 +146,8 @@ class AdagradUpdateFunction(AddUpdateFunction):
 
 
 class AssignUpdateFunction(UpdateFunction):
+    """update = overwrite (value := delta)."""
+
     name = "assign"
     device_fn = DEV_ASSIGN
 

@@ -111,6 +111,9 @@ def _executor_factory(backend: str):
 
 
 class CommandSender:
+    """Client that sends one command line to the job server's TCP port.  Reference:
+    jobserver/src/main/java/edu/snu/cay/jobserver/client/CommandSender.java:49-83."""
+
     def __init__(self, port: int = DEFAULT_PORT, host: str = "127.0.0.1") -> None:
         self.addr = (host, port)
 

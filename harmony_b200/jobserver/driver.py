@@ -252,6 +252,10 @@ class JobDispatcher:
 
 
 class JobServerDriver:
+    """The long-running driver: FSM NOT_INIT -> INIT -> CLOSED, resource pool, SUBMIT / SHUTDOWN / STATUS handling,
+    scheduler hook-up, job dispatch and bookkeeping.  Reference:
+    jobserver/src/main/java/edu/snu/cay/jobserver/driver/JobServerDriver.java:80-109,125-145,178-214,222-266."""
+
     def __init__(self, et_master: ETMaster, conf: Configuration,
                  client_sink: Optional[Callable[[str], None]] = None) -> None:
         self.et_master = et_master

@@ -25,6 +25,8 @@ NUM_VALIDATE_RETRIES, VALIDATE_SLEEP_S = 30, 0.2
 
 
 class ExampleDataParser(DataParser):
+    """Dummy-input parser of the AddInteger / AddVector examples (a record is its line)."""
+
     def parse_line(self, line: str):
         return line
 
@@ -41,6 +43,10 @@ def write_dummy_input(num_records: int, path: str = None) -> str:
 
 
 class AddVectorTrainer(Trainer):
+    """Sleep-based fake compute pushing a constant delta vector; validates the final sums in cleanup (self-checking
+    under migration).  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/examples/addvector/AddVectorTrainer.java:104-181."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, **_: Any) -> None:
         self.acc = model_accessor
         self.delta = float(params.get("delta", 1))

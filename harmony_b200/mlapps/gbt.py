@@ -26,6 +26,8 @@ from ..utils.flags import Configuration
 
 
 class GBTDataParser(DataParser):
+    """`y idx:val ...` -> (idx, val, y).  Reference: dolphin/mlapps/gbt/GBTETDataParser.java."""
+
     index_bound_param = "features"
 
     def record_indices(self, record):
@@ -95,6 +97,10 @@ class GBTree:
 
 
 class GBTTrainer(Trainer):
+    """Per mini-batch: pull the label's forest, residuals, grow one tree by exact greedy splits, push it to a
+    random key of the label.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/mlapps/gbt/GBTTrainer.java:244-760."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, **_: Any) -> None:
         self.acc = model_accessor
         self.num_features = int(params["features"])

@@ -10,6 +10,8 @@ from .gbt import GBTree, GBTTrainer
 
 
 class GBTDeviceTrainer(GBTTrainer):
+    """GBTTrainer whose residuals, split search, routing and evaluation run in ops/csrc/k12_ops.cu."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, context=None, **kw: Any) -> None:
         super().__init__(params, model_accessor, **kw)
         import torch

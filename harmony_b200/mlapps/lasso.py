@@ -23,6 +23,8 @@ CLOSE_TO_ZERO = 1e-9
 
 
 class LassoDataParser(DataParser):
+    """`y idx:val ...` -> (idx, val, y).  Reference: dolphin/mlapps/lasso/LassoETParser.java:49-75."""
+
     index_bound_param = "features"
 
     def record_indices(self, record):
@@ -52,6 +54,10 @@ def sthresh(x: float, lam: float, col_norm: float) -> float:
 
 
 class LassoTrainer(Trainer):
+    """Cyclic coordinate descent with soft-thresholding over the pulled model; pushes step * (new - old) per
+    partition.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/mlapps/lasso/LassoTrainer.java:170-224,292-322."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, **_: Any) -> None:
         self.acc = model_accessor
         self.num_features = int(params["features"])

@@ -10,6 +10,8 @@ from ..dolphin.worker import Trainer
 
 
 class LassoDeviceTrainer(Trainer):
+    """Dolphin Trainer over lasso_cd_kernel: pull + coordinate descent + push in one launch."""
+
     fused_step = True
 
     def __init__(self, params: Dict[str, Any], model_table, **_: Any) -> None:

@@ -29,6 +29,8 @@ LOG = logging.getLogger(__name__)
 
 
 class LDADataParser(DataParser):
+    """One document per line: word ids.  Reference: dolphin/mlapps/lda/LDAETDataParser.java."""
+
     index_bound_param = "num_vocabs"
 
     def record_indices(self, record):

@@ -9,6 +9,9 @@ from ..dolphin.worker import Trainer
 
 
 class LDADeviceTrainer(Trainer):
+    """Dolphin Trainer over LDADeviceModel; initial random assignment pushed as counts (LDATrainer.java:113-194),
+    likelihoods via the lgamma-sum kernel."""
+
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
 
     def __init__(self, params: Dict[str, Any], model_table, local_model_table=None, input_table=None,

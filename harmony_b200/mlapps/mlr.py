@@ -83,6 +83,10 @@ def softmax_clamped(logits: np.ndarray) -> np.ndarray:
 
 
 class MLRTrainer(Trainer):
+    """Host MLR trainer on the feature-major model: sparse logits, clamped softmax, gradient rows, push; loss /
+    accuracy evaluation.  Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/mlapps/mlr/MLRTrainer.java:190-300,374-398,404-470,475-505."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, **_: Any) -> None:
         self.acc = model_accessor
         self.num_classes = int(params["classes"])

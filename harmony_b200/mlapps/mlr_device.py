@@ -19,6 +19,9 @@ LOG = logging.getLogger(__name__)
 
 
 class MLRDeviceTrainer(Trainer):
+    """Dolphin Trainer over the fused MLR kernels: pull mode (rows move), ship mode (-mlr_mode ship, activations
+    move, BSP) or dense input (tcgen05).  Reference arithmetic: MLRTrainer.java:374-398,475-505."""
+
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
     wants_sorted_batches = False
 

@@ -93,6 +93,10 @@ def nmf_gradients(L: np.ndarray, R: np.ndarray, ptr, slot, vals, lam: float):
 
 
 class NMFTrainer(Trainer):
+    """Host NMF trainer: pull the batch's columns of R, gradients for L (local model table) and R, push.
+    Reference:
+    jobserver/src/main/java/edu/snu/cay/dolphin/mlapps/nmf/NMFTrainer.java:144-153,156-210,328-367,375-406."""
+
     def __init__(self, params: Dict[str, Any], model_accessor, local_model_table=None, context=None,
                  input_table=None, **_: Any) -> None:
         self.acc = model_accessor

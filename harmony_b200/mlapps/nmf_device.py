@@ -10,6 +10,8 @@ from .nmf import batch_arrays
 
 
 class NMFDeviceTrainer(Trainer):
+    """Dolphin Trainer over NMFDeviceModel (fused pull / compute / push on one stream)."""
+
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
 
     def __init__(self, params: Dict[str, Any], model_table, local_model_table=None, input_table=None,

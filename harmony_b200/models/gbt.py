@@ -21,6 +21,9 @@ def _i64(mask: int) -> int:
 
 
 class DeviceTreeBuilder:
+    """Level-wise exact greedy tree growth and forest prediction on the GPU (ops/csrc/k12_ops.cu).  Reference:
+    dolphin/mlapps/gbt/GBTTrainer.java:327-531."""
+
     def __init__(self, device, num_features: int, types: Dict[int, int], max_depth: int, leaf_min: int,
                  lam: float, gamma: float) -> None:
         from ..ops import native

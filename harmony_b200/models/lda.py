@@ -12,6 +12,9 @@ from ..et.device_table import DeviceTable
 
 @dataclass
 class LDABatch:
+    """One LDA mini-batch on the device: document pointers, token -> vocabulary slot, batch vocabulary (+ summary
+    row key)."""
+
     doc_ptr: torch.Tensor    # int32 [nd+1]   token offsets into the worker-local token arrays
     tok_slot: torch.Tensor   # int32 [ntok_total_local] slot of each token's word in `vocab` (batch-local)
     vocab: torch.Tensor      # int64 [U+1]    distinct words of the batch + the summary key V (last)
@@ -36,6 +39,10 @@ def build_lda_batch(docs, tok_base: int, V: int) -> LDABatch:
 
 
 class LDADeviceModel:
+    """Device LDA step: pull batch vocabulary rows + summary row, warp-per-document collapsed Gibbs sampling,
+    sparse (row, topic, +-1) pushes with clamp / nnz bookkeeping at the owners.  Reference:
+    dolphin/mlapps/lda/SparseLDASampler.java:141-274, LDATrainer.java:317-357."""
+
     def __init__(self, table: DeviceTable, num_topics: int, num_vocabs: int, n_local_tokens: int,
                  alpha: float, beta: float, seed: int = 0) -> None:
         from ..ops import native

@@ -13,6 +13,10 @@ from ..et.partitioner import PART_ORDERED
 
 
 class DenseMLR:
+    """Dense-input MLR on the tensor cores: logits = X . W and W += X^T D as tcgen05 kind::tf32 GEMMs whose B tiles
+    are TMA-loaded from the owners' slabs (pull fused) and whose epilogue reduce-adds into the owners' rows
+    (push fused); ops/csrc/mlr_dense_tc.cu."""
+
     def __init__(self, table: DeviceTable, num_classes: int, use_2cta: bool = True) -> None:
         # use_2cta: cta_group::2 kernels (256 x 256 tile per CTA pair, ~640 TFLOP/s tf32 measured vs ~340 for
         # the single-CTA 128 x 128 kernel, which is L2-bandwidth bound at 32 FLOP per staged byte)

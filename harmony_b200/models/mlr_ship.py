@@ -73,6 +73,10 @@ def route_batches(table: DeviceTable, worker_batches: Sequence[MLRBatch], rank: 
 
 
 class MLRShipModel:
+    """One BSP step of MLR in ship mode: owner-side partial logits reduce-added into the worker's buffer over peer
+    memory, softmax + error rows stored into every owner's buffer, owner-local row update
+    (ops/csrc/mlr_ship_ops.cu).  Same arithmetic as MLRTrainer.java:374-398,475-505."""
+
     def __init__(self, table: DeviceTable, arena: PeerArena, group: PeerGroup, clock: DeviceClock,
                  num_classes: int, step_size: float, batch_size: int) -> None:
         from ..ops import native

@@ -13,6 +13,9 @@ from ..et.device_table import DeviceTable
 
 @dataclass
 class NMFBatch:
+    """One NMF mini-batch on the device: CSR of the rows, distinct columns, slot of every non-zero in the staging
+    buffer."""
+
     csr_ptr: torch.Tensor    # int32 [n+1]
     col_slot: torch.Tensor   # int32 [nnz]  index into `ucols`
     val: torch.Tensor        # float32 [nnz]
@@ -49,6 +52,10 @@ def synthetic_nmf_batch(n_rows: int, n_cols: int, nnz_per_row: int, row_base: in
 
 
 class NMFDeviceModel:
+    """Device NMF step: pull distinct columns of R into an L2-resident staging buffer, nmf_batch_kernel (SDDMM +
+    both SpMMs + local L update), push with SGD + clamp at the owners.  Reference:
+    dolphin/mlapps/nmf/NMFTrainer.java:156-210,328-367."""
+
     def __init__(self, table: DeviceTable, rank: int, n_local_rows: int, step: float, lam: float = 0.0,
                  max_val: float = 1e6, init_lo: float = 0.0, init_hi: float = 1.0, seed: int = 0) -> None:
         from ..ops import native

@@ -18,6 +18,10 @@ from .peer import PeerArena, PeerGroup
 
 
 class DeviceClock:
+    """Device-side SSP clocks / barriers over peer memory: st.release.sys publishes a worker's clock into every
+    GPU's array, a bounded spin kernel waits for min(clocks) >= mine - slack.  Replaces MiniBatchBarrier ->
+    MiniBatchController round trips (dolphin/core/master/MiniBatchController.java:51-117) on the SPMD path."""
+
     def __init__(self, arena: PeerArena, group: Optional[PeerGroup] = None, slack: int = 0,
                  timeout_cycles: int = 20_000_000_000) -> None:
         from ..ops import native

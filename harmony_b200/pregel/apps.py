@@ -16,6 +16,9 @@ LONG_MAX = 2 ** 63 - 1
 
 
 class PagerankComputation(Computation):
+    """PageRank vertex program (damping 0.85, fixed number of supersteps).  Reference:
+    jobserver/src/main/java/edu/snu/cay/pregel/graphapps/pagerank/PagerankComputation.java:45-69."""
+
     def compute(self, vertex: Vertex, messages: Iterable[float]) -> None:
         if self.get_superstep() == 0:
             vertex.set_value(1.0)
@@ -29,6 +32,9 @@ class PagerankComputation(Computation):
 
 
 class ShortestPathComputation(Computation):
+    """Single-source shortest paths vertex program.  Reference:
+    jobserver/src/main/java/edu/snu/cay/pregel/graphapps/shortestpath/ShortestPathComputation.java:42-66."""
+
     def compute(self, vertex: Vertex, messages: Iterable[int]) -> None:
         source = int(self.params.get("source", 0))
         if self.get_superstep() == 0:

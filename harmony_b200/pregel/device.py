@@ -26,6 +26,10 @@ INT_INF = 2 ** 31 - 1
 
 
 class DevicePregel:
+    """GPU-resident supersteps: vertex values and flip-flopped message tables in device tables, the combiner is the
+    push kernel's update function at the owner (sum / min).  Reference:
+    pregel/graph/impl/MessageManager.java:61-110."""
+
     def __init__(self, arena: PeerArena, group: PeerGroup, num_vertices: int,
                  local_adj: Dict[int, List[Tuple[int, int]]]) -> None:
         """`local_adj`: vertex id -> [(target, weight)] for the vertices this rank owns."""

@@ -17,6 +17,8 @@ from ..common.dataloader import DataParser, register_parser
 
 
 class Edge:
+    """(target vertex, value).  Reference: pregel/graph/api/Edge.java."""
+
     __slots__ = ("target_vertex_id", "value")
 
     def __init__(self, target_vertex_id: int, value: Any = None) -> None:
@@ -24,6 +26,8 @@ class Edge:
 
 
 class Vertex:
+    """Vertex id, value, edges, halted flag.  Reference: pregel/graph/api/Vertex.java."""
+
     def __init__(self, vertex_id: int, edges: List[Edge], value: Any = None) -> None:
         self.id, self.edges, self.value = vertex_id, edges, value
         self._halt = False
@@ -79,16 +83,23 @@ register_parser("graph_none_edge_value", NoneEdgeValueGraphParser)
 
 
 class MessageCombiner:
+    """combine(vertex, old, new) SPI applied at the receiving message table.  Reference:
+    pregel/combiner/MessageCombiner.java."""
+
     def combine(self, vertex_id: int, original: Any, message: Any) -> Any:
         raise NotImplementedError
 
 
 class DoubleSumMessageCombiner(MessageCombiner):
+    """Sum combiner (PageRank).  Reference: pregel/combiner/DoubleSumMessageCombiner.java."""
+
     def combine(self, vertex_id, original, message):
         return original + message
 
 
 class MinimumLongMessageCombiner(MessageCombiner):
+    """Min combiner (shortest path).  Reference: pregel/combiner/MinimumLongMessageCombiner.java."""
+
     def combine(self, vertex_id, original, message):
         return min(original, message)
 

@@ -31,6 +31,9 @@ VERTEX_TABLE_ID, MSG_TABLE_ID = "vertex_table", "msg_table"
 
 
 class PregelMaster:
+    """Superstep control: gathers every worker's (halted, sent-messages) flags, AND-reduces them, starts the next
+    superstep or stops.  Reference: jobserver/src/main/java/edu/snu/cay/pregel/PregelMaster.java:88-172."""
+
     def __init__(self, master: ETMaster, job_id: str, params: Dict[str, Any]) -> None:
         self._m, self.job_id, self.params = master, job_id, params
         self._tasklets: List[Any] = []
@@ -75,6 +78,10 @@ class PregelMaster:
 
 
 class PregelWorkerTask(Tasklet):
+    """Worker loop: per superstep run the computation over the local vertices with the current message table, flush
+    outgoing messages, report to the master.  Reference:
+    jobserver/src/main/java/edu/snu/cay/pregel/PregelWorkerTask.java:100-161."""
+
     def __init__(self, context) -> None:
         super().__init__(context)
         p = context.params
@@ -140,6 +147,8 @@ class PregelWorkerTask(Tasklet):
 # app descriptor, tables, launchers
 # ------------------------------------------------------------------------------------------
 class PregelApp:
+    """App descriptor of a Pregel job (computation, combiner, parser, value types)."""
+
     def __init__(self, app_id: str, computation_class: str, parser: str, combiner_class: Optional[str] = None,
                  parameters=()) -> None:
         self.app_id, self.computation_class, self.parser = app_id, computation_class, parser
@@ -170,6 +179,8 @@ def parse_conf(app: PregelApp, argv: Sequence[str]) -> Configuration:
 
 
 class PregelJobMaster(JobMaster):
+    """JobMaster of a Pregel job inside the job server.  Reference: pregel/jobserver/PregelJobMaster.java."""
+
     def __init__(self, entity: "PregelJobEntity") -> None:
         self.entity = entity
         self.master: Optional[PregelMaster] = None
@@ -185,6 +196,9 @@ class PregelJobMaster(JobMaster):
 
 
 class PregelJobEntity(JobEntity):
+    """A submitted Pregel job: vertex table + two message tables on all executors.  Reference:
+    jobserver/src/main/java/edu/snu/cay/pregel/jobserver/PregelJobEntity.java:76-111."""
+
     def __init__(self, driver: JobServerDriver, conf: Configuration, app: PregelApp, n: int) -> None:
         self.driver, self.conf, self.app, self.n = driver, conf, app, n
         self.job_id = f"{app.app_id}-{n}"
@@ -212,6 +226,9 @@ class PregelJobEntity(JobEntity):
 
 
 class PregelJobEntityBuilder:
+    """Builds a PregelJobEntity from the job configuration.  Reference:
+    pregel/jobserver/PregelJobEntityBuilder.java."""
+
     def __init__(self, driver: JobServerDriver, conf: Configuration) -> None:
         self.driver, self.conf = driver, conf
 
@@ -221,6 +238,9 @@ class PregelJobEntityBuilder:
 
 
 class PregelJobLauncher:
+    """Client side of submit_pagerank.sh / submit_shortest_path.sh.  Reference:
+    pregel/jobserver/PregelJobLauncher.java."""
+
     @staticmethod
     def submit_job(app_path: str, app: PregelApp, argv: Sequence[str], port: Optional[int] = None) -> str:
         conf = parse_conf(app, argv).with_values(

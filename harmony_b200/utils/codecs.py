@@ -16,6 +16,8 @@ import numpy as np
 
 
 class Codec:
+    """encode / decode SPI (checkpoint files, TCP frames).  Reference: REEF Codec users in utils/."""
+
     def encode(self, obj: Any) -> bytes:
         raise NotImplementedError
 
@@ -24,6 +26,8 @@ class Codec:
 
 
 class IntegerCodec(Codec):
+    """4-byte big-endian int.  Reference: utils/src/main/java/edu/snu/cay/utils/IntegerCodec.java."""
+
     def encode(self, obj: int) -> bytes:
         return struct.pack(">i", int(obj))
 
@@ -32,6 +36,8 @@ class IntegerCodec(Codec):
 
 
 class LongCodec(Codec):
+    """8-byte big-endian long.  Reference: utils/src/main/java/edu/snu/cay/utils/LongCodec.java."""
+
     def encode(self, obj: int) -> bytes:
         return struct.pack(">q", int(obj))
 
@@ -40,6 +46,8 @@ class LongCodec(Codec):
 
 
 class NullCodec(Codec):
+    """Encodes nothing.  Reference: utils/src/main/java/edu/snu/cay/utils/NullCodec.java."""
+
     def encode(self, obj: Any) -> bytes:
         return b""
 
@@ -48,6 +56,8 @@ class NullCodec(Codec):
 
 
 class SerializableCodec(Codec):
+    """Generic object codec.  Reference: utils/src/main/java/edu/snu/cay/utils/StreamingSerializableCodec.java."""
+
     def encode(self, obj: Any) -> bytes:
         return pickle.dumps(obj, protocol=5)
 

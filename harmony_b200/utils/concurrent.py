@@ -93,6 +93,8 @@ class ResultFuture(Generic[T]):
 
 
 class CompletedFuture(ResultFuture[T]):
+    """A ResultFuture that is already complete."""
+
     def __init__(self, result: T = None) -> None:
         super().__init__()
         self.on_completed(result)
@@ -157,6 +159,8 @@ def new_fixed_thread_pool(n: int, name: str = "hb-pool") -> CatchableExecutor:
 
 
 class CountDownLatch:
+    """java.util.concurrent.CountDownLatch equivalent."""
+
     def __init__(self, count: int) -> None:
         self._count = count
         self._cond = threading.Condition()

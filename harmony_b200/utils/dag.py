@@ -9,6 +9,9 @@ V = TypeVar("V", bound=Hashable)
 
 
 class DAG(Generic[V]):
+    """Generic DAG (roots, neighbours, in-degree, JSON) used by reconfiguration plans.  Reference:
+    utils/src/main/java/edu/snu/cay/utils/DAG.java:31-101, DAGImpl.java."""
+
     def __init__(self) -> None:
         self._adj: Dict[V, Set[V]] = {}
         self._indeg: Dict[V, int] = {}

@@ -91,6 +91,8 @@ class Configuration(Mapping[str, Any]):
 
 
 class FlagError(ValueError):
+    """A bad, unknown or missing CLI flag."""
+
     pass
 
 

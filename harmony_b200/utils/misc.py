@@ -13,6 +13,8 @@ C = TypeVar("C")
 
 @dataclass(frozen=True)
 class Tuple3(Generic[A, B, C]):
+    """Immutable triple.  Reference: utils/src/main/java/edu/snu/cay/utils/Tuple3.java."""
+
     first: A
     second: B
     third: C

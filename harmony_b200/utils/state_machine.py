@@ -11,10 +11,15 @@ from typing import Dict, Hashable, List, Set, Tuple
 
 
 class IllegalStateError(RuntimeError):
+    """Raised by StateMachine.check_state / set_state on an illegal state or transition."""
+
     pass
 
 
 class StateMachine:
+    """Named states + legal-transition table with check_state / set_state / compare_and_set_state.  Reference:
+    utils/src/main/java/edu/snu/cay/utils/StateMachine.java:27,44,65,96,199-282."""
+
     class Builder:
         def __init__(self) -> None:
             self._states: Dict[Hashable, str] = {}
