@@ -421,6 +421,8 @@ class DolphinMaster:
         if t == "SyncMsg":
             self.state_manager.on_sync_msg(body["executor_id"], body["state"])
         elif t == "MiniBatchSyncMsg":
+            if body.get("progress") is not None:           # piggybacked ProgressMsg of the previous mini-batch
+                self.progress_tracker.on_progress_msg(body["worker_id"], body["progress"])
             self.mini_batch_controller.on_sync(body["worker_id"])
         elif t == "ProgressMsg":
             self.progress_tracker.on_progress_msg(body["executor_id"], body["progress"])

@@ -16,7 +16,7 @@ import logging
 import random
 import threading
 import time
-from typing import Any, Dict, List, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 from ..et.tasklet import CPU, NET, TaskUnitInfo, Tasklet, load_class
 from ..utils import trace
@@ -222,8 +222,12 @@ class WorkerSideMsgSender:
     def send_sync_msg(self, state: str) -> None:
         self._send({"type": "SyncMsg", "executor_id": self.worker_id, "state": state})
 
-    def send_mini_batch_sync_msg(self) -> None:
-        self._send({"type": "MiniBatchSyncMsg", "worker_id": self.worker_id})
+    def send_mini_batch_sync_msg(self, progress: Optional[int] = None) -> None:
+        """`progress` piggybacks the ProgressMsg of the mini-batch that just finished (one message less per batch)."""
+        body = {"type": "MiniBatchSyncMsg", "worker_id": self.worker_id}
+        if progress is not None:
+            body["progress"] = progress
+        self._send(body)
 
     def send_model_eval_ask_msg(self) -> None:
         self._send({"type": "ModelEvalAskMsg", "executor_id": self.worker_id})
@@ -254,8 +258,8 @@ class MiniBatchBarrier:
         self._ev = threading.Semaphore(0)
         self._stop = False
 
-    def await_(self) -> bool:
-        self._sender.send_mini_batch_sync_msg()
+    def await_(self, progress: Optional[int] = None) -> bool:
+        self._sender.send_mini_batch_sync_msg(progress)
         self._ev.acquire()
         return self._stop
 
@@ -372,6 +376,9 @@ class WorkerTasklet(Tasklet):
         from ..common.metric import MemoryMetricTracker
         # host RSS + HBM sampled every -memory_measure_interval ms; max / mean ride on the epoch metrics
         mem = MemoryMetricTracker(max(0.01, int(self.context.params.get("memory_measure_interval", 1000)) / 1000.0))
+        pending_progress: Optional[int] = None
+        flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
+        last_flush = 0.0
         while not stop and not self._abort.is_set():
             epoch_t0 = time.perf_counter()
             mem.start()
@@ -381,7 +388,9 @@ class WorkerTasklet(Tasklet):
                 batch = self.data_provider.get_next_batch_data()
                 if not batch:
                     break
-                if self.mini_batch_barrier.await_():       # SYNC (void unit): SSP clock + stop flag
+                # SYNC (void unit): SSP clock + stop flag; carries the progress of the previous mini-batch
+                done, pending_progress = pending_progress, None
+                if self.mini_batch_barrier.await_(done):
                     stop = True
                     break
                 self.trainer.set_mini_batch_data(batch)
@@ -400,7 +409,7 @@ class WorkerTasklet(Tasklet):
                 seq += 1
                 bt = time.perf_counter() - t0
                 am = self.accessor.get_and_reset_metrics()
-                self.sender.send_progress_msg(total_batches)
+                pending_progress = total_batches
                 total_batches += 1
                 n_batches += 1
                 n_inst += len(batch)
@@ -409,10 +418,14 @@ class WorkerTasklet(Tasklet):
                                                                     - am.get("push_time_sec", 0.0)),
                                   am.get("push_time_sec", 0.0), len(batch) / bt if bt > 0 else 0.0)
                 self.context.metric_collector.add_custom_metric(bm.to_dict())
-                self.context.metric_collector.flush()
+                now = time.perf_counter()
+                if now - last_flush >= flush_every:        # batch metrics ride together (the epoch end flushes too)
+                    self.context.metric_collector.flush()
+                    last_flush = now
             if n_batches == 0 and not stop:
                 # this worker holds no data (all blocks migrated away): just keep syncing
-                if self.mini_batch_barrier.await_():
+                done, pending_progress = pending_progress, None
+                if self.mini_batch_barrier.await_(done):
                     stop = True
                 else:
                     time.sleep(0.01)
@@ -423,6 +436,8 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.add_custom_metric(em.to_dict())
             self.context.metric_collector.flush()
             epoch += 1
+        if pending_progress is not None:                   # aborted between a batch and its next sync
+            self.sender.send_progress_msg(pending_progress)
         if self.use_task_units:
             self.context.task_units.leave(self.job_id)
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
