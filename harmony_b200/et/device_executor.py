@@ -46,13 +46,15 @@ class DeviceContext:
             self.side_stream = torch.cuda.Stream(device=self.device)
         self.torch_device = torch.device("cuda", self.device)
 
-    def tasklet_stream(self):
+    def tasklet_stream(self, priority: int = 0):
         """A fresh non-blocking stream for one tasklet: tasklets of different jobs (or of executors that share a
         GPU) overlap on the device instead of serialising on the legacy default stream -- the GPU half of the
         reference's multi-job co-scheduling (LocalTaskUnitScheduler.java:36-37 gives CPU x1 / NET x2 slots; here the
         hardware scheduler interleaves the streams' kernels)."""
         import torch
-        return torch.cuda.Stream(device=self.device)
+        # CUDA has two levels: 0 (default) and -1 (high); a job submitted with -job_priority high gets its kernels
+        # scheduled ahead of co-located jobs' when both have work queued
+        return torch.cuda.Stream(device=self.device, priority=-1 if priority < 0 else 0)
 
 
 class DeviceBlock(Block):

@@ -125,7 +125,9 @@ class TaskletRuntime:
         if ctx is None:
             return tasklet.run()
         import torch
-        stream = ctx.tasklet_stream()
+        params = getattr(tasklet.context, "params", None) or {}
+        high = str(params.get("job_priority", "normal")).lower() in ("high", "-1")
+        stream = ctx.tasklet_stream(-1 if high else 0)
         with torch.cuda.device(ctx.device), torch.cuda.stream(stream):
             try:
                 return tasklet.run()
