@@ -4,4 +4,5 @@
 # ./run_gbt.sh -num_dolphin_workers 1 -num_servers 1 -input sample_gbt -metadata_path sample_gbt.meta -features 784 -step_size 0.1 -max_num_epochs 5 -num_mini_batches 4 -num_worker_blocks 4
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
+export HB_BIN_DIR="$DIR/bin"
 exec python -c "import sys; from harmony_b200.mlapps.gbt import main_run as main; sys.exit(main(sys.argv[1:]))" "$@"

@@ -4,4 +4,5 @@
 # ./run_pagerank.sh -input inputs/adj_list -num_pregel_workers 2
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
+export HB_BIN_DIR="$DIR/bin"
 exec python -c "import sys; from harmony_b200.pregel.apps import main_run_pagerank as main; sys.exit(main(sys.argv[1:]))" "$@"

@@ -4,4 +4,5 @@
 # ./submit_shortest_path.sh -input inputs/shortest_path -source 1
 DIR="$(cd "$(dirname "${BASH_SOURCE[0]}")/.." && pwd)"
 export PYTHONPATH="$DIR:$PYTHONPATH"
+export HB_BIN_DIR="$DIR/bin"
 exec python -c "import sys; from harmony_b200.pregel.apps import main_submit_shortest_path as main; sys.exit(main(sys.argv[1:]))" "$@"

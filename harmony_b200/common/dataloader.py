@@ -27,6 +27,31 @@ def strip_scheme(path: str) -> str:
     return path
 
 
+PATH_FLAGS = ("input", "test_data_path", "metadata_path", "model_path", "local_model_path", "input_chkp_path",
+              "host_to_bandwidth_file_path", "host_to_core_file_path")
+
+
+def resolve_data_paths(conf):
+    """Relative data paths are resolved against the current directory first and then against the launch scripts'
+    directory (`HB_BIN_DIR`, exported by bin/*.sh): the EXAMPLE USAGE lines name `sample_mlr`, `inputs/adj_list`
+    ... the way the reference's scripts do when run from jobserver/bin.  The job server may run in another working
+    directory than the client, so the client sends absolute paths."""
+    bin_dir = os.environ.get("HB_BIN_DIR")
+    changed = {}
+    for k in PATH_FLAGS:
+        v = conf.get(k)
+        if not v or not isinstance(v, str):
+            continue
+        p = strip_scheme(v)
+        if os.path.isabs(p):
+            continue
+        if os.path.exists(p):
+            changed[k] = os.path.abspath(p)
+        elif bin_dir and os.path.exists(os.path.join(bin_dir, p)):
+            changed[k] = os.path.abspath(os.path.join(bin_dir, p))
+    return conf.with_values(**changed) if changed else conf
+
+
 @dataclass
 class SplitInfo:
     """Serialisable byte-range split of an input file.  Reference:

@@ -29,7 +29,8 @@ LOG = logging.getLogger(__name__)
 def parse_job_conf(app: ETDolphinConfiguration, argv: Sequence[str]) -> Configuration:
     reg = P.dolphin_registry(app.parameters, P.EXAMPLES if app.app_id.startswith("Add") else [])
     conf, _ = reg.parse(list(argv), allow_unknown=False)
-    return conf
+    from ..common.dataloader import resolve_data_paths
+    return resolve_data_paths(conf)
 
 
 class DolphinJobLauncher:

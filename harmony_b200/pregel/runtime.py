@@ -175,7 +175,8 @@ def parse_conf(app: PregelApp, argv: Sequence[str]) -> Configuration:
     reg = P.registry(P.COMMON, P.JOBSERVER, P.PREGEL, [P.Param("num_worker_blocks", int, 64, "", "worker")],
                      app.parameters)
     conf, _ = reg.parse(list(argv), allow_unknown=True)
-    return conf
+    from ..common.dataloader import resolve_data_paths
+    return resolve_data_paths(conf)
 
 
 class PregelJobMaster(JobMaster):
