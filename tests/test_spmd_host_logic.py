@@ -93,3 +93,32 @@ def test_peer_group_bootstrap_over_gloo_two_processes(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert sorted(o.strip().splitlines()[-1] for o in outs) == ["ok 0", "ok 1"]
+
+
+def test_device_batch_builders_index_the_staging_buffers_consistently():
+    """Host preprocessing of the NMF / LDA / MLR device steps: slots index the pulled staging rows, the last
+    vocabulary entry is the LDA summary key, the MLR by-feature grouping is a permutation of the CSR non-zeros."""
+    from harmony_b200.models.lda import build_lda_batch
+    from harmony_b200.models.nmf import build_nmf_batch
+    rng = np.random.default_rng(3)
+    # NMF: ucols[col_slot] reproduces the original columns; ucols sorted & distinct
+    ptr = np.array([0, 3, 3, 7]); cols = rng.integers(0, 50, 7); vals = rng.random(7).astype(np.float32)
+    b = build_nmf_batch(ptr, cols, vals, np.array([5, 6, 7]))
+    np.testing.assert_array_equal(b.ucols.numpy()[b.col_slot.numpy()], cols)
+    assert np.all(np.diff(b.ucols.numpy()) > 0) and b.csr_ptr.dtype.is_floating_point is False
+    # LDA: vocab = distinct words + [V]; tok_slot maps every token to its word; token window addresses z
+    docs = [rng.integers(0, 30, n).astype(np.int32) for n in (4, 0, 9)]
+    lb = build_lda_batch(docs, tok_base=100, V=30)
+    words = np.concatenate(docs)
+    v = lb.vocab.numpy()
+    assert v[-1] == 30 and np.all(np.diff(v[:-1]) > 0)
+    np.testing.assert_array_equal(v[lb.tok_slot.numpy()], words)
+    assert (lb.tok_lo, lb.tok_hi) == (100, 113) and lb.doc_ptr.tolist() == [0, 4, 4, 13]
+    # MLR: (samp, uniq_feat[group], xval) is a permutation of (row, col, val)
+    mb = synthetic_batch(17, 200, 5, 6, seed=1)
+    rows = np.repeat(np.arange(17), np.diff(mb.csr_ptr.numpy()))
+    fp = mb.feat_ptr.numpy()
+    feat_of = np.repeat(mb.uniq_feat.numpy(), np.diff(fp))
+    a = sorted(zip(rows.tolist(), mb.csr_col.numpy().tolist(), mb.csr_val.numpy().tolist()))
+    c = sorted(zip(mb.samp.numpy().tolist(), feat_of.tolist(), mb.xval.numpy().tolist()))
+    assert a == c
