@@ -181,3 +181,30 @@ def mlr_reference_step(W: torch.Tensor, batch: MLRBatch, num_classes: int, step:
     if lam != 0.0:
         Wn = Wn - step * lam * B * W
     return Wn, loss, acc
+
+
+def load_batches(path: str, batch_size: int, rank: int = 0, world: int = 1, num_classes: int = 0,
+                 num_features: int = 0, drop_last: bool = False):
+    """SPMD data loading for library users: rank `rank` of `world` reads its byte-range split of a `label idx:val ...`
+    file (exact Hadoop-style line ownership, native multi-threaded parser when the extension is built) and returns
+    its mini-batches as `MLRBatch`es (CSR + by-feature grouping) ready for `.pin()` / `.to("cuda")`.
+    Labels / feature ids are validated against `num_classes` / `num_features` when given."""
+    from ..common.dataloader import get_splits, make_parser, read_split_bytes
+    params = {}
+    if num_classes:
+        params["classes"] = num_classes
+    if num_features:
+        params["features"] = num_features
+    parser = make_parser({"name": "mlr", "params": params})
+    records = parser.parse_bytes(read_split_bytes(get_splits(path, world)[rank]))
+    out = []
+    for lo in range(0, len(records), batch_size):
+        chunk = records[lo:lo + batch_size]
+        if drop_last and len(chunk) < batch_size:
+            break
+        ptr = np.zeros(len(chunk) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(r[0]) for r in chunk])
+        col = np.concatenate([r[0] for r in chunk]) if chunk else np.zeros(0, dtype=np.int32)
+        val = np.concatenate([r[1] for r in chunk]) if chunk else np.zeros(0, dtype=np.float32)
+        out.append(build_batch(ptr, col, val, np.asarray([r[2] for r in chunk], dtype=np.int32)))
+    return out

@@ -122,3 +122,18 @@ def test_device_batch_builders_index_the_staging_buffers_consistently():
     a = sorted(zip(rows.tolist(), mb.csr_col.numpy().tolist(), mb.csr_val.numpy().tolist()))
     c = sorted(zip(mb.samp.numpy().tolist(), feat_of.tolist(), mb.xval.numpy().tolist()))
     assert a == c
+
+
+def test_load_batches_splits_a_file_exactly_over_ranks(tmp_path):
+    from harmony_b200.common.samples import write_mlr_sample
+    from harmony_b200.models.mlr import load_batches
+    path = write_mlr_sample(str(tmp_path / "d"), n=333, features=64, classes=4, nnz=6, seed=5)
+    one = load_batches(path, 50)
+    assert [b.batch_size for b in one] == [50] * 6 + [33]
+    per_rank = [load_batches(path, 50, r, 3, num_classes=4, num_features=64) for r in range(3)]
+    assert sum(b.batch_size for bs in per_rank for b in bs) == 333            # every line owned by exactly one rank
+    all_vals = np.sort(np.concatenate([b.csr_val.numpy() for bs in per_rank for b in bs]))
+    np.testing.assert_array_equal(all_vals, np.sort(np.concatenate([b.csr_val.numpy() for b in one])))
+    assert all(b.batch_size == 50 for b in load_batches(path, 50, drop_last=True))
+    with pytest.raises(ValueError):
+        load_batches(path, 50, num_features=32)                                 # feature ids reach 63
