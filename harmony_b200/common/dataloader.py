@@ -279,17 +279,30 @@ class LocalKeyGenerator:
         if not hasattr(part, "key_range"):
             raise KeyGenerationError("key generation needs an ordered table")
         keys: List[int] = []
-        # spread evenly over local blocks so every block (== mini-batch) gets data
-        per = -(-n // len(blocks))
-        for b in blocks:
+        # water-fill: after this call every local block holds (as nearly as possible) the same number of records, no
+        # matter how many small splits the records arrive in -- one block is one mini-batch, so uneven blocks mean
+        # uneven (or empty) mini-batches and workers that idle while others train
+        done = {b: self._next.get(b, part.key_range(b)[0]) - part.key_range(b)[0] for b in blocks}
+        level = -(-(sum(done.values()) + n) // len(blocks))
+        for b in sorted(blocks, key=lambda x: (done[x], x)):
             lo, hi = part.key_range(b)
-            cur = self._next.get(b, lo)
-            take = min(per, n - len(keys), hi - cur + 1)
+            cur = lo + done[b]
+            take = min(max(level - done[b], 0), n - len(keys), hi - cur + 1)
             if take > 0:
                 keys.extend(range(cur, cur + take))
                 self._next[b] = cur + take
             if len(keys) >= n:
                 break
+        if len(keys) < n:                   # some block's key range is full: overflow into the others
+            for b in blocks:
+                lo, hi = part.key_range(b)
+                cur = self._next.get(b, lo)
+                take = min(n - len(keys), hi - cur + 1)
+                if take > 0:
+                    keys.extend(range(cur, cur + take))
+                    self._next[b] = cur + take
+                if len(keys) >= n:
+                    break
         if len(keys) < n:
             raise KeyGenerationError(f"local key space exhausted: need {n}, got {len(keys)}")
         return keys

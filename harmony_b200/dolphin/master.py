@@ -38,7 +38,9 @@ class MasterSideMsgSender:
     def _send(self, worker_id: str, body: Dict[str, Any]) -> None:
         rt = self._runner.get_worker_tasklet(worker_id)
         if rt is None:
-            LOG.warning("no worker tasklet on %s for %s", worker_id, body["type"])
+            # a worker started by a plan op talks to the master before the optimizer has handed its tasklet over:
+            # keep the message until the tasklet is registered
+            self._runner.defer(worker_id, body)
             return
         rt.send(body)
 
@@ -179,13 +181,30 @@ class MiniBatchController:
         self._closed = False
         self._lock = threading.Lock()
 
+    def on_idle_sync(self, worker_id: str) -> None:
+        """A worker that currently holds no input data (all its blocks migrated away) asks whether to stop: it
+        neither consumes the global budget nor holds the SSP clock back while it idles."""
+        with self._lock:
+            self._progress.pop(worker_id, None)
+            self._blocked.discard(worker_id)
+            if self._progress:
+                new_min = min(self._progress.values())
+                if new_min > self._min:
+                    self._min = new_min
+                    for w in self._blocked:
+                        self._sender.send_mini_batch_control_msg(w, False)
+                    self._blocked.clear()
+            self._sender.send_mini_batch_control_msg(worker_id, self._closed)
+
     def on_sync(self, worker_id: str) -> None:
         with self._lock:
             if self._closed:
                 self._sender.send_mini_batch_control_msg(worker_id, True)
                 return
             self._count += 1
-            prog = self._progress.get(worker_id, 0) + 1
+            # a worker that joins mid-run (added by a plan, or back from idling) starts level with the slowest
+            # worker instead of at 0 (which would stall everybody else until it has caught up alone)
+            prog = self._progress.get(worker_id, max(self._min - 1, 0)) + 1
             self._progress[worker_id] = prog
             new_min = min(self._progress.values())
             if new_min > self._min:
@@ -204,10 +223,23 @@ class MiniBatchController:
             else:
                 self._sender.send_mini_batch_control_msg(worker_id, False)
 
+    def on_return(self, worker_id: str) -> None:
+        """A stopped worker hands back a mini-batch it was granted but did not run."""
+        with self._lock:
+            if not self._closed and self._count > 0:
+                self._count -= 1
+
     def on_worker_deleted(self, worker_id: str) -> None:
         with self._lock:
             self._progress.pop(worker_id, None)
             self._blocked.discard(worker_id)
+            if self._progress:               # the clock no longer waits for the deleted worker
+                new_min = min(self._progress.values())
+                if new_min > self._min:
+                    self._min = new_min
+                    for w in self._blocked:
+                        self._sender.send_mini_batch_control_msg(w, False)
+                    self._blocked.clear()
 
     @property
     def num_mini_batches_done(self) -> int:
@@ -287,12 +319,32 @@ class ETTaskRunner:
         self.job_id = job_id
         self.worker_tasklets: Dict[str, RunningTasklet] = {}
         self.server_tasklets: Dict[str, RunningTasklet] = {}
+        self._deferred: Dict[str, List[Dict[str, Any]]] = {}     # master -> worker messages awaiting registration
+        self._ever_started: Dict[str, RunningTasklet] = {}
         self._lock = threading.Lock()
         self.msg_handler: Optional[Callable[[Any], None]] = None
 
     def get_worker_tasklet(self, worker_id: str) -> Optional[RunningTasklet]:
         with self._lock:
             return self.worker_tasklets.get(worker_id)
+
+    def defer(self, worker_id: str, body: Dict[str, Any]) -> None:
+        with self._lock:
+            rt = self.worker_tasklets.get(worker_id)
+            if rt is None:
+                self._deferred.setdefault(worker_id, []).append(body)
+                return
+        rt.send(body)
+
+    def register_worker(self, rt: RunningTasklet) -> None:
+        """A worker tasklet started outside `submit_worker` (plan START op): route master messages to it, including
+        the ones that were addressed to it before it was known."""
+        with self._lock:
+            self.worker_tasklets[rt.executor_id] = rt
+            self._ever_started.setdefault(rt.tasklet_id + "@" + rt.executor_id + str(id(rt)), rt)
+            pending = self._deferred.pop(rt.executor_id, [])
+        for body in pending:
+            rt.send(body)
 
     def submit_worker(self, ex: AllocatedExecutor, params: Dict[str, Any], cls: str = WORKER_TASKLET,
                       suffix: str = "worker") -> RunningTasklet:
@@ -311,10 +363,13 @@ class ETTaskRunner:
 
     def update_executor_entry(self, added_workers: Dict[str, RunningTasklet], deleted_workers: Set[str],
                               added_servers: Dict[str, RunningTasklet], deleted_servers: Set[str]) -> None:
+        for rt in added_workers.values():
+            self.register_worker(rt)
         with self._lock:
-            self.worker_tasklets.update(added_workers)
             for w in deleted_workers:
-                self.worker_tasklets.pop(w, None)
+                if w not in added_workers:
+                    self.worker_tasklets.pop(w, None)
+                self._deferred.pop(w, None)
             self.server_tasklets.update(added_servers)
             for s in deleted_servers:
                 self.server_tasklets.pop(s, None)
@@ -322,13 +377,27 @@ class ETTaskRunner:
     def wait_and_get_results(self, timeout: Optional[float] = None, on_failure=None):
         """Waits for every worker; when one FAILS the others are aborted (they would otherwise wait
         for it at a barrier forever) and the job fails fast."""
-        with self._lock:
-            workers = list(self.worker_tasklets.values())
         failed = threading.Event()
-        for w in workers:
-            w._result.add_listener(lambda r: failed.set() if (r is not None and not r.is_success) else None)
+        watched: Dict[str, RunningTasklet] = {}
+
+        def snapshot() -> List[RunningTasklet]:
+            """Every worker tasklet the job has had so far: the initial ones, the ones plans started later, and the
+            ones plans stopped (they end `Done` with a partial result)."""
+            with self._lock:
+                for rt in self.worker_tasklets.values():
+                    self._ever_started.setdefault(rt.tasklet_id + "@" + rt.executor_id + str(id(rt)), rt)
+                current = list(self._ever_started.items())
+            for key, rt in current:
+                if key not in watched:
+                    watched[key] = rt
+                    rt._result.add_listener(lambda r: failed.set() if (r is not None and not r.is_success) else None)
+            return [rt for _, rt in current]
         deadline = None if timeout is None else time.time() + timeout
-        while not all(w.is_done() for w in workers):
+        workers = snapshot()
+        while True:
+            workers = snapshot()
+            if all(w.is_done() for w in workers):
+                break
             if failed.wait(0.05):
                 if on_failure is not None:
                     on_failure()
@@ -423,7 +492,12 @@ class DolphinMaster:
         elif t == "MiniBatchSyncMsg":
             if body.get("progress") is not None:           # piggybacked ProgressMsg of the previous mini-batch
                 self.progress_tracker.on_progress_msg(body["worker_id"], body["progress"])
-            self.mini_batch_controller.on_sync(body["worker_id"])
+            if body.get("idle"):
+                self.mini_batch_controller.on_idle_sync(body["worker_id"])
+            else:
+                self.mini_batch_controller.on_sync(body["worker_id"])
+        elif t == "MiniBatchReturnMsg":
+            self.mini_batch_controller.on_return(body["worker_id"])
         elif t == "ProgressMsg":
             self.progress_tracker.on_progress_msg(body["executor_id"], body["progress"])
         elif t == "ModelEvalAskMsg":

@@ -25,7 +25,7 @@ from ..et.config import TaskletConfiguration
 from ..et.driver import AllocatedExecutor, ETMaster
 from ..et.plan import LoggingPlanExecutor, PlanExecutor
 from .master import SERVER_TASKLET, WORKER_TASKLET, DolphinMaster
-from .plan import (HOMOGENEOUS, NAMESPACE_SERVER, NAMESPACE_WORKER, Plan, PlanCompiler, TransferStep, empty_plan)
+from .plan import (HETEROGENEOUS, HOMOGENEOUS, NAMESPACE_SERVER, NAMESPACE_WORKER, Plan, PlanCompiler, TransferStep, empty_plan)
 
 LOG = logging.getLogger(__name__)
 NEW_WORKER_ID_PREFIX, NEW_SERVER_ID_PREFIX = "NEW_WORKER-", "NEW_SERVER-"
@@ -127,7 +127,9 @@ class HomogeneousOptimizer(Optimizer):
         self.host_bw = host_to_bandwidth or {}
 
     def _bw(self, p: EvaluatorParameters) -> float:
-        return self.host_bw.get(p.hostname, self.default_bw) / 8.0    # bit/s -> byte/s
+        # entries of -host_to_bandwidth_file_path may name a host or one executor id (the executors of one box share
+        # the hostname; an executor whose GPU is shared or throttled is rated individually)
+        return self.host_bw.get(p.id, self.host_bw.get(p.hostname, self.default_bw)) / 8.0    # bit/s -> byte/s
 
     def _sorted(self, params: List[EvaluatorParameters], available: int, unit_cost, prefix: str) -> List[_Summary]:
         nodes = [_Summary(p.id, p.num_blocks, 1.0 / max(unit_cost(p), 1e-12), self._bw(p)) for p in params]
@@ -215,6 +217,133 @@ class HomogeneousOptimizer(Optimizer):
             for n in nodes[n_active:n_opt]:
                 plan.evaluators_to_add[ns].append(n.id)
         plan.transfer_steps[ns].extend(generate_transfer_steps(nodes[:max(n_opt, n_active)]))
+
+
+class HeterogeneousOptimizer(HomogeneousOptimizer):
+    """Chooses WHICH executors work and which serve, not only how many: executors differ in compute speed (measured
+    batch compute time, or `-host_to_core_file_path` for executors that have not worked yet) and in bandwidth
+    (`-host_to_bandwidth_file_path`).  The epoch-time model is the homogeneous one evaluated per role assignment,
+
+        T(W, S) = B / sum_{i in W} 1 / (c_i + pull * max(1 / b_i, |W| / sum_{j in S} b_j)),
+
+    searched exhaustively up to 14 executors and by pairwise role swaps beyond; data blocks go to the workers in
+    proportion to their throughput, model blocks to the servers in proportion to their bandwidth; an executor that
+    changes role is deleted in one namespace and added in the other under the SAME id, which the plan compiler turns
+    into a switch (no re-allocation).  The reference keeps this optimizer out of its build because it needs a Gurobi
+    licence (optimizer/impl/hetero/{HeterogeneousOptimizer,ILPSolver,ILPPlanGenerator}.java, pom.xml:196-200); the
+    search space of one box (<= 16 executors) does not need an ILP solver."""
+
+    EXHAUSTIVE_LIMIT = 14
+
+    def __init__(self, num_total_mini_batches: int, default_bandwidth: float = NVLINK_BPS,
+                 opt_benefit_threshold: float = 0.0, host_to_bandwidth: Optional[Dict[str, float]] = None,
+                 host_to_cores: Optional[Dict[str, float]] = None) -> None:
+        super().__init__(num_total_mini_batches, default_bandwidth, opt_benefit_threshold, host_to_bandwidth)
+        self.host_cores = host_to_cores or {}
+
+    def _comp_costs(self, sp: List[EvaluatorParameters], wp: List[EvaluatorParameters]) -> Dict[str, float]:
+        """Seconds of compute per mini-batch for every executor; servers are rated by cores relative to the workers."""
+        measured = {p.id: max(p.metrics.get("batch_comp_time_sec", 0.0), 1e-9) for p in wp}
+        mean_cost = sum(measured.values()) / max(len(measured), 1) if measured else 1.0
+        worker_cores = [self.host_cores.get(p.hostname, 1.0) for p in wp] or [1.0]
+        mean_cores = sum(worker_cores) / len(worker_cores)
+        out = dict(measured)
+        for p in sp:
+            cores = self.host_cores.get(p.id, self.host_cores.get(p.hostname, mean_cores))
+            out[p.id] = mean_cost * mean_cores / max(cores, 1e-9)
+        return out
+
+    @staticmethod
+    def _epoch_time(B: int, workers: Sequence[str], servers: Sequence[str], cost: Dict[str, float],
+                    bw: Dict[str, float], pull: float) -> float:
+        sbw = sum(bw[s] for s in servers)
+        if not workers or sbw <= 0:
+            return float("inf")
+        inv = sum(1.0 / (cost[w] + pull * max(1.0 / bw[w], len(workers) / sbw)) for w in workers)
+        return B / inv if inv > 0 else float("inf")
+
+    def optimize(self, eval_params, available_evaluators, model_params) -> Plan:
+        sp, wp = eval_params[NAMESPACE_SERVER], eval_params[NAMESPACE_WORKER]
+        every = {p.id: p for p in list(sp) + list(wp)}
+        ids = sorted(every)
+        n = len(ids)
+        if n < 2 or not wp or not sp:
+            return empty_plan(HETEROGENEOUS)
+        pull = float(model_params.get(AVG_PULL_SIZE_PER_MINI_BATCH, 0.0))
+        cost = self._comp_costs(sp, wp)
+        bw = {i: self._bw(every[i]) for i in ids}
+        data_blocks = sum(p.num_blocks for p in wp)
+        model_blocks = sum(p.num_blocks for p in sp)
+
+        def feasible(k: int) -> bool:          # k workers, n - k servers
+            return 1 <= k <= n - 1 and k <= max(data_blocks, 1) and (n - k) <= max(model_blocks, 1)
+
+        def t_of(wset) -> float:
+            return self._epoch_time(self.B, [i for i in ids if i in wset], [i for i in ids if i not in wset],
+                                    cost, bw, pull)
+        cur_w = frozenset(p.id for p in wp)
+        cur_t = t_of(cur_w)
+        best_w, best_t = cur_w, cur_t
+        if n <= self.EXHAUSTIVE_LIMIT:
+            for mask in range(1, (1 << n) - 1):
+                if not feasible(bin(mask).count("1")):
+                    continue
+                wset = frozenset(ids[i] for i in range(n) if mask >> i & 1)
+                t = t_of(wset)
+                if t < best_t - 1e-12:
+                    best_w, best_t = wset, t
+        else:
+            improved = True
+            while improved:                     # steepest descent over single moves and pairwise swaps
+                improved = False
+                cands = [best_w ^ {i} for i in ids] + [best_w ^ {i, j} for i in best_w for j in ids if j not in best_w]
+                for c in cands:
+                    if feasible(len(c)):
+                        t = t_of(c)
+                        if t < best_t - 1e-12:
+                            best_w, best_t, improved = frozenset(c), t, True
+        if best_w == cur_w or (cur_t != float("inf") and (cur_t - best_t) / cur_t < max(self.threshold, 1e-9)):
+            return self._rebalance_only(sp, wp, cost, bw, pull)
+        plan = Plan(optimizer_type=HETEROGENEOUS)
+        new_s = [i for i in ids if i not in best_w]
+        self._assign_roles(plan, NAMESPACE_SERVER, sp, new_s, {i: bw[i] for i in new_s})
+        sbw = sum(bw[i] for i in new_s)
+        wts = {i: 1.0 / (cost[i] + pull * max(1.0 / bw[i], len(best_w) / sbw)) for i in best_w}
+        self._assign_roles(plan, NAMESPACE_WORKER, wp, sorted(best_w), wts)
+        return plan.validate()
+
+    def _rebalance_only(self, sp, wp, cost, bw, pull) -> Plan:
+        """Roles stay; still move blocks when the current distribution is far from proportional."""
+        plan = Plan(optimizer_type=HETEROGENEOUS)
+        s_ids = [p.id for p in sp]
+        sbw = sum(bw[i] for i in s_ids)
+        self._assign_roles(plan, NAMESPACE_SERVER, sp, s_ids, {i: bw[i] for i in s_ids})
+        self._assign_roles(plan, NAMESPACE_WORKER, wp, [p.id for p in wp],
+                           {p.id: 1.0 / (cost[p.id] + pull * max(1.0 / bw[p.id], len(wp) / sbw)) for p in wp})
+        moved = sum(t.num_blocks for ns in (NAMESPACE_SERVER, NAMESPACE_WORKER) for t in plan.transfer_steps[ns])
+        total = sum(p.num_blocks for p in list(sp) + list(wp))
+        return plan if total and moved / total > max(self.threshold, 0.1) else empty_plan(HETEROGENEOUS)
+
+    @staticmethod
+    def _assign_roles(plan: Plan, ns: str, current: List[EvaluatorParameters], target_ids: List[str],
+                      weights: Dict[str, float]) -> None:
+        cur = {p.id: p.num_blocks for p in current}
+        total = sum(cur.values())
+        wsum = sum(weights.values()) or 1.0
+        nodes: Dict[str, _Summary] = {}
+        for i in target_ids:
+            nodes[i] = _Summary(i, cur.get(i, 0), 0.0, 0.0, int(total * weights[i] / wsum))
+        order = sorted(target_ids, key=lambda i: -weights[i])
+        for k in range(total - sum(nd.num_optimal_blocks for nd in nodes.values())):
+            nodes[order[k % len(order)]].num_optimal_blocks += 1
+        for i in target_ids:
+            if i not in cur:
+                plan.evaluators_to_add[ns].append(i)
+        for i in cur:
+            if i not in nodes:
+                plan.evaluators_to_delete[ns].append(i)
+                nodes[i] = _Summary(i, cur[i], 0.0, 0.0, 0)
+        plan.transfer_steps[ns].extend(generate_transfer_steps(list(nodes.values())))
 
 
 def generate_transfer_steps(nodes: Sequence[_Summary]) -> List[TransferStep]:
@@ -356,6 +485,7 @@ class MoveModelBlocksOptimizer(_OneShot):
 
 _OPTIMIZERS: Dict[str, Callable[..., Optimizer]] = {
     "EmptyPlanOptimizer": EmptyPlanOptimizer, "HomogeneousOptimizer": HomogeneousOptimizer,
+    "HeterogeneousOptimizer": HeterogeneousOptimizer,
     "AddOneServerOptimizer": AddOneServerOptimizer, "AddOneWorkerOptimizer": AddOneWorkerOptimizer,
     "DeleteOneServerOptimizer": DeleteOneServerOptimizer, "DeleteOneWorkerOptimizer": DeleteOneWorkerOptimizer,
     "ExchangeOneOptimizer": ExchangeOneOptimizer, "MoveModelBlocksOptimizer": MoveModelBlocksOptimizer,
@@ -363,14 +493,17 @@ _OPTIMIZERS: Dict[str, Callable[..., Optimizer]] = {
 
 
 def make_optimizer(name: str, **kw: Any) -> Optimizer:
+    """`-optimizer <class name>` (the reference's fully qualified Java names are accepted: the last component
+    selects the implementation); constructor arguments are matched by name."""
+    import inspect
     short = name.split(".")[-1].split("$")[-1]
     cls = _OPTIMIZERS.get(short)
     if cls is None:
         raise ValueError(f"unknown optimizer {name}")
-    try:
+    params = inspect.signature(cls.__init__).parameters
+    if any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
         return cls(**kw)
-    except TypeError:
-        return cls()
+    return cls(**{k: v for k, v in kw.items() if k in params})
 
 
 class ETOptimizationOrchestrator:
@@ -389,7 +522,9 @@ class ETOptimizationOrchestrator:
                                         default_bandwidth=float(conf.get("default_bandwidth", NVLINK_BPS)),
                                         opt_benefit_threshold=float(conf.get("opt_benefit_threshold", 0.0)),
                                         host_to_bandwidth=parse_host_to_value_file(
-                                            conf.get("host_to_bandwidth_file_path", "")))
+                                            conf.get("host_to_bandwidth_file_path", "")),
+                                        host_to_cores=parse_host_to_value_file(
+                                            conf.get("host_to_core_file_path", "")))
         ex_name = conf.get("et_plan_executor", "PlanExecutorImpl")
         self.plan_executor = LoggingPlanExecutor(master) if ex_name.endswith("LoggingPlanExecutor") \
             else PlanExecutor(master)
@@ -471,18 +606,21 @@ class ETOptimizationOrchestrator:
                     rt = res.payload
                     if "-worker-" in rt.tasklet_id:
                         new_worker_tasklets[rt.executor_id] = rt
+                        self._dm.task_runner.register_worker(rt)      # it may sync with the master right away
                     else:
                         new_server_tasklets[rt.executor_id] = rt
             self.plan_executor.register_listener(listener_id, on_op)
             vmap = self.plan_executor.execute(et_plan).get(timeout=600) or {}
             self.plan_executor.unregister_listener(listener_id)
-            actual = lambda e: vmap.get(e, e)  # noqa: E731
+            # ground truth = where tasklets were actually started: a virtual id of the plan is either mapped to a
+            # freshly allocated executor (vmap) or was translated into a SWITCH of an existing one
+            del vmap
             switched_s2w = set(new_worker_tasklets) & self.servers
             switched_w2s = set(new_server_tasklets) & self.workers
-            added_w = {actual(e) for e in plan.get_evaluators_to_add(NAMESPACE_WORKER)} | switched_s2w
-            deleted_w = set(plan.get_evaluators_to_delete(NAMESPACE_WORKER)) | switched_w2s
-            added_s = {actual(e) for e in plan.get_evaluators_to_add(NAMESPACE_SERVER)} | switched_w2s
-            deleted_s = set(plan.get_evaluators_to_delete(NAMESPACE_SERVER)) | switched_s2w
+            added_w = set(new_worker_tasklets)
+            deleted_w = (set(plan.get_evaluators_to_delete(NAMESPACE_WORKER)) & self.workers) | switched_w2s
+            added_s = set(new_server_tasklets)
+            deleted_s = (set(plan.get_evaluators_to_delete(NAMESPACE_SERVER)) & self.servers) | switched_s2w
             self.workers = (self.workers | added_w) - deleted_w
             self.servers = (self.servers | added_s) - deleted_s
             self._dm.task_runner.update_executor_entry(new_worker_tasklets, deleted_w, new_server_tasklets, deleted_s)

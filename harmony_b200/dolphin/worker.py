@@ -222,12 +222,18 @@ class WorkerSideMsgSender:
     def send_sync_msg(self, state: str) -> None:
         self._send({"type": "SyncMsg", "executor_id": self.worker_id, "state": state})
 
-    def send_mini_batch_sync_msg(self, progress: Optional[int] = None) -> None:
-        """`progress` piggybacks the ProgressMsg of the mini-batch that just finished (one message less per batch)."""
+    def send_mini_batch_sync_msg(self, progress: Optional[int] = None, idle: bool = False) -> None:
+        """`progress` piggybacks the ProgressMsg of the mini-batch that just finished (one message less per batch);
+        `idle` = this worker has no data right now: ask for the stop flag without consuming the budget."""
         body = {"type": "MiniBatchSyncMsg", "worker_id": self.worker_id}
         if progress is not None:
             body["progress"] = progress
+        if idle:
+            body["idle"] = True
         self._send(body)
+
+    def send_mini_batch_return_msg(self) -> None:
+        self._send({"type": "MiniBatchReturnMsg", "worker_id": self.worker_id})
 
     def send_model_eval_ask_msg(self) -> None:
         self._send({"type": "ModelEvalAskMsg", "executor_id": self.worker_id})
@@ -258,8 +264,8 @@ class MiniBatchBarrier:
         self._ev = threading.Semaphore(0)
         self._stop = False
 
-    def await_(self, progress: Optional[int] = None) -> bool:
-        self._sender.send_mini_batch_sync_msg(progress)
+    def await_(self, progress: Optional[int] = None, idle: bool = False) -> bool:
+        self._sender.send_mini_batch_sync_msg(progress, idle)
         self._ev.acquire()
         return self._stop
 
@@ -345,12 +351,10 @@ class WorkerTasklet(Tasklet):
     def _unit(self, name: str, resource: str, seq: int, fn) -> float:
         info = TaskUnitInfo(self.job_id, name, resource, seq)
         sched = self.context.task_units
-        if self.use_task_units:
+        # a stopping worker (plan op / job teardown) finishes the mini-batch it has already been granted -- the global
+        # budget counted it -- but no longer takes part in the job's unit barriers
+        if self.use_task_units and not self._abort.is_set():
             sched.wait_schedule(self.context.tasklet_id, info)
-        if self._abort.is_set():
-            if self.use_task_units:
-                sched.on_task_unit_finished(self.context.tasklet_id, info)
-            raise RuntimeError("tasklet aborted")
         t0 = time.perf_counter()
         try:
             with trace.span(name, job=self.job_id):
@@ -392,6 +396,10 @@ class WorkerTasklet(Tasklet):
                 done, pending_progress = pending_progress, None
                 if self.mini_batch_barrier.await_(done):
                     stop = True
+                    if self._abort.is_set():
+                        # stopped while asking for a mini-batch: the controller counted the request against the global
+                        # budget but the batch will not run here -- hand it back so another worker trains on it
+                        self.sender.send_mini_batch_return_msg()
                     break
                 self.trainer.set_mini_batch_data(batch)
                 self.accessor.get_and_reset_metrics()
@@ -425,7 +433,7 @@ class WorkerTasklet(Tasklet):
             if n_batches == 0 and not stop:
                 # this worker holds no data (all blocks migrated away): just keep syncing
                 done, pending_progress = pending_progress, None
-                if self.mini_batch_barrier.await_(done):
+                if self.mini_batch_barrier.await_(done, idle=True):
                     stop = True
                 else:
                     time.sleep(0.01)
@@ -436,16 +444,22 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.add_custom_metric(em.to_dict())
             self.context.metric_collector.flush()
             epoch += 1
-        if pending_progress is not None:                   # aborted between a batch and its next sync
+        if pending_progress is not None:                   # stopped between a batch and its next sync
             self.sender.send_progress_msg(pending_progress)
         if self.use_task_units:
             self.context.task_units.leave(self.job_id)
+        result = {"num_batches": total_batches, "num_epochs": epoch, "trainer": type(self.trainer).__name__}
+        if self._abort.is_set():
+            # stopped by a plan op (worker deleted / switched to a server) or by the teardown of a failed job: the
+            # job goes on (or is over) without this worker -- no CLEANUP barrier, no end-of-training validation
+            return {**result, "stopped": True, **self.trainer.summary()}
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
         summary = self.trainer.summary()
         self.trainer.cleanup()
-        return {"num_batches": total_batches, "num_epochs": epoch, "trainer": type(self.trainer).__name__, **summary}
+        return {**result, **summary}
 
     def close(self) -> None:
+        """Graceful stop: the loop ends at the next mini-batch boundary (a batch in flight completes)."""
         self._abort.set()
         self.mini_batch_barrier.on_control_msg(True)
         self.global_barrier.on_release_msg()

@@ -28,10 +28,21 @@ def _args(optimizer, workers=2, servers=2, epochs=6):
 
 
 @pytest.mark.parametrize("optimizer", ["EmptyPlanOptimizer", "DeleteOneServerOptimizer", "AddOneServerOptimizer",
-                                       "MoveModelBlocksOptimizer"])
+                                       "MoveModelBlocksOptimizer", "DeleteOneWorkerOptimizer", "AddOneWorkerOptimizer",
+                                       "ExchangeOneOptimizer"])
 def test_addvector_validates_under_server_reconfiguration(optimizer):
+    """Servers AND workers are added / deleted / switched on the live job; AddVector checks in its cleanup that every
+    granted mini-batch was applied exactly once (a stopped worker finishes the batch in flight and hands back a
+    batch it was granted but did not start; a worker started by a plan gets the master's messages from its first
+    sync on)."""
     res = ETDolphinLauncher.launch(examples.ADD_VECTOR, _args(optimizer))
     assert res.ok, res.messages
+    if optimizer == "DeleteOneWorkerOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 2, W: 1)" in m for m in res.messages), res.messages
+    if optimizer == "AddOneWorkerOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 2, W: 3)" in m for m in res.messages), res.messages
+    if optimizer == "ExchangeOneOptimizer":
+        assert any("(S: 2, W: 2) -> (S: 1, W: 3)" in m for m in res.messages), res.messages
     if optimizer == "DeleteOneServerOptimizer":
         assert any("(S: 2, W: 2) -> (S: 1, W: 2)" in m for m in res.messages), res.messages
     if optimizer == "AddOneServerOptimizer":
@@ -123,3 +134,44 @@ def test_worker_state_manager_barriers_with_optimization():
     assert sm.sm.current_state == "RUN_FINISHING"
     sm.on_sync_msg("c", "RUN"); sm.on_sync_msg("d", "RUN")
     assert sm.sm.current_state == "CLEANUP" and sorted(released[1:]) == ["a", "c", "d"]
+
+
+def test_heterogeneous_optimizer_swaps_roles_and_compiles_to_switches():
+    """The fat-pipe executor should serve and the fast one should work: the optimizer proposes the role swap under the
+    same ids (-> SWITCH ops, no re-allocation) and block moves proportional to bandwidth / throughput."""
+    from harmony_b200.dolphin.optimizer import HeterogeneousOptimizer
+    bw = {"fat": 8e11, "thin": 1e10, "h2": 1e11, "h3": 1e11}
+    opt = HeterogeneousOptimizer(num_total_mini_batches=100, default_bandwidth=1e11, host_to_bandwidth=bw)
+    servers = [EvaluatorParameters("s_thin", 16, {}, hostname="thin")]
+    workers = [EvaluatorParameters("w_fat", 8, {"batch_comp_time_sec": 0.5}, hostname="fat"),
+               EvaluatorParameters("w2", 8, {"batch_comp_time_sec": 0.5}, hostname="h2"),
+               EvaluatorParameters("w3", 8, {"batch_comp_time_sec": 0.5}, hostname="h3")]
+    plan = opt.optimize({NAMESPACE_SERVER: servers, NAMESPACE_WORKER: workers}, 4,
+                        {"AVG_PULL_SIZE_PER_MINI_BATCH": 4e9})
+    assert not plan.is_empty() and plan.optimizer_type == "HETEROGENEOUS"
+    assert plan.get_evaluators_to_delete(NAMESPACE_SERVER) == ["s_thin"] and "w_fat" in plan.get_evaluators_to_add(NAMESPACE_SERVER)
+    assert "w_fat" in plan.get_evaluators_to_delete(NAMESPACE_WORKER) and "s_thin" in plan.get_evaluators_to_add(NAMESPACE_WORKER)
+    # every model block leaves the old server, every data block of the new server goes to a worker
+    assert sum(t.num_blocks for t in plan.get_transfer_steps(NAMESPACE_SERVER) if t.src_id == "s_thin") == 16
+    assert sum(t.num_blocks for t in plan.get_transfer_steps(NAMESPACE_WORKER) if t.src_id == "w_fat") == 8
+    et = _compiler().compile(plan, 0)
+    types = _types(et)
+    assert types.get("ALLOCATE", 0) == 0 and types.get("DEALLOCATE", 0) == 0      # pure switches
+    assert types["MOVE"] >= 2 and types["START"] >= 2 and types["STOP"] >= 1
+    # already optimal: a homogeneous cluster stays as it is
+    same = HeterogeneousOptimizer(num_total_mini_batches=100, default_bandwidth=1e11)
+    s2 = [EvaluatorParameters("s0", 16, {})]
+    w2 = [EvaluatorParameters(f"w{i}", 8, {"batch_comp_time_sec": 0.5}) for i in range(3)]
+    assert same.optimize({NAMESPACE_SERVER: s2, NAMESPACE_WORKER: w2}, 4, {"AVG_PULL_SIZE_PER_MINI_BATCH": 1e3}).is_empty()
+
+
+def test_heterogeneous_optimizer_switches_roles_on_a_live_job(tmp_path):
+    """AddVector keeps its sums exact while the optimizer turns the thin-pipe server into a worker and a worker into
+    the server (SWITCH ops: stop / move / unassociate / associate / subscribe / start on live executors)."""
+    bwf = tmp_path / "bw"
+    bwf.write_text("# executor ids on one host\nexecutor-2 1e6\nexecutor-3 1e6\nexecutor-0 8e12\nexecutor-1 8e9\n")
+    args = _args("HeterogeneousOptimizer") + ["-host_to_bandwidth_file_path", str(bwf)]
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, args)
+    assert res.ok, res.messages
+    changed = [m for m in res.messages if "(S: " in m]
+    assert changed, res.messages          # at least one reconfiguration happened and the job still validated
