@@ -108,7 +108,8 @@ def test_device_move_aborts_cleanly_when_the_receiver_fails(cluster):
     np.testing.assert_array_equal(np.asarray(t0.multi_get_or_init(keys).get(30)), np.full((256, 4), 2.0))
 
 
-@pytest.mark.parametrize("optimizer", ["DeleteOneServerOptimizer", "AddOneServerOptimizer", "MoveModelBlocksOptimizer"])
+@pytest.mark.parametrize("optimizer", ["DeleteOneServerOptimizer", "AddOneServerOptimizer", "MoveModelBlocksOptimizer",
+                                       "ExchangeOneOptimizer", "DeleteOneWorkerOptimizer"])
 def test_addvector_job_reconfigures_over_the_device_protocol(optimizer, monkeypatch):
     """The self-validating AddVector job with a live re-partition, `-backend device`, executors emulated on the host:
     plan compiler -> plan executor -> MOVE op -> quiesce / copy / flip / resume, while workers keep pushing."""
