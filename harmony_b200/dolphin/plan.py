@@ -142,6 +142,11 @@ class PlanCompiler:
         unassoc: Dict[str, UnassociateOp] = {}
         sub: Dict[str, SubscribeOp] = {}
         unsub: Dict[str, UnsubscribeOp] = {}
+        # apps with a worker-local model table (NMF's L, LDA's assignments): its blocks are key-aligned with the input
+        # table's, so every worker-side associate / unassociate / move has a twin on that table
+        local = self.local_model_table_id
+        assoc_l: Dict[str, AssociateOp] = {}
+        unassoc_l: Dict[str, UnassociateOp] = {}
         # switch
         for e in switch[NAMESPACE_SERVER]:        # server -> worker
             stop[e] = p.add_op(StopOp(e))
@@ -149,10 +154,15 @@ class PlanCompiler:
             sub[e] = p.add_op(SubscribeOp(e, self.model_table_id), [unassoc[e]])
             assoc[e] = p.add_op(AssociateOp(e, self.input_table_id))
             start[e] = p.add_op(self._start_op(e, True), [assoc[e], sub[e]])
+            if local:
+                assoc_l[e] = p.add_op(AssociateOp(e, local))
+                p.dag.add_edge(assoc_l[e], start[e])
         for e in switch[NAMESPACE_WORKER]:        # worker -> server
             stop[e] = p.add_op(StopOp(e))
             unsub[e] = p.add_op(UnsubscribeOp(e, self.model_table_id), [stop[e]])
             unassoc[e] = p.add_op(UnassociateOp(e, self.input_table_id), [stop[e]])
+            if local:
+                unassoc_l[e] = p.add_op(UnassociateOp(e, local), [stop[e]])
             assoc[e] = p.add_op(AssociateOp(e, self.model_table_id), [unsub[e]])
             start[e] = p.add_op(self._start_op(e, False), [assoc[e]])
         # delete
@@ -166,6 +176,9 @@ class PlanCompiler:
                 if ns == NAMESPACE_WORKER:
                     unsub[e] = p.add_op(UnsubscribeOp(e, self.model_table_id), [stop[e]])
                     p.dag.add_edge(unsub[e], dealloc[e])
+                    if local:
+                        unassoc_l[e] = p.add_op(UnassociateOp(e, local))
+                        p.dag.add_edge(unassoc_l[e], dealloc[e])
                 else:
                     p.dag.add_edge(stop[e], dealloc[e])
         # add
@@ -177,6 +190,9 @@ class PlanCompiler:
                 if ns == NAMESPACE_WORKER:
                     sub[e] = p.add_op(SubscribeOp(e, self.model_table_id), [alloc[e]])
                     start[e] = p.add_op(self._start_op(e, True), [sub[e]])
+                    if local:
+                        assoc_l[e] = p.add_op(AssociateOp(e, local), [alloc[e]])
+                        p.dag.add_edge(assoc_l[e], start[e])
                 else:
                     start[e] = p.add_op(self._start_op(e, False), [alloc[e]])
         # add/del dependency when resources are short
@@ -193,6 +209,20 @@ class PlanCompiler:
             table = self.input_table_id if ns == NAMESPACE_WORKER else self.model_table_id
             for t in ts:
                 moves.append(p.add_op(MoveOp(t.src_id, t.dst_id, table, t.num_blocks)))
+        if local:
+            # the twin move follows the input move and picks the same (lowest) block ids: the two tables keep
+            # identical partitions, so a record and its local-model row always live on the same worker
+            for m in list(moves):
+                if m.table_id == self.input_table_id:
+                    tw = p.add_op(MoveOp(m.src_executor_id, m.dst_executor_id, local, m.num_blocks), [m])
+                    if m.dst_executor_id in assoc_l:
+                        p.dag.add_edge(assoc_l[m.dst_executor_id], tw)
+                    if m.dst_executor_id in start:
+                        p.dag.add_edge(tw, start[m.dst_executor_id])
+                    if m.src_executor_id in unassoc_l:
+                        p.dag.add_edge(tw, unassoc_l[m.src_executor_id])
+                    if m.src_executor_id in stop:
+                        p.dag.add_edge(stop[m.src_executor_id], tw)
         for m in moves:
             if m.dst_executor_id in assoc:
                 p.dag.add_edge(assoc[m.dst_executor_id], m)

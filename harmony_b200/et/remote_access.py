@@ -279,8 +279,9 @@ class RemoteAccessOpSender:
                 time.sleep(RESEND_INTERVAL_S)
                 if comps is None:
                     break
-                owner, unlock = comps.ownership.resolve_executor_with_lock(op.block_id)
-                unlock()
+                # lock-free read of the ownership array: the caller may still hold this block's read lock (first
+                # attempt of a multi-key request), and re-acquiring it behind a waiting ownership update would deadlock
+                owner = comps.ownership.resolve_executor(op.block_id)
                 if owner is None:   # became local meanwhile
                     self._ex.handler.enqueue_local(op)
                     return

@@ -175,3 +175,42 @@ def test_heterogeneous_optimizer_switches_roles_on_a_live_job(tmp_path):
     assert res.ok, res.messages
     changed = [m for m in res.messages if "(S: " in m]
     assert changed, res.messages          # at least one reconfiguration happened and the job still validated
+
+
+def test_plan_compiler_adds_twin_ops_for_the_worker_local_model_table():
+    c = _compiler()
+    c.local_model_table_id = "local_model"
+    p = Plan(); p.evaluators_to_add[NAMESPACE_WORKER].append("NEW"); p.transfer_steps[NAMESPACE_WORKER].append(TransferStep("w0", "NEW", 2))
+    et = c.compile(p, 1)
+    assert _types(et) == {"ALLOCATE": 1, "ASSOCIATE": 2, "SUBSCRIBE": 1, "START": 1, "MOVE": 2}
+    moves = [o for o in et.ops() if o.op_type == "MOVE"]
+    inp, loc = (moves[0], moves[1]) if moves[0].table_id == c.input_table_id else (moves[1], moves[0])
+    assert loc.table_id == "local_model" and et.dag.is_adjacent(inp, loc)           # same blocks, input first
+    start = next(o for o in et.ops() if o.op_type == "START")
+    assert et.dag.is_adjacent(loc, start)
+    p = Plan(); p.evaluators_to_delete[NAMESPACE_WORKER].append("w1"); p.transfer_steps[NAMESPACE_WORKER].append(TransferStep("w1", "w0", 3))
+    assert _types(c.compile(p)) == {"STOP": 1, "MOVE": 2, "UNASSOCIATE": 2, "UNSUBSCRIBE": 1, "DEALLOCATE": 1}
+
+
+@pytest.mark.parametrize("app_name,optimizer", [("nmf", "AddOneWorkerOptimizer"), ("nmf", "DeleteOneWorkerOptimizer"),
+                                                ("lda", "ExchangeOneOptimizer")])
+def test_apps_with_local_model_tables_reconfigure_workers_live(app_name, optimizer, tmp_path):
+    """NMF's L rows / LDA's topic assignments live in a worker-local table whose blocks must travel with the input
+    blocks when workers are added, deleted or switched."""
+    from harmony_b200.common.samples import write_lda_sample, write_nmf_sample
+    from harmony_b200.mlapps import lda, nmf
+    opt = ["-optimizer", optimizer, "-optimization_interval_ms", "300", "-delay_after_optimization_ms", "100",
+           "-min_num_required_batch_metrics", "1", "-num_extra_resources", "1", "-num_dolphin_workers", "2",
+           "-num_servers", "2", "-num_mini_batches", "8", "-num_worker_blocks", "8", "-num_server_blocks", "4"]
+    if app_name == "nmf":
+        d = write_nmf_sample(str(tmp_path / "n"), rows=160, cols=30, rank=4)
+        res = ETDolphinLauncher.launch(nmf.APP, ["-input", d, "-max_num_epochs", "30", "-step_size", "0.01", "-rank", "4",
+                                                 "-features", "30", "-decay_rate", "1.0"] + opt)
+        assert res.ok, res.messages
+        assert max(r["last_batch_loss"] for r in res.results) < 8.0, res.results       # ~4 without reconfiguration
+    else:
+        d = write_lda_sample(str(tmp_path / "l"), docs=80, vocab=50, topics=3, doc_len=30)
+        res = ETDolphinLauncher.launch(lda.APP, ["-input", d, "-max_num_epochs", "10", "-num_topics", "3",
+                                                 "-num_vocabs", "50"] + opt)
+        assert res.ok, res.messages
+    assert any("(S: 2, W: 2) -> " in m for m in res.messages), res.messages
