@@ -381,6 +381,7 @@ class WorkerTasklet(Tasklet):
         # host RSS + HBM sampled every -memory_measure_interval ms; max / mean ride on the epoch metrics
         mem = MemoryMetricTracker(max(0.01, int(self.context.params.get("memory_measure_interval", 1000)) / 1000.0))
         pending_progress: Optional[int] = None
+        idle_left = False          # True while this worker has left the unit barriers because it holds no data
         flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
         last_flush = 0.0
         while not stop and not self._abort.is_set():
@@ -432,11 +433,18 @@ class WorkerTasklet(Tasklet):
                     last_flush = now
             if n_batches == 0 and not stop:
                 # this worker holds no data (all blocks migrated away): just keep syncing
+                # ... and stays out of the job's unit barriers meanwhile (the others must not wait for it)
+                if self.use_task_units and not idle_left:
+                    self.context.task_units.leave(self.job_id)
+                    idle_left = True
                 done, pending_progress = pending_progress, None
                 if self.mini_batch_barrier.await_(done, idle=True):
                     stop = True
                 else:
                     time.sleep(0.01)
+            elif idle_left and not stop:
+                self.context.task_units.join(self.job_id)       # it has data again
+                idle_left = False
             if not stop:
                 self.trainer.on_epoch_finished(epoch)
             em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0,
@@ -446,7 +454,7 @@ class WorkerTasklet(Tasklet):
             epoch += 1
         if pending_progress is not None:                   # stopped between a batch and its next sync
             self.sender.send_progress_msg(pending_progress)
-        if self.use_task_units:
+        if self.use_task_units and not idle_left:
             self.context.task_units.leave(self.job_id)
         result = {"num_batches": total_batches, "num_epochs": epoch, "trainer": type(self.trainer).__name__}
         if self._abort.is_set():

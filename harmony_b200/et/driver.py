@@ -544,6 +544,11 @@ class GlobalTaskUnitScheduler:
         if n is not None and n > 1:
             self.on_job_resize(job_id, n - 1)
 
+    def on_join(self, job_id: str, executor_id: str) -> None:
+        with self._lock:
+            if job_id in self._job_size:
+                self._job_size[job_id] += 1
+
     def on_wait(self, m: Dict[str, Any]) -> None:
         key = (m["job_id"], m["unit_name"], m["seq"])
         with self._lock:
@@ -1104,6 +1109,8 @@ class ETMaster:
             self.chkp_master.on_load_done(m["op_id"], m.get("num_items"))
         elif t == "TaskUnitWait":
             self.task_units.on_wait(m)
+        elif t == "TaskUnitJoin":
+            self.task_units.on_join(m["job_id"], m["executor_id"])
         elif t == "TaskUnitLeave":
             self.task_units.on_leave(m["job_id"], m["executor_id"])
         elif t == "TaskletStatus":

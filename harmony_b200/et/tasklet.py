@@ -209,6 +209,12 @@ class LocalTaskUnitScheduler:
             self._ex.send_to_driver({"type": "TaskUnitLeave", "job_id": job_id,
                                      "executor_id": self._ex.executor_id})
 
+    def join(self, job_id: str) -> None:
+        """The worker takes part in the job's unit barriers again (it had left while it held no data)."""
+        if self.enabled:
+            self._ex.send_to_driver({"type": "TaskUnitJoin", "job_id": job_id,
+                                     "executor_id": self._ex.executor_id})
+
     def on_task_unit_finished(self, tasklet_id: str, unit: TaskUnitInfo) -> None:
         if not self.enabled or unit.resource == VOID:
             return

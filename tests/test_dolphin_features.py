@@ -248,3 +248,21 @@ def test_bad_input_fails_the_job_not_the_server(tmp_path):
         assert js.driver.wait_job("MLR-3", timeout=120)[0]
     finally:
         js.stop(kill=True)
+
+
+def test_worker_without_data_idles_without_blocking_the_job(tmp_path):
+    """One record, two executors: the worker that received no data must neither consume the mini-batch budget nor
+    make the other worker wait at the job's task-unit barriers (job-server path: task units on)."""
+    one = tmp_path / "one"
+    one.write_text("1 0:0.5 3:1.0\n")
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port})).start()
+    try:
+        args = ["-input", str(one), "-classes", "4", "-features", "8", "-max_num_epochs", "3", "-num_mini_batches", "2",
+                "-num_worker_blocks", "2", "-step_size", "0.1", "-port", str(port)]
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, args, port=port).startswith("true")
+        ok, result = js.driver.wait_job("MLR-0", timeout=60)
+        assert ok, result
+        assert sorted(r["num_batches"] for r in result) == [0, 6]          # the whole budget ran where the data is
+    finally:
+        js.stop(kill=True)
