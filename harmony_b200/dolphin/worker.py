@@ -55,6 +55,10 @@ class Trainer:
     def cleanup(self) -> None:
         pass
 
+    def on_worker_stopped(self) -> None:
+        """A plan removed this worker mid-training (deleted / switched to a server).  Unlike `cleanup()` this is not
+        the end of the job: publish worker-local state that must survive (its blocks migrate next), validate nothing."""
+
     def summary(self) -> Dict[str, float]:
         """Optional end-of-training numbers returned with the tasklet result."""
         return {}
@@ -460,6 +464,9 @@ class WorkerTasklet(Tasklet):
         if self._abort.is_set():
             # stopped by a plan op (worker deleted / switched to a server) or by the teardown of a failed job: the
             # job goes on (or is over) without this worker -- no CLEANUP barrier, no end-of-training validation
+            on_stopped = getattr(self.trainer, "on_worker_stopped", None)
+            if on_stopped is not None:
+                on_stopped()
             return {**result, "stopped": True, **self.trainer.summary()}
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
         summary = self.trainer.summary()

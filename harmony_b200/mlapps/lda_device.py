@@ -94,6 +94,9 @@ class LDADeviceTrainer(Trainer):
             - float(self._torch.lgamma(lens + K * a).sum())
         return {"docLLH": doc, "wordLLH": word}
 
+    def on_worker_stopped(self) -> None:
+        self.cleanup()          # publish the HBM-resident local model before its table blocks migrate
+
     def cleanup(self) -> None:
         if self.local_table is not None and self._docs:
             z = self.model.z.cpu().numpy()

@@ -69,6 +69,9 @@ class NMFDeviceTrainer(Trainer):
     def summary(self) -> Dict[str, float]:
         return {"last_batch_loss": float(self.model.loss[0])}
 
+    def on_worker_stopped(self) -> None:
+        self.cleanup()          # publish the HBM-resident local model before its table blocks migrate
+
     def cleanup(self) -> None:
         # publish the local model into the local-model table (checkpoint / offline evaluation)
         if self.local_table is not None and self._keys:
