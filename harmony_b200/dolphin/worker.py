@@ -389,6 +389,22 @@ class WorkerTasklet(Tasklet):
         flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
         last_flush = 0.0
         while not stop and not self._abort.is_set():
+            if self.input_table.get_local_tablet().get_num_data_items() == 0:
+                # no input data here (all blocks migrated away, or none was loaded): ask the master whether to stop,
+                # without consuming the mini-batch budget, holding the SSP clock back or counting in the job's unit
+                # barriers; no epoch accounting while idle
+                if self.use_task_units and not idle_left:
+                    self.context.task_units.leave(self.job_id)
+                    idle_left = True
+                done, pending_progress = pending_progress, None
+                if self.mini_batch_barrier.await_(done, idle=True):
+                    stop = True
+                    break
+                time.sleep(0.05)
+                continue
+            if idle_left:
+                self.context.task_units.join(self.job_id)       # it has data again
+                idle_left = False
             epoch_t0 = time.perf_counter()
             mem.start()
             self.data_provider.prepare_data_for_epoch()
@@ -436,19 +452,7 @@ class WorkerTasklet(Tasklet):
                     self.context.metric_collector.flush()
                     last_flush = now
             if n_batches == 0 and not stop:
-                # this worker holds no data (all blocks migrated away): just keep syncing
-                # ... and stays out of the job's unit barriers meanwhile (the others must not wait for it)
-                if self.use_task_units and not idle_left:
-                    self.context.task_units.leave(self.job_id)
-                    idle_left = True
-                done, pending_progress = pending_progress, None
-                if self.mini_batch_barrier.await_(done, idle=True):
-                    stop = True
-                else:
-                    time.sleep(0.01)
-            elif idle_left and not stop:
-                self.context.task_units.join(self.job_id)       # it has data again
-                idle_left = False
+                time.sleep(0.01)                 # its blocks left in the middle of the epoch: idle from the next pass
             if not stop:
                 self.trainer.on_epoch_finished(epoch)
             em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0,
