@@ -146,7 +146,7 @@ class TaskletRuntime:
         if t is not None:
             t.on_msg(payload)
         else:
-            LOG.warning("custom message for unknown tasklet %s", tasklet_id)
+            LOG.debug("custom message for unknown tasklet %s (already finished)", tasklet_id)
 
     def running(self):
         with self._lock:
