@@ -266,3 +266,63 @@ def test_worker_without_data_idles_without_blocking_the_job(tmp_path):
         assert sorted(r["num_batches"] for r in result) == [0, 6]          # the whole budget ran where the data is
     finally:
         js.stop(kill=True)
+
+
+@pytest.mark.parametrize("slack", [0, 1, 3])
+def test_minibatch_controller_random_schedules_keep_the_ssp_invariants(slack):
+    """Random interleavings of syncs, idle syncs, deletions, late joiners and hand-backs: the controller never grants
+    more than the budget, never lets a worker run more than `slack` batches ahead of the slowest active one, and never
+    leaves everybody blocked (liveness)."""
+    import random
+    from harmony_b200.dolphin.master import MiniBatchController
+
+    class Sender:
+        def __init__(self):
+            self.msgs = []
+
+        def send_mini_batch_control_msg(self, w, stop):
+            self.msgs.append((w, stop))
+    for seed in range(25):
+        rng = random.Random(seed)
+        snd = Sender()
+        total_epochs, nmb = 4, 6
+        c = MiniBatchController(total_epochs, nmb, slack, snd)
+        workers = [f"w{i}" for i in range(4)]
+        waiting, granted, stopped = set(), {w: 0 for w in workers}, set()
+        idle_req = set()                                         # pending requests that were idle syncs (not grants)
+        joined_late = False
+        for _ in range(400):
+            # deliver control messages
+            for w, stop in snd.msgs:
+                if w in waiting:
+                    waiting.discard(w)
+                    if stop:
+                        stopped.add(w)
+                    elif w not in idle_req:
+                        granted[w] += 1
+                    idle_req.discard(w)
+            snd.msgs.clear()
+            active = [w for w in workers if w not in stopped]
+            runnable = [w for w in active if w not in waiting]
+            if not active:
+                break
+            assert runnable or c._closed, "every active worker is blocked: SSP deadlock"
+            if not runnable:
+                continue
+            w = rng.choice(runnable)
+            r = rng.random()
+            if r < 0.04 and len(active) > 1:                 # a plan deletes the worker
+                c.on_worker_deleted(w); stopped.add(w)
+            elif r < 0.08:                                   # it idles for a while
+                c.on_idle_sync(w); waiting.add(w); idle_req.add(w)
+            elif r < 0.10 and not joined_late:               # a plan adds a worker
+                workers.append("late"); granted["late"] = 0; joined_late = True
+            elif r < 0.12 and granted[w] > 0:                # stopped right after being granted: hand the batch back
+                c.on_return(w); granted[w] -= 1
+            else:
+                c.on_sync(w); waiting.add(w)
+            prog = {x: p for x, p in c._progress.items()}
+            if len(prog) > 1:
+                assert max(prog.values()) - min(prog.values()) <= slack + 1, prog
+            assert c.num_mini_batches_done <= total_epochs * nmb + len(workers)
+        assert sum(granted.values()) <= total_epochs * nmb
