@@ -272,3 +272,47 @@ def test_executor_failure_fails_running_tasklets(cluster):
     res = rt.get_task_result(timeout=5)
     assert not res.is_success and "injected fault" in res.error
     assert seen == [execs[0].id] and execs[0].id not in master.executors
+
+
+def test_task_unit_barriers_with_uneven_workers_never_deadlock():
+    """Three jobs share four executors; the workers of a job run DIFFERENT numbers of mini-batches (global budget) and
+    leave the job's unit barriers when they finish.  Units: PULL(NET) -> COMP(CPU) -> PUSH(NET) per batch with the
+    per-executor slots CPU x1 / NET x2.  Every worker must finish (no barrier waits for a departed peer, no slot is
+    held across a barrier)."""
+    import random
+    import threading
+    from harmony_b200.et import local_cluster
+    from harmony_b200.et.tasklet import CPU, NET, TaskUnitInfo
+    master, execs, launcher = local_cluster(4)
+    try:
+        jobs = ["J0", "J1", "J2"]
+        for j in jobs:
+            master.task_units.on_job_start(j, 4)
+        done, errors = [], []
+
+        def worker(job, eid, n_batches, seed):
+            rng = random.Random(seed)
+            sched = launcher.executors[eid].task_unit_scheduler
+            tid = f"{job}-worker-{eid}"
+            try:
+                for seq in range(n_batches):
+                    for name, res in (("PULL", NET), ("COMP", CPU), ("PUSH", NET)):
+                        info = TaskUnitInfo(job, name, res, seq)
+                        sched.wait_schedule(tid, info)
+                        time.sleep(rng.random() * 0.002)
+                        sched.on_task_unit_finished(tid, info)
+                sched.leave(job)
+                done.append((job, eid))
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+        ths = []
+        for ji, job in enumerate(jobs):
+            for ei, e in enumerate(execs):
+                ths.append(threading.Thread(target=worker, args=(job, e.id, 3 + (ei * 2 + ji) % 6, 10 * ji + ei),
+                                            daemon=True))
+        [t.start() for t in ths]
+        [t.join(60) for t in ths]
+        assert not errors, errors
+        assert len(done) == 12, f"{12 - len(done)} workers are stuck at a unit barrier"
+    finally:
+        master.close()
