@@ -214,3 +214,60 @@ def test_apps_with_local_model_tables_reconfigure_workers_live(app_name, optimiz
                                                  "-num_vocabs", "50"] + opt)
         assert res.ok, res.messages
     assert any("(S: 2, W: 2) -> " in m for m in res.messages), res.messages
+
+
+def test_plan_compiler_random_plans_compile_to_executable_dags():
+    """Random valid plans (adds, deletes, switches in either direction, transfers; with and without a local-model
+    table): the compiled DAG must be executable to completion in dependency order and respect the safety orderings
+    (a block moves to an executor only after it is associated, leaves one only after its tasklet stopped and before it
+    is unassociated; a tasklet starts only after its blocks arrived)."""
+    import random
+    for seed in range(60):
+        rng = random.Random(seed)
+        c = _compiler()
+        if seed % 2:
+            c.local_model_table_id = "local_model"
+        servers = [f"s{i}" for i in range(rng.randint(1, 3))]
+        workers = [f"w{i}" for i in range(rng.randint(1, 3))]
+        p = Plan()
+        ns_nodes = {NAMESPACE_SERVER: list(servers), NAMESPACE_WORKER: list(workers)}
+        extra = 0
+        for ns, prefix in ((NAMESPACE_SERVER, "NS"), (NAMESPACE_WORKER, "NW")):
+            if rng.random() < 0.5:
+                p.evaluators_to_add[ns].append(prefix + "0"); extra += 1
+            if len(ns_nodes[ns]) > 1 and rng.random() < 0.5:
+                p.evaluators_to_delete[ns].append(ns_nodes[ns][-1])
+        for ns in (NAMESPACE_SERVER, NAMESPACE_WORKER):
+            dels, adds = set(p.evaluators_to_delete[ns]), list(p.evaluators_to_add[ns])
+            keep = [n for n in ns_nodes[ns] if n not in dels]
+            for d in dels:                                   # a deleted node sends everything away
+                p.transfer_steps[ns].append(TransferStep(d, rng.choice(keep + adds), rng.randint(1, 4)))
+            for a in adds:                                   # a new node receives something
+                p.transfer_steps[ns].append(TransferStep(rng.choice(keep), a, rng.randint(1, 4)))
+        p.validate()
+        et = c.compile(p, extra)
+        ops = list(et.ops())
+        order, guard = [], 0
+        while et.get_ready_ops():
+            op = sorted(et.get_ready_ops(), key=repr)[rng.randrange(len(et.get_ready_ops()))]
+            order.append(op)
+            et.on_complete(op)
+            guard += 1
+            assert guard <= len(ops)
+        assert len(order) == len(ops), f"seed {seed}: {len(ops) - len(order)} ops can never run (cycle)"
+        pos = {id(o): i for i, o in enumerate(order)}
+        first = lambda pred: min([pos[id(o)] for o in order if pred(o)], default=None)  # noqa: E731
+        for m in [o for o in order if o.op_type == "MOVE"]:
+            dst, src = m.dst_executor_id, m.src_executor_id
+            a = first(lambda o: o.op_type == "ASSOCIATE" and o.executor_id == dst and o.table_id == m.table_id)
+            if a is not None:
+                assert a < pos[id(m)], (seed, "move before associate", m)
+            st = first(lambda o: o.op_type == "START" and o.executor_id == dst)
+            if st is not None:
+                assert pos[id(m)] < st, (seed, "start before its blocks arrived", m)
+            sp = first(lambda o: o.op_type == "STOP" and o.executor_id == src)
+            if sp is not None:
+                assert sp < pos[id(m)], (seed, "move before the source tasklet stopped", m)
+            un = first(lambda o: o.op_type == "UNASSOCIATE" and o.executor_id == src and o.table_id == m.table_id)
+            if un is not None:
+                assert pos[id(m)] < un, (seed, "unassociate before its blocks left", m)
