@@ -205,3 +205,39 @@ def test_bench_reference_arm_reports_unavailable():
     assert p.returncode == 0, p.stderr
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and isinstance(line["unavailable"], str) and line["unavailable"]
+
+
+def test_native_parser_fuzz_against_python():
+    """Random well-formed inputs with awkward spacing / number formats (tabs, CRLF, `+`, exponents, blank and comment
+    lines, very long lines) through the multi-threaded native parser and the Python parsers."""
+    import random
+    from harmony_b200.ops import native_or_none
+    if native_or_none() is None:
+        pytest.skip("native extension not built")
+    from harmony_b200.common import dataloader as dl
+    rng = random.Random(0)
+
+    def num(x):
+        return rng.choice([f"{x}", f"{x:.3f}", f"{x:.2e}", f"+{x:.4f}" if x >= 0 else f"{x:.4f}"])
+    sep = lambda: rng.choice([" ", "  ", "\t", " \t "])  # noqa: E731
+    eol = lambda: rng.choice(["\n", "\r\n", " \n", "\n\n", "\n# c\n"])  # noqa: E731
+    for name, gen in (
+        ("mlr", lambda: str(rng.randint(0, 9)) + "".join(sep() + f"{rng.randint(0, 999)}:{num(rng.uniform(-5, 5))}"
+                                                          for _ in range(rng.randint(0, 40)))),
+        ("lasso", lambda: num(rng.uniform(-9, 9)) + "".join(sep() + f"{rng.randint(0, 99)}:{num(rng.uniform(-5, 5))}"
+                                                             for _ in range(rng.randint(1, 300)))),
+        ("nmf", lambda: f"{rng.randint(1, 500)}:" + "".join(sep() + f"{rng.randint(1, 99)},{num(rng.uniform(0, 5))}"
+                                                           for _ in range(rng.randint(1, 30)))),
+        ("lda", lambda: sep().join(str(rng.randint(0, 9999)) for _ in range(rng.randint(1, 120)))),
+    ):
+        text = "".join(gen() + eol() for _ in range(600))
+        data = text.encode()
+        p = dl.make_parser(name)
+        fast, slow = p.parse_bytes(data), p.parse(text.splitlines())
+        assert len(fast) == len(slow) == 600, name
+        for a, b in zip(fast, slow):
+            a = a if isinstance(a, tuple) else (a,)
+            b = b if isinstance(b, tuple) else (b,)
+            for x, y in zip(a, b):
+                np.testing.assert_allclose(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64),
+                                           rtol=1e-6, atol=0, err_msg=name)
