@@ -241,3 +241,31 @@ def test_native_parser_fuzz_against_python():
             for x, y in zip(a, b):
                 np.testing.assert_allclose(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64),
                                            rtol=1e-6, atol=0, err_msg=name)
+
+
+def test_split_reader_fuzz_every_line_in_exactly_one_split(tmp_path):
+    """Random files (with / without trailing newline, empty lines, one huge line) cut into 1..40 byte-range splits:
+    the concatenation of the splits' lines is the file's lines, for the line reader and the byte reader alike."""
+    import random
+    from harmony_b200.common import dataloader as dl
+    rng = random.Random(1)
+    for case in range(40):
+        lines = ["x" * rng.choice([0, 1, 5, 40, 400]) + str(i) for i in range(rng.randint(1, 120))]
+        if case % 7 == 0:
+            lines[rng.randrange(len(lines))] = "y" * 5000
+        body = "\n".join(lines) + ("\n" if case % 2 else "")
+        path = tmp_path / f"f{case}"
+        path.write_text(body)
+        want = body.split("\n")
+        if want and want[-1] == "":
+            want = want[:-1]
+        k = rng.randint(1, 40)
+        splits = dl.get_splits(str(path), k)
+        assert len(splits) == k
+        by_lines = [ln for s in splits for ln in dl.read_split(s)]
+        by_bytes = b"".join(dl.read_split_bytes(s) for s in splits).decode()
+        by_bytes = by_bytes.split("\n")
+        if by_bytes and by_bytes[-1] == "":
+            by_bytes = by_bytes[:-1]
+        assert by_lines == want, (case, k)
+        assert by_bytes == want, (case, k)
