@@ -271,3 +271,40 @@ def test_plan_compiler_random_plans_compile_to_executable_dags():
             un = first(lambda o: o.op_type == "UNASSOCIATE" and o.executor_id == src and o.table_id == m.table_id)
             if un is not None:
                 assert pos[id(m)] < un, (seed, "unassociate before its blocks left", m)
+
+
+@pytest.mark.parametrize("kind", ["HomogeneousOptimizer", "HeterogeneousOptimizer"])
+def test_optimizers_random_inputs_yield_valid_conserving_plans(kind):
+    """Random clusters (block counts, compute times, bandwidths, extra resources): whatever the optimizer decides must
+    validate, conserve the blocks of each namespace, empty every deleted executor, never over-draw a sender, and
+    compile."""
+    import random
+    from harmony_b200.dolphin.optimizer import HeterogeneousOptimizer
+    for seed in range(80):
+        rng = random.Random(seed)
+        ns_ = rng.randint(1, 4); nw = rng.randint(1, 4)
+        hosts = {f"h{i}": rng.choice([1e9, 1e10, 1e11, 8e11]) for i in range(ns_ + nw)}
+        servers = [EvaluatorParameters(f"s{i}", rng.randint(1, 12), {}, hostname=f"h{i}") for i in range(ns_)]
+        workers = [EvaluatorParameters(f"w{i}", rng.randint(1, 12), {"batch_comp_time_sec": rng.uniform(0.01, 1.0)},
+                                       hostname=f"h{ns_ + i}") for i in range(nw)]
+        cls = HeterogeneousOptimizer if kind == "HeterogeneousOptimizer" else HomogeneousOptimizer
+        opt = cls(num_total_mini_batches=100, default_bandwidth=1e10, opt_benefit_threshold=rng.choice([0.0, 0.05]),
+                  host_to_bandwidth=hosts)
+        extra = rng.randint(0, 2)
+        plan = opt.optimize({NAMESPACE_SERVER: servers, NAMESPACE_WORKER: workers}, ns_ + nw + extra,
+                            {"AVG_PULL_SIZE_PER_MINI_BATCH": rng.choice([1e2, 1e6, 1e9])})
+        plan.validate()
+        for ns, nodes in ((NAMESPACE_SERVER, servers), (NAMESPACE_WORKER, workers)):
+            blocks = {p.id: p.num_blocks for p in nodes}
+            for a in plan.get_evaluators_to_add(ns):
+                blocks.setdefault(a, 0)
+            total = sum(blocks.values())
+            for t in plan.get_transfer_steps(ns):
+                assert t.num_blocks > 0 and blocks[t.src_id] >= t.num_blocks, (seed, ns, t, blocks)
+                blocks[t.src_id] -= t.num_blocks
+                blocks[t.dst_id] = blocks.get(t.dst_id, 0) + t.num_blocks
+            assert sum(blocks.values()) == total
+            for d in plan.get_evaluators_to_delete(ns):
+                assert blocks[d] == 0, (seed, ns, d, blocks)
+        if not plan.is_empty():
+            _compiler().compile(plan, extra)
