@@ -128,3 +128,67 @@ def test_gbt_regression_reduces_residual():
         assert res.ok
         out[epochs] = res.results[0]["last_batch_residual_mse"]
     assert out[8] < 0.3 * out[1], out
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.05])
+def test_host_mlr_gradient_matches_autograd(lam):
+    """The host MLR trainer's pushed delta == -step * d/dW [ sum_i CE_i + lam * B / 2 * |W|^2 ] by torch autograd
+    (the same objective the GPU kernels are tested against: models/mlr.py:mlr_reference_step)."""
+    import torch
+    from harmony_b200.mlapps.mlr import MLRTrainer
+    rng = np.random.default_rng(0)
+    F, C, B, step = 40, 5, 16, 0.1
+    W0 = rng.standard_normal((F, C)).astype(np.float32) * 0.3
+    batch = []
+    for i in range(B):
+        idx = np.sort(rng.choice(F, 6, replace=False)).astype(np.int32)
+        batch.append((i, (idx, rng.random(6).astype(np.float32), int(rng.integers(0, C)))))
+
+    class Acc:
+        pushed = None
+
+        def pull_many(self, keys):
+            return W0[np.asarray(keys)]
+
+        def push_many(self, keys, deltas):
+            Acc.pushed = (np.asarray(keys), np.asarray(deltas))
+    tr = MLRTrainer({"classes": C, "features": F, "step_size": step, "lambda": lam, "decay_rate": 0.9,
+                     "decay_period": 5}, Acc())
+    tr.set_mini_batch_data(batch); tr.pull_model(); tr.local_compute(); tr.push_update()
+    keys, delta = Acc.pushed
+    W = torch.tensor(W0, dtype=torch.float64, requires_grad=True)
+    X = torch.zeros((B, F), dtype=torch.float64)
+    y = torch.tensor([b[1][2] for b in batch])
+    for i, (_, (idx, val, _l)) in enumerate(batch):
+        X[i, idx.astype(np.int64)] = torch.tensor(val, dtype=torch.float64)
+    loss = torch.nn.functional.cross_entropy(X @ W, y, reduction="sum") + lam * B / 2 * (W * W).sum()
+    loss.backward()
+    want = (-step * W.grad).numpy()
+    got = np.zeros((F, C))
+    got[keys] = delta
+    touched = np.unique(np.concatenate([b[1][0] for b in batch]))
+    rows = np.arange(F) if lam else touched
+    np.testing.assert_allclose(got[rows], want[rows], rtol=2e-4, atol=2e-6)
+    if not lam:
+        assert np.all(got[np.setdiff1d(np.arange(F), touched)] == 0)
+
+
+def test_host_nmf_gradients_match_autograd():
+    """nmf_gradients == d/d(L, R) [ sum_nnz (L_i . R_j - D_ij)^2 + lam (|L|^2 + |R|^2) ] by torch autograd."""
+    import torch
+    from harmony_b200.mlapps.nmf import nmf_gradients
+    rng = np.random.default_rng(1)
+    n, U, rank, lam = 7, 5, 4, 0.03
+    ptr = np.array([0, 2, 2, 5, 6, 9, 11, 12])
+    slot = rng.integers(0, U, 12)
+    vals = rng.random(12)
+    L0, R0 = rng.random((n, rank)), rng.random((U, rank))
+    gL, gR, loss = nmf_gradients(L0.copy(), R0.copy(), ptr, slot, vals, lam)
+    L = torch.tensor(L0, requires_grad=True); R = torch.tensor(R0, requires_grad=True)
+    rows = torch.tensor(np.repeat(np.arange(n), np.diff(ptr)))
+    e = (L[rows] * R[torch.tensor(slot)]).sum(1) - torch.tensor(vals)
+    obj = (e * e).sum() + lam * ((L * L).sum() + (R * R).sum())
+    obj.backward()
+    np.testing.assert_allclose(gL, L.grad.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(gR, R.grad.numpy(), rtol=1e-5, atol=1e-6)
+    assert abs(loss - float((e * e).sum())) < 1e-9
