@@ -192,3 +192,19 @@ def test_host_nmf_gradients_match_autograd():
     np.testing.assert_allclose(gL, L.grad.numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(gR, R.grad.numpy(), rtol=1e-5, atol=1e-6)
     assert abs(loss - float((e * e).sum())) < 1e-9
+
+
+def test_nmf_print_mat_stores_the_local_model_through_the_datastorer(tmp_path):
+    """-print_mat true: every worker writes its rows of L (keyed by the matrix row id) under -base_dir."""
+    import glob
+    data = write_nmf_sample(str(tmp_path / "n"), rows=40, cols=20, rank=3)
+    res = ETDolphinLauncher.launch(nmf.APP, ["-input", data, "-max_num_epochs", "2", "-num_mini_batches", "2",
+                                             "-num_worker_blocks", "2", "-num_server_blocks", "4", "-step_size", "0.01",
+                                             "-rank", "3", "-features", "20", "-num_dolphin_workers", "2",
+                                             "-num_servers", "1", "-print_mat", "true", "-base_dir", str(tmp_path / "o")])
+    assert res.ok
+    files = sorted(glob.glob(str(tmp_path / "o" / "nmf" / "*" / "L-*.txt")))
+    assert len(files) == 2
+    rows = sorted(int(line.split(":")[0]) for f in files for line in open(f))
+    assert rows == list(range(1, 41))
+    assert all(len(line.split(":")[1].split()) == 3 for f in files for line in open(f))
