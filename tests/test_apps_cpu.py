@@ -208,3 +208,22 @@ def test_nmf_print_mat_stores_the_local_model_through_the_datastorer(tmp_path):
     rows = sorted(int(line.split(":")[0]) for f in files for line in open(f))
     assert rows == list(range(1, 41))
     assert all(len(line.split(":")[1].split()) == 3 for f in files for line in open(f))
+
+
+def test_directory_input_with_part_files(tmp_path):
+    """-input may be a directory of part files (the HDFS output layout): hidden / underscore files are skipped and the
+    records of every part are loaded exactly once."""
+    from harmony_b200.common.samples import write_mlr_sample
+    d = tmp_path / "parts"
+    d.mkdir()
+    for i in range(3):
+        write_mlr_sample(str(d / f"part-0000{i}"), n=40, features=64, classes=4, seed=i)
+    (d / "_SUCCESS").write_text("")
+    (d / ".part-00000.crc").write_text("garbage that must not be parsed")
+    from harmony_b200.mlapps import mlr
+    res = ETDolphinLauncher.launch(mlr.APP, ["-input", str(d), "-max_num_epochs", "1", "-num_mini_batches", "6",
+                                             "-num_worker_blocks", "6", "-num_server_blocks", "4", "-step_size", "0.05",
+                                             "-classes", "4", "-features", "64", "-num_dolphin_workers", "2",
+                                             "-num_servers", "1"])
+    assert res.ok, res.messages
+    assert sum(r["num_batches"] for r in res.results) == 6
