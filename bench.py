@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--distinct_batches", type=int, default=4)
     ap.add_argument("--zipf", type=float, default=0.0)
     ap.add_argument("--no_e2e", action="store_true")
+    ap.add_argument("--ship_phases", action="store_true",
+                    help="ship mode: also time the five parts of a step (partial fwd / barrier / softmax+bcast / "
+                         "barrier / update) with CUDA events, outside the headline region")
     ap.add_argument("--mode", default="auto", choices=["auto", "pull", "ship"],
                     help="pull: workers read/reduce model rows over NVLink (PS pull/push); "
                          "ship: owners compute the sparse dot, only [B,C] activations cross NVLink; "
@@ -293,6 +296,14 @@ def main():
             torch.cuda.synchronize(dev)
             t_pull += evs[0].elapsed_time(evs[1]); t_push += evs[1].elapsed_time(evs[2])
         phase = {"pull_fwd_ms": max_over_ranks(t_pull / reps), "bwd_push_ms": max_over_ranks(t_push / reps)}
+    elif args.impl == "harmony" and mode == "ship" and args.ship_phases:
+        reps = min(args.steps, 10)
+        acc = {}
+        for i in range(reps):
+            barrier_sync()
+            for k, v in ship.step_timed(dev_batches[i % len(dev_batches)]).items():
+                acc[k] = acc.get(k, 0.0) + v
+        phase = {k: max_over_ranks(v / reps) for k, v in sorted(acc.items())}
 
     # ---------------- end-to-end: pinned host -> H2D every step, loss D2H every step ----------------
     e2e = None
@@ -366,7 +377,8 @@ def main():
                                    % ((nnz + uniq) * row_bytes / 1e9),
                        "sgd": "step_size %.1e, decay_rate 0.9 / decay_period 5 epochs (applied per epoch)" % args.step_size},
             "clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(loss_dev, 5),
-            "phases": None if phase is None else {
+            "phases": None if phase is None else {k: round(v, 4) for k, v in phase.items()}
+            if "pull_fwd_ms" not in phase else {
                 "pull_fwd_ms": round(phase["pull_fwd_ms"], 4), "bwd_push_ms": round(phase["bwd_push_ms"], 4),
                 "pull_GBps_per_gpu": round(nnz * row_bytes / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
                 "push_GBps_per_gpu": round(uniq * row_bytes / (phase["bwd_push_ms"] / 1e3) / 1e9, 1),

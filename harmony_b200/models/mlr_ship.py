@@ -123,5 +123,29 @@ class MLRShipModel:
                                   r.xval, self.D, False)     # red.add beats a load-add-store RMW here (521 us vs 818 us measured)
         count_launch()
 
+    def step_timed(self, rb: RoutedBatch) -> dict:
+        """`step()` with CUDA events around its five parts (bench.py --ship_phases; every rank must call it, the two
+        barriers are collective).  Returns milliseconds per part; the caller synchronises before reading them."""
+        bp, rpb, stride, _dim, mode = self.table.view()
+        r = rb.routed
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        self._n.mlr_partial_forward(bp, rpb, stride, self.num_classes, mode, r.csr_ptr, r.csr_col, r.csr_val,
+                                    self.B, self.logit_ptrs)
+        ev[1].record()
+        self.clock.barrier()
+        ev[2].record()
+        self._n.mlr_softmax_bcast(self.L, rb.labels, self.num_classes, self.step_size, self.d_ptrs, self.rank,
+                                  self.stats)
+        ev[3].record()
+        self.clock.barrier()
+        ev[4].record()
+        self._n.mlr_backward_push(bp, rpb, stride, self.num_classes, mode, r.uniq_feat, r.feat_ptr, r.samp,
+                                  r.xval, self.D, False)
+        ev[5].record()
+        torch.cuda.synchronize(self.device)
+        names = ("partial_fwd_ms", "barrier1_ms", "softmax_bcast_ms", "barrier2_ms", "bwd_update_ms")
+        return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+
     def decay_step(self, rate: float) -> None:
         self.step_size *= rate
