@@ -43,32 +43,62 @@ class TimeMetricTracker(MetricTracker):
 
 
 class MemoryMetricTracker(MetricTracker):
-    """Samples host RSS and device memory every `period_s`; reports max and mean."""
+    """Samples host RSS and device memory every `period_s`; reports max and mean of the bracketed window.  One
+    sampler thread serves every start / stop window of the tracker (an epoch of a fast job is shorter than the
+    thread start + join it used to cost); it retires by itself after a few idle periods."""
+
+    IDLE_PERIODS = 4
 
     def __init__(self, period_s: float = 0.1) -> None:
         self.period_s = period_s
         self._samples: List[tuple] = []
-        self._stop = threading.Event()
+        self._lock = threading.Lock()
+        self._active = False
+        self._closed = threading.Event()
         self._thread: Optional[threading.Thread] = None
+        self._last: Optional[tuple] = None
+
+    def _run(self) -> None:
+        idle = 0
+        while not self._closed.wait(self.period_s):
+            with self._lock:
+                if not self._active:
+                    idle += 1
+                    if idle >= self.IDLE_PERIODS:
+                        self._thread = None
+                        return
+                    continue
+                idle = 0
+            sample = (used_memory_mb(), device_memory_mb())
+            with self._lock:
+                if self._active:
+                    self._samples.append(sample)
 
     def start(self) -> None:
-        self._samples.clear()
-        self._stop.clear()
-
-        def run():
-            while not self._stop.wait(self.period_s):
-                self._samples.append((used_memory_mb(), device_memory_mb()))
-        self._thread = threading.Thread(target=run, daemon=True)
-        self._thread.start()
+        with self._lock:
+            self._samples = []
+            self._active = True
+            if self._thread is None and not self._closed.is_set():
+                self._thread = threading.Thread(target=self._run, daemon=True, name="memory-metric")
+                self._thread.start()
 
     def stop(self) -> Dict[str, float]:
-        self._stop.set()
-        if self._thread is not None:
-            self._thread.join(timeout=2)
-        s = self._samples or [(used_memory_mb(), device_memory_mb())]
+        with self._lock:
+            self._active = False
+            s, self._samples = self._samples, []
+        if not s:
+            # window shorter than the sampling period: one sample now, reused by windows that close within a period
+            now = time.perf_counter()
+            if self._last is None or now - self._last[0] >= self.period_s:
+                self._last = (now, (used_memory_mb(), device_memory_mb()))
+            s = [self._last[1]]
         host, dev = [a for a, _ in s], [b for _, b in s]
         return {"METRIC_MEMORY_MAX_MB": max(host), "METRIC_MEMORY_AVG_MB": sum(host) / len(host),
                 "METRIC_DEVICE_MEMORY_MAX_MB": max(dev), "METRIC_DEVICE_MEMORY_AVG_MB": sum(dev) / len(dev)}
+
+    def close(self) -> None:
+        """Retire the sampler thread now (it would also retire by itself)."""
+        self._closed.set()
 
 
 class DeviceTimeMetricTracker(MetricTracker):

@@ -35,20 +35,23 @@ class MasterSideMsgSender:
     def __init__(self, task_runner: "ETTaskRunner") -> None:
         self._runner = task_runner
 
-    def _send(self, worker_id: str, body: Dict[str, Any]) -> None:
+    def _send(self, worker_id: str, body: Dict[str, Any], inline: bool = False) -> None:
         rt = self._runner.get_worker_tasklet(worker_id)
         if rt is None:
             # a worker started by a plan op talks to the master before the optimizer has handed its tasklet over:
             # keep the message until the tasklet is registered
             self._runner.defer(worker_id, body)
             return
-        rt.send(body)
+        if inline:
+            rt.send(body, inline=True)           # barrier releases: handled on the executor's inbox thread
+        else:
+            rt.send(body)
 
     def send_release_msg(self, worker_id: str) -> None:
-        self._send(worker_id, {"type": "ReleaseMsg"})
+        self._send(worker_id, {"type": "ReleaseMsg"}, inline=True)
 
     def send_mini_batch_control_msg(self, worker_id: str, stop: bool) -> None:
-        self._send(worker_id, {"type": "MiniBatchControlMsg", "stop": stop})
+        self._send(worker_id, {"type": "MiniBatchControlMsg", "stop": stop}, inline=True)
 
     def send_model_eval_ans_msg(self, worker_id: str, do_next: bool) -> None:
         self._send(worker_id, {"type": "ModelEvalAnsMsg", "do_next": do_next})

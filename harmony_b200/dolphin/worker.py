@@ -217,11 +217,16 @@ class WorkerSideMsgSender:
         self.job_id = job_id
         self.worker_id = context.executor.executor_id
 
-    def _send(self, body: Dict[str, Any]) -> None:
-        self._ctx.send_to_driver({"job_id": self.job_id, "dolphin": body})
+    def _send(self, body: Dict[str, Any], inline: bool = False) -> None:
+        payload = {"job_id": self.job_id, "dolphin": body}
+        if inline:
+            # per-mini-batch traffic whose master-side handling never blocks (SSP bookkeeping + a reply)
+            self._ctx.send_to_driver(payload, inline=True)
+        else:
+            self._ctx.send_to_driver(payload)
 
     def send_progress_msg(self, progress: int) -> None:
-        self._send({"type": "ProgressMsg", "executor_id": self.worker_id, "progress": progress})
+        self._send({"type": "ProgressMsg", "executor_id": self.worker_id, "progress": progress}, inline=True)
 
     def send_sync_msg(self, state: str) -> None:
         self._send({"type": "SyncMsg", "executor_id": self.worker_id, "state": state})
@@ -234,10 +239,10 @@ class WorkerSideMsgSender:
             body["progress"] = progress
         if idle:
             body["idle"] = True
-        self._send(body)
+        self._send(body, inline=True)
 
     def send_mini_batch_return_msg(self) -> None:
-        self._send({"type": "MiniBatchReturnMsg", "worker_id": self.worker_id})
+        self._send({"type": "MiniBatchReturnMsg", "worker_id": self.worker_id}, inline=True)
 
     def send_model_eval_ask_msg(self) -> None:
         self._send({"type": "ModelEvalAskMsg", "executor_id": self.worker_id})
@@ -460,6 +465,7 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.add_custom_metric(em.to_dict())
             self.context.metric_collector.flush()
             epoch += 1
+        mem.close()
         if pending_progress is not None:                   # stopped between a batch and its next sync
             self.sender.send_progress_msg(pending_progress)
         if self.use_task_units and not idle_left:

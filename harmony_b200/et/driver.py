@@ -609,8 +609,13 @@ class RunningTasklet:
     def stop(self) -> None:
         self._m.send(self.executor_id, {"type": "TaskletStop", "tasklet_id": self.tasklet_id})
 
-    def send(self, payload: Any) -> None:
-        self._m.send(self.executor_id, {"type": "TaskletCustom", "tasklet_id": self.tasklet_id, "payload": payload})
+    def send(self, payload: Any, inline: bool = False) -> None:
+        """`inline`: the tasklet's handler for this payload never blocks (a barrier release): the executor runs it on
+        its inbox thread instead of handing it to the handler pool -- one thread hop less per mini-batch."""
+        m = {"type": "TaskletCustom", "tasklet_id": self.tasklet_id, "payload": payload}
+        if inline:
+            m["inline"] = True
+        self._m.send(self.executor_id, m)
 
     def get_task_result(self, timeout: Optional[float] = None) -> TaskletResult:
         return self._result.get(timeout)
@@ -1121,10 +1126,18 @@ class ETMaster:
         elif t == "TaskletCustom":
             with self._lock:
                 rt = self._tasklets.get((m["executor_id"], m["tasklet_id"]))
+            # `inline` = the sender vouches that the handler never blocks (per-mini-batch sync / progress): run it
+            # here, on the inbox thread, and save the pool hop (the inbox loop logs a failing handler)
             if rt is not None and rt.custom_handler is not None:
-                self.pool.submit(rt.custom_handler, m["payload"])
+                if m.get("inline"):
+                    rt.custom_handler(m["payload"])
+                else:
+                    self.pool.submit(rt.custom_handler, m["payload"])
             elif "TaskletCustom" in self.custom_handlers:
-                self.pool.submit(self.custom_handlers["TaskletCustom"], m)
+                if m.get("inline"):
+                    self.custom_handlers["TaskletCustom"](m)
+                else:
+                    self.pool.submit(self.custom_handlers["TaskletCustom"], m)
         elif t == "MetricReport":
             self.pool.submit(self.metrics.on_report, m)
         elif t == "ExecutorRegister":

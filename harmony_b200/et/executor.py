@@ -86,6 +86,8 @@ class Executor:
             self.sender.on_table_access_res_batch(m)
         elif t == "TaskUnitReady":
             self.task_unit_scheduler.on_ready(m)
+        elif t == "TaskletCustom" and m.get("inline"):
+            self._on_TaskletCustom(m)            # non-blocking by the sender's contract (barrier releases)
         else:
             fn = getattr(self, "_on_" + t, None)
             if fn is None:

@@ -65,10 +65,14 @@ class TaskletContext:
         self.task_units = executor.task_unit_scheduler
         self.metric_collector = executor.metric_collector
 
-    def send_to_driver(self, payload: Any) -> None:
-        """TaskletCustomMsgSender.send (evaluator/impl/TaskletCustomMsgSender.java:53-70)."""
-        self.executor.send_to_driver({"type": "TaskletCustom", "tasklet_id": self.tasklet_id,
-                                      "executor_id": self.executor.executor_id, "payload": payload})
+    def send_to_driver(self, payload: Any, inline: bool = False) -> None:
+        """TaskletCustomMsgSender.send (evaluator/impl/TaskletCustomMsgSender.java:53-70).  `inline`: the driver-side
+        handler of this payload never blocks, the driver may run it on its inbox thread."""
+        m = {"type": "TaskletCustom", "tasklet_id": self.tasklet_id, "executor_id": self.executor.executor_id,
+             "payload": payload}
+        if inline:
+            m["inline"] = True
+        self.executor.send_to_driver(m)
 
 
 def load_class(path: str):

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import os
+import sys
 import socket
 from dataclasses import dataclass
 from typing import Generic, List, Sequence, Tuple, TypeVar
@@ -35,18 +36,27 @@ def get_num_units(ranges: Sequence[Tuple[int, int]]) -> int:
     return sum(hi - lo + 1 for lo, hi in ranges)
 
 
+_PROC = None
+
+
 def used_memory_mb() -> float:
+    """Resident set size of this process (the psutil handle is cached: building one reads /proc/<pid>/stat)."""
+    global _PROC
     try:
-        import psutil
-        return psutil.Process(os.getpid()).memory_info().rss / (1 << 20)
+        if _PROC is None or _PROC.pid != os.getpid():
+            import psutil
+            _PROC = psutil.Process(os.getpid())
+        return _PROC.memory_info().rss / (1 << 20)
     except Exception:  # noqa: BLE001
         return 0.0
 
 
 def device_memory_mb() -> float:
+    """HBM allocated through torch in this process; 0 when torch was never loaded (a host-backend executor must not
+    pay the torch import -- and the import lock -- for a memory sample)."""
+    torch = sys.modules.get("torch")
     try:
-        import torch
-        if torch.cuda.is_available():
+        if torch is not None and torch.cuda.is_available():
             return torch.cuda.memory_allocated() / (1 << 20)
     except Exception:  # noqa: BLE001
         pass

@@ -269,3 +269,31 @@ def test_split_reader_fuzz_every_line_in_exactly_one_split(tmp_path):
             by_bytes = by_bytes[:-1]
         assert by_lines == want, (case, k)
         assert by_bytes == want, (case, k)
+
+
+def test_memory_metric_tracker_windows_share_one_sampler_thread():
+    """Short windows (shorter than the period) still report a sample; longer ones collect several; the sampler thread is
+    reused across windows and retires by itself."""
+    import threading
+    import time
+    from harmony_b200.common.metric import MemoryMetricTracker
+    t = MemoryMetricTracker(0.01)
+    t.start()
+    out = t.stop()                                   # empty window: falls back to one sample
+    assert out["METRIC_MEMORY_MAX_MB"] > 0 and out["METRIC_MEMORY_AVG_MB"] <= out["METRIC_MEMORY_MAX_MB"]
+    first = t._thread
+    for _ in range(3):
+        t.start()
+        time.sleep(0.05)
+        assert t._thread is first                    # no thread churn per window
+        out = t.stop()
+        assert out["METRIC_MEMORY_MAX_MB"] > 0
+    deadline = time.time() + 2
+    while t._thread is not None and time.time() < deadline:
+        time.sleep(0.01)
+    assert t._thread is None                         # idle for a few periods: retired
+    t.start()
+    assert t._thread is not None and t._thread is not first
+    t.stop()
+    t.close()
+    assert not any(th.name == "memory-metric" and th.is_alive() and th is first for th in threading.enumerate())
