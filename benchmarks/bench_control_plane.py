@@ -41,13 +41,17 @@ def main():
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--batches", type=int, default=50, help="mini-batches per worker per epoch")
     ap.add_argument("--profile", action="store_true")
-    ap.add_argument("--extra", nargs="*", default=[])
+    ap.add_argument("--jobserver", type=int, default=0, metavar="J",
+                    help="submit J concurrent copies of the job to one job server (task-unit co-scheduling on)")
+    ap.add_argument("--extra", default="", help="comma-separated extra job flags, e.g. --extra=-clock_slack,2")
     a = ap.parse_args()
     sys.modules.setdefault("bench_control_plane", sys.modules[__name__])
     data = examples.write_dummy_input(a.workers * a.batches * 2)
     argv = ["-input", data, "-max_num_epochs", str(a.epochs), "-num_mini_batches", str(a.batches),
-            "-num_dolphin_workers", str(a.workers), "-num_servers", "1", "-num_worker_blocks", str(a.workers * 4),
-            "-num_server_blocks", "4", "-num_keys", "4", "-backend", "host"] + ["-" + x for x in a.extra]
+            "-num_dolphin_workers", str(a.workers), "-num_servers", "1", "-num_worker_blocks", str(a.batches),
+            "-num_server_blocks", "4", "-num_keys", "4", "-backend", "host"] + [x for x in a.extra.split(",") if x]
+    if a.jobserver:
+        return run_jobserver(a, argv)
     prof = None
     if a.profile:
         import cProfile
@@ -68,6 +72,34 @@ def main():
     if prof:
         import pstats
         pstats.Stats(prof).sort_stats("cumulative").print_stats(25)
+
+
+def run_jobserver(a, argv):
+    import socket
+    from harmony_b200.dolphin.launcher import parse_job_conf
+    from harmony_b200.jobserver.client import CommandSender, JobServer
+    from harmony_b200.utils.flags import Configuration
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    sys.modules["bench_control_plane"].APP = APP
+    js = JobServer(Configuration({"num_executors": a.workers, "port": port})).start()
+    try:
+        conf = parse_job_conf(APP, argv + ["-port", str(port)]).with_values(
+            job_entity_builder="harmony_b200.dolphin.jobserver:DolphinJobEntityBuilder", app="bench_control_plane:APP")
+        t0 = time.perf_counter()
+        for _ in range(a.jobserver):
+            assert CommandSender(port).send_job_submit_command(conf.serialize()).startswith("true")
+        n = 0
+        for j in range(a.jobserver):
+            ok, result = js.driver.wait_job("NoOp-%d" % j, timeout=600)
+            assert ok, result
+            n += sum(r["num_batches"] for r in result)
+        dt = time.perf_counter() - t0
+    finally:
+        js.stop(kill=True)
+    print(json.dumps({"metric": "control_plane_mini_batches_per_sec", "value": round(n / dt, 1), "workers": a.workers,
+                      "jobs": a.jobserver, "mini_batches": n, "wall_s": round(dt, 3), "path": "job server"}))
 
 
 if __name__ == "__main__":
