@@ -41,6 +41,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=20)
     ap.add_argument("--batches", type=int, default=50, help="mini-batches per worker per epoch")
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--executor_mode", default="inproc", choices=["inproc", "process"],
+                    help="with --jobserver: executors as threads of the driver process or as one process each (TCP)")
     ap.add_argument("--jobserver", type=int, default=0, metavar="J",
                     help="submit J concurrent copies of the job to one job server (task-unit co-scheduling on)")
     ap.add_argument("--extra", default="", help="comma-separated extra job flags, e.g. --extra=-clock_slack,2")
@@ -83,7 +85,11 @@ def run_jobserver(a, argv):
         sk.bind(("127.0.0.1", 0))
         port = sk.getsockname()[1]
     sys.modules["bench_control_plane"].APP = APP
-    js = JobServer(Configuration({"num_executors": a.workers, "port": port})).start()
+    os.environ["PYTHONPATH"] = os.pathsep.join(
+        [os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+         os.environ.get("PYTHONPATH", "")])          # executor processes import the no-op trainer from this file
+    js = JobServer(Configuration({"num_executors": a.workers, "port": port, "executor_mode": a.executor_mode,
+                                  "backend": "host"})).start()
     try:
         conf = parse_job_conf(APP, argv + ["-port", str(port)]).with_values(
             job_entity_builder="harmony_b200.dolphin.jobserver:DolphinJobEntityBuilder", app="bench_control_plane:APP")
@@ -99,7 +105,7 @@ def run_jobserver(a, argv):
     finally:
         js.stop(kill=True)
     print(json.dumps({"metric": "control_plane_mini_batches_per_sec", "value": round(n / dt, 1), "workers": a.workers,
-                      "jobs": a.jobserver, "mini_batches": n, "wall_s": round(dt, 3), "path": "job server"}))
+                      "jobs": a.jobserver, "executor_mode": a.executor_mode, "mini_batches": n, "wall_s": round(dt, 3), "path": "job server"}))
 
 
 if __name__ == "__main__":

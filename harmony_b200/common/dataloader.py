@@ -243,18 +243,26 @@ def make_parser(spec: Any) -> DataParser:
         return spec
     if spec is None:
         return DefaultDataParser()
-    if isinstance(spec, str):
+    name, params = (spec, {}) if isinstance(spec, str) else (spec["name"], spec.get("params", {}))
+    if name not in _PARSERS:
         _ensure_app_parsers()
-        return _PARSERS[spec]()
-    _ensure_app_parsers()
-    return _PARSERS[spec["name"]](**spec.get("params", {}))
+    if name not in _PARSERS and ":" in name:
+        # "package.module:ParserClass" -- a user parser that an executor PROCESS has not imported yet
+        import importlib
+        mod, _, cls = name.partition(":")
+        return getattr(importlib.import_module(mod), cls)(**params)
+    if name not in _PARSERS:
+        raise KeyError(f"unknown data parser {name!r} (registered: {sorted(_PARSERS)}); user parsers are named "
+                       f"'module:Class' or registered with register_parser() in a module the executors import")
+    return _PARSERS[name](**params)
 
 
 def _ensure_app_parsers() -> None:
     # app parsers register themselves on import
     import importlib
     for mod in ("harmony_b200.mlapps.mlr", "harmony_b200.mlapps.nmf", "harmony_b200.mlapps.lda",
-                "harmony_b200.mlapps.lasso", "harmony_b200.mlapps.gbt", "harmony_b200.pregel.graph"):
+                "harmony_b200.mlapps.lasso", "harmony_b200.mlapps.gbt", "harmony_b200.mlapps.examples",
+                "harmony_b200.pregel.graph"):
         try:
             importlib.import_module(mod)
         except ImportError:

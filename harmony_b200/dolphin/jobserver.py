@@ -134,6 +134,13 @@ class DolphinJobEntity(JobEntity):
                   "data_parser": self.worker_tc.data_parser, "app_id": self.app.app_id,
                   "num_job_workers": max(1, len(self.executors)),
                   "job_executor_ids": [e.id for e in self.executors]})
+        # the task-unit barriers exist to interleave the phases of jobs that SHARE executors: a scheduler that gives
+        # each job the pool for itself makes them pure overhead (one driver round trip per phase per mini-batch)
+        mode = str(self.conf.get("task_unit_scheduling", "auto")).lower()
+        if mode not in ("auto", "on", "off"):
+            raise ValueError(f"-task_unit_scheduling must be auto, on or off (got {mode!r})")
+        exclusive = bool(getattr(getattr(self.driver, "scheduler", None), "exclusive", False))
+        p["task_units_enabled"] = mode == "on" or (mode == "auto" and not exclusive)
         return p
 
     def setup_executors_and_tables(self, executors: Sequence[AllocatedExecutor]) -> None:

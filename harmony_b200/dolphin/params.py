@@ -53,6 +53,9 @@ DOLPHIN = [
     P("test_data_path", str, "", "", "worker"), P("input_chkp_path", str, "", "", "worker"),
     P("model_cache_enabled", bool, False, "", "worker"),
     P("job_priority", str, "normal", "normal | high: CUDA stream priority of the job's tasklets on shared GPUs", "worker"),
+    P("task_unit_scheduling", str, "auto", "on | off | auto: per-phase global barriers that interleave the phases of "
+                                           "co-located jobs (one driver round trip per phase); auto = on unless the "
+                                           "job server's scheduler runs jobs exclusively", "worker"),
     P("batch_metric_flush_interval_ms", int, 50, "batch metrics are flushed to the driver at most this often "
                                                  "(0 = after every mini-batch, as the reference)", "worker"),
     P("num_dolphin_workers", int, 1, "", "launcher"), P("num_servers", int, 1, "0 = co-located", "launcher"),

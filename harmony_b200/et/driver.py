@@ -520,6 +520,7 @@ class GlobalTaskUnitScheduler:
         self._job_size: Dict[str, int] = {}
         self._waiting: Dict[Tuple[str, str, int], List[Tuple[str, str]]] = {}
         self._lock = threading.Lock()
+        self.num_waits = 0                 # TaskUnitWait messages served (one driver round trip each)
 
     def on_job_start(self, job_id: str, num_executors: int) -> None:
         with self._lock:
@@ -552,6 +553,7 @@ class GlobalTaskUnitScheduler:
     def on_wait(self, m: Dict[str, Any]) -> None:
         key = (m["job_id"], m["unit_name"], m["seq"])
         with self._lock:
+            self.num_waits += 1
             n = self._job_size.get(m["job_id"], 1)
             lst = self._waiting.setdefault(key, [])
             lst.append((m["executor_id"], m["tasklet_id"]))

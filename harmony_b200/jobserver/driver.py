@@ -74,6 +74,8 @@ class JobEntity:
 class JobScheduler:
     """Pluggable global scheduling policy."""
 
+    exclusive = False      # True: a running job never shares executors with another one
+
     def bind(self, driver: "JobServerDriver") -> None:
         self.driver = driver
 
@@ -100,6 +102,8 @@ class SchedulerImpl(JobScheduler):
 
 class FifoExclusiveScheduler(JobScheduler):
     """One job at a time on the whole pool; later arrivals queue."""
+
+    exclusive = True
 
     def __init__(self) -> None:
         self._queue: List[JobEntity] = []

@@ -326,3 +326,22 @@ def test_minibatch_controller_random_schedules_keep_the_ssp_invariants(slack):
                 assert max(prog.values()) - min(prog.values()) <= slack + 1, prog
             assert c.num_mini_batches_done <= total_epochs * nmb + len(workers)
         assert sum(granted.values()) <= total_epochs * nmb
+
+
+@pytest.mark.parametrize("scheduler,extra,expect_units", [
+    ("SchedulerImpl", [], True),                                  # jobs share executors: phases are co-scheduled
+    ("FifoExclusiveScheduler", [], False),                        # a job has the pool for itself: no barrier round trips
+    ("SchedulerImpl", ["-task_unit_scheduling", "off"], False),
+    ("FifoExclusiveScheduler", ["-task_unit_scheduling", "on"], True)])
+def test_task_unit_scheduling_follows_the_scheduler_unless_overridden(scheduler, extra, expect_units):
+    tmp = tempfile.mkdtemp(prefix="hbunits")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=80)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port, "scheduler": scheduler})).start()
+    try:
+        assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(data, port, ["-max_num_epochs", "1"] + extra),
+                                             port=port).startswith("true")
+        assert js.driver.wait_job("MLR-0", timeout=120)[0]
+        assert (js.et_master.task_units.num_waits > 0) == expect_units
+    finally:
+        js.stop(kill=True)

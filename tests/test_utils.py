@@ -297,3 +297,25 @@ def test_memory_metric_tracker_windows_share_one_sampler_thread():
     t.stop()
     t.close()
     assert not any(th.name == "memory-metric" and th.is_alive() and th is first for th in threading.enumerate())
+
+
+def test_parsers_resolve_in_a_fresh_executor_process():
+    """An executor PROCESS has imported no app module when its first TableLoad arrives: every built-in parser name and
+    a 'module:Class' user parser must resolve there; an unknown name says what is registered."""
+    import subprocess
+    import sys
+    code = ("from harmony_b200.common.dataloader import make_parser\n"
+            "for n in ('example', 'mlr', 'nmf', 'lda', 'lasso', 'gbt', 'graph'):\n"
+            "    make_parser(n)\n"
+            "p = make_parser('harmony_b200.mlapps.examples:ExampleDataParser')\n"
+            "assert type(p).__name__ == 'ExampleDataParser'\n"
+            "try:\n"
+            "    make_parser('nope')\n"
+            "except KeyError as e:\n"
+            "    assert 'registered' in str(e)\n"
+            "else:\n"
+            "    raise SystemExit('unknown parser accepted')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=root), capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
