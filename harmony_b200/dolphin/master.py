@@ -50,8 +50,11 @@ class MasterSideMsgSender:
     def send_release_msg(self, worker_id: str) -> None:
         self._send(worker_id, {"type": "ReleaseMsg"}, inline=True)
 
-    def send_mini_batch_control_msg(self, worker_id: str, stop: bool) -> None:
-        self._send(worker_id, {"type": "MiniBatchControlMsg", "stop": stop}, inline=True)
+    def send_mini_batch_control_msg(self, worker_id: str, stop: bool, granted: int = 1) -> None:
+        body = {"type": "MiniBatchControlMsg", "stop": stop}
+        if granted != 1:
+            body["granted"] = granted            # a lease: the worker runs this many mini-batches before its next sync
+        self._send(worker_id, body, inline=True)
 
     def send_model_eval_ans_msg(self, worker_id: str, do_next: bool) -> None:
         self._send(worker_id, {"type": "ModelEvalAnsMsg", "do_next": do_next})
@@ -170,7 +173,11 @@ class WorkerStateManager:
 
 class MiniBatchController:
     """SSP clock: a worker is blocked while its progress > min progress + slack; everyone is told
-    to stop when the GLOBAL budget epochs x num_mini_batches is used up."""
+    to stop when the GLOBAL budget epochs x num_mini_batches is used up.
+
+    A sync may ask for a lease of `want` mini-batches (-mini_batch_grant_size): the grant is counted against the budget
+    and the clock at once, tapers to single batches as the budget runs out (so the last batches still spread over the
+    workers), and the SSP check applies to the FIRST batch of the lease -- the staleness bound widens by want - 1."""
 
     def __init__(self, num_epochs: int, num_mini_batches_in_epoch: int, slack: int,
                  sender: MasterSideMsgSender) -> None:
@@ -183,6 +190,23 @@ class MiniBatchController:
         self._min = 0
         self._closed = False
         self._lock = threading.Lock()
+        self._grant: Dict[str, int] = {}          # size of each worker's latest grant
+
+    def _reply(self, worker_id: str, stop: bool) -> None:
+        g = self._grant.get(worker_id, 1)
+        if g == 1 or stop:
+            self._sender.send_mini_batch_control_msg(worker_id, stop)
+        else:
+            self._sender.send_mini_batch_control_msg(worker_id, stop, g)
+
+    def _release_blocked(self, everyone: bool = False) -> None:
+        """Release the blocked requests whose first mini-batch is within the SSP bound again (with single-batch grants
+        that is all of them whenever the clock advances); `everyone`: the budget is used up."""
+        for w in list(self._blocked):
+            start = self._progress.get(w, 0) - self._grant.get(w, 1) + 1
+            if everyone or start <= self._min + self.slack:
+                self._blocked.discard(w)
+                self._reply(w, False)
 
     def on_idle_sync(self, worker_id: str) -> None:
         """A worker that currently holds no input data (all its blocks migrated away) asks whether to stop: it
@@ -194,43 +218,46 @@ class MiniBatchController:
                 new_min = min(self._progress.values())
                 if new_min > self._min:
                     self._min = new_min
-                    for w in self._blocked:
-                        self._sender.send_mini_batch_control_msg(w, False)
-                    self._blocked.clear()
+                    self._release_blocked()
             self._sender.send_mini_batch_control_msg(worker_id, self._closed)
 
-    def on_sync(self, worker_id: str) -> None:
+    def on_sync(self, worker_id: str, want: int = 1) -> None:
         with self._lock:
             if self._closed:
                 self._sender.send_mini_batch_control_msg(worker_id, True)
                 return
-            self._count += 1
+            g = 1
+            if want > 1:
+                # taper: never lease more than half of an even share of what is left
+                share = (self.total - self._count) // (2 * max(1, len(self._progress)))
+                g = max(1, min(want, share))
+            self._grant[worker_id] = g
+            self._count += g
             # a worker that joins mid-run (added by a plan, or back from idling) starts level with the slowest
-            # worker instead of at 0 (which would stall everybody else until it has caught up alone)
-            prog = self._progress.get(worker_id, max(self._min - 1, 0)) + 1
+            # worker (its grant ends where the slowest one's ends) instead of at 0, which would stall everybody else
+            # until it has caught up alone
+            prog = self._progress.get(worker_id, max(self._min - g, 0)) + g
             self._progress[worker_id] = prog
             new_min = min(self._progress.values())
             if new_min > self._min:
                 self._min = new_min
-                for w in self._blocked:
-                    self._sender.send_mini_batch_control_msg(w, False)
-                self._blocked.clear()
+                self._release_blocked()
             if self._count + 1 > self.total:
-                self._closed = True     # let everyone run their last mini-batch, then stop
-                self._sender.send_mini_batch_control_msg(worker_id, False)
-                for w in self._blocked:
-                    self._sender.send_mini_batch_control_msg(w, False)
-                self._blocked.clear()
-            elif prog > self._min + self.slack:
+                self._closed = True     # let everyone run their last mini-batch(es), then stop
+                self._reply(worker_id, False)
+                self._release_blocked(everyone=True)
+            elif prog - g + 1 > self._min + self.slack:
                 self._blocked.add(worker_id)
             else:
-                self._sender.send_mini_batch_control_msg(worker_id, False)
+                self._reply(worker_id, False)
 
-    def on_return(self, worker_id: str) -> None:
-        """A stopped worker hands back a mini-batch it was granted but did not run."""
+    def on_return(self, worker_id: str, count: Optional[int] = None) -> None:
+        """A stopped worker hands back mini-batches it was granted but did not run (`count` None: its whole latest
+        grant -- it was stopped while waiting for the reply and never saw the size)."""
         with self._lock:
-            if not self._closed and self._count > 0:
-                self._count -= 1
+            n = self._grant.get(worker_id, 1) if count is None else count
+            if not self._closed and n > 0:
+                self._count = max(0, self._count - n)
 
     def on_worker_deleted(self, worker_id: str) -> None:
         with self._lock:
@@ -240,9 +267,7 @@ class MiniBatchController:
                 new_min = min(self._progress.values())
                 if new_min > self._min:
                     self._min = new_min
-                    for w in self._blocked:
-                        self._sender.send_mini_batch_control_msg(w, False)
-                    self._blocked.clear()
+                    self._release_blocked()
 
     @property
     def num_mini_batches_done(self) -> int:
@@ -264,16 +289,19 @@ class BatchProgressTracker:
         self._per_worker: Dict[str, int] = {}
         self._lock = threading.Lock()
 
-    def on_progress_msg(self, worker_id: str, progress: int) -> None:
+    def on_progress_msg(self, worker_id: str, progress: int, count: int = 1) -> None:
+        """`count` > 1: one report for the mini-batches of a lease (`progress` is the index of the last one)."""
         with self._lock:
             self._per_worker[worker_id] = progress
-            self._count += 1
-            c = self._count
-        if c % self.per_epoch == 0 and c <= self.total:
-            e = c // self.per_epoch
-            self._report(f"Epoch progress: [{e} / {self.num_epochs}], JobId: {self.job_id}")
-            if self._on_epoch is not None:
-                self._on_epoch(e - 1)
+            first = self._count + 1
+            self._count += max(1, count)
+            last = self._count
+        for c in range(first, last + 1):
+            if c % self.per_epoch == 0 and c <= self.total:
+                e = c // self.per_epoch
+                self._report(f"Epoch progress: [{e} / {self.num_epochs}], JobId: {self.job_id}")
+                if self._on_epoch is not None:
+                    self._on_epoch(e - 1)
 
     def get_progress(self) -> float:
         with self._lock:
@@ -493,16 +521,22 @@ class DolphinMaster:
         if t == "SyncMsg":
             self.state_manager.on_sync_msg(body["executor_id"], body["state"])
         elif t == "MiniBatchSyncMsg":
-            if body.get("progress") is not None:           # piggybacked ProgressMsg of the previous mini-batch
-                self.progress_tracker.on_progress_msg(body["worker_id"], body["progress"])
+            if body.get("progress") is not None:           # piggybacked ProgressMsg of the previous mini-batch(es)
+                self.progress_tracker.on_progress_msg(body["worker_id"], body["progress"],
+                                                      int(body.get("progress_count", 1)))
             if body.get("idle"):
                 self.mini_batch_controller.on_idle_sync(body["worker_id"])
+            elif int(body.get("want", 1)) > 1:
+                self.mini_batch_controller.on_sync(body["worker_id"], int(body["want"]))
             else:
                 self.mini_batch_controller.on_sync(body["worker_id"])
         elif t == "MiniBatchReturnMsg":
-            self.mini_batch_controller.on_return(body["worker_id"])
+            if "count" in body:
+                self.mini_batch_controller.on_return(body["worker_id"], int(body["count"]))
+            else:
+                self.mini_batch_controller.on_return(body["worker_id"])
         elif t == "ProgressMsg":
-            self.progress_tracker.on_progress_msg(body["executor_id"], body["progress"])
+            self.progress_tracker.on_progress_msg(body["executor_id"], body["progress"], int(body.get("count", 1)))
         elif t == "ModelEvalAskMsg":
             self._on_model_eval_ask(body["executor_id"])
         elif t == "GroupGather":

@@ -225,24 +225,36 @@ class WorkerSideMsgSender:
         else:
             self._ctx.send_to_driver(payload)
 
-    def send_progress_msg(self, progress: int) -> None:
-        self._send({"type": "ProgressMsg", "executor_id": self.worker_id, "progress": progress}, inline=True)
+    def send_progress_msg(self, progress: int, count: int = 1) -> None:
+        body = {"type": "ProgressMsg", "executor_id": self.worker_id, "progress": progress}
+        if count != 1:
+            body["count"] = count
+        self._send(body, inline=True)
 
     def send_sync_msg(self, state: str) -> None:
         self._send({"type": "SyncMsg", "executor_id": self.worker_id, "state": state})
 
-    def send_mini_batch_sync_msg(self, progress: Optional[int] = None, idle: bool = False) -> None:
-        """`progress` piggybacks the ProgressMsg of the mini-batch that just finished (one message less per batch);
-        `idle` = this worker has no data right now: ask for the stop flag without consuming the budget."""
+    def send_mini_batch_sync_msg(self, progress: Optional[int] = None, idle: bool = False, want: int = 1,
+                                 progress_count: int = 1) -> None:
+        """`progress` piggybacks the ProgressMsg of the mini-batch(es) finished since the last sync (one message less
+        per batch); `idle` = this worker has no data right now: ask for the stop flag without consuming the budget;
+        `want` > 1 asks for a lease of up to that many mini-batches (-mini_batch_grant_size)."""
         body = {"type": "MiniBatchSyncMsg", "worker_id": self.worker_id}
         if progress is not None:
             body["progress"] = progress
+            if progress_count != 1:
+                body["progress_count"] = progress_count
         if idle:
             body["idle"] = True
+        if want > 1:
+            body["want"] = want
         self._send(body, inline=True)
 
-    def send_mini_batch_return_msg(self) -> None:
-        self._send({"type": "MiniBatchReturnMsg", "worker_id": self.worker_id}, inline=True)
+    def send_mini_batch_return_msg(self, count: int = 1) -> None:
+        body = {"type": "MiniBatchReturnMsg", "worker_id": self.worker_id}
+        if count != 1:
+            body["count"] = count
+        self._send(body, inline=True)
 
     def send_model_eval_ask_msg(self) -> None:
         self._send({"type": "ModelEvalAskMsg", "executor_id": self.worker_id})
@@ -272,14 +284,20 @@ class MiniBatchBarrier:
         self._sender = sender
         self._ev = threading.Semaphore(0)
         self._stop = False
+        self.granted = 1                 # mini-batches covered by the last reply (a lease when > 1)
 
-    def await_(self, progress: Optional[int] = None, idle: bool = False) -> bool:
-        self._sender.send_mini_batch_sync_msg(progress, idle)
+    def await_(self, progress: Optional[int] = None, idle: bool = False, want: int = 1,
+               progress_count: int = 1) -> bool:
+        if want > 1 or progress_count != 1:
+            self._sender.send_mini_batch_sync_msg(progress, idle, want, progress_count)
+        else:
+            self._sender.send_mini_batch_sync_msg(progress, idle)
         self._ev.acquire()
         return self._stop
 
-    def on_control_msg(self, stop: bool) -> None:
+    def on_control_msg(self, stop: bool, granted: int = 1) -> None:
         self._stop = stop
+        self.granted = max(1, int(granted))
         self._ev.release()
 
 
@@ -351,7 +369,7 @@ class WorkerTasklet(Tasklet):
         if t == "ReleaseMsg":
             self.global_barrier.on_release_msg()
         elif t == "MiniBatchControlMsg":
-            self.mini_batch_barrier.on_control_msg(payload["stop"])
+            self.mini_batch_barrier.on_control_msg(payload["stop"], payload.get("granted", 1))
         elif t == "GroupGatherRes":
             grp = getattr(self.context, "job_group", None)
             if grp is not None:
@@ -390,6 +408,11 @@ class WorkerTasklet(Tasklet):
         # host RSS + HBM sampled every -memory_measure_interval ms; max / mean ride on the epoch metrics
         mem = MemoryMetricTracker(max(0.01, int(self.context.params.get("memory_measure_interval", 1000)) / 1000.0))
         pending_progress: Optional[int] = None
+        pending_n = 0              # mini-batches finished since the last sync (> 1 only inside a lease)
+        # -mini_batch_grant_size k: one sync leases up to k mini-batches (k - 1 driver round trips less; the SSP
+        # staleness bound widens by k - 1); 1 = the reference's sync per mini-batch
+        grant_size = max(1, int(self.context.params.get("mini_batch_grant_size", 1)))
+        credits = 0                # granted mini-batches not started yet
         idle_left = False          # True while this worker has left the unit barriers because it holds no data
         flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
         last_flush = 0.0
@@ -401,8 +424,11 @@ class WorkerTasklet(Tasklet):
                 if self.use_task_units and not idle_left:
                     self.context.task_units.leave(self.job_id)
                     idle_left = True
-                done, pending_progress = pending_progress, None
-                if self.mini_batch_barrier.await_(done, idle=True):
+                if credits:                                  # its data left in the middle of a lease
+                    self.sender.send_mini_batch_return_msg(credits)
+                    credits = 0
+                done, n_done, pending_progress, pending_n = pending_progress, pending_n, None, 0
+                if self.mini_batch_barrier.await_(done, idle=True, progress_count=max(1, n_done)):
                     stop = True
                     break
                 time.sleep(0.05)
@@ -418,15 +444,23 @@ class WorkerTasklet(Tasklet):
                 batch = self.data_provider.get_next_batch_data()
                 if not batch:
                     break
-                # SYNC (void unit): SSP clock + stop flag; carries the progress of the previous mini-batch
-                done, pending_progress = pending_progress, None
-                if self.mini_batch_barrier.await_(done):
-                    stop = True
-                    if self._abort.is_set():
-                        # stopped while asking for a mini-batch: the controller counted the request against the global
-                        # budget but the batch will not run here -- hand it back so another worker trains on it
-                        self.sender.send_mini_batch_return_msg()
-                    break
+                if credits > 0:
+                    if self._abort.is_set():                 # graceful stop inside a lease: the rest is handed back
+                        stop = True
+                        break
+                    credits -= 1                             # this mini-batch is already granted
+                else:
+                    # SYNC (void unit): SSP clock + stop flag; carries the progress of the previous mini-batch(es)
+                    done, n_done, pending_progress, pending_n = pending_progress, pending_n, None, 0
+                    if self.mini_batch_barrier.await_(done, want=grant_size, progress_count=max(1, n_done)):
+                        stop = True
+                        if self._abort.is_set():
+                            # stopped while asking for mini-batches: the controller counted the request against the
+                            # global budget but they will not run here -- hand back whatever it granted, so that
+                            # another worker trains on them
+                            self.sender.send_mini_batch_return_msg()
+                        break
+                    credits = self.mini_batch_barrier.granted - 1
                 self.trainer.set_mini_batch_data(batch)
                 self.accessor.get_and_reset_metrics()
                 t0 = time.perf_counter()
@@ -444,6 +478,7 @@ class WorkerTasklet(Tasklet):
                 bt = time.perf_counter() - t0
                 am = self.accessor.get_and_reset_metrics()
                 pending_progress = total_batches
+                pending_n += 1
                 total_batches += 1
                 n_batches += 1
                 n_inst += len(batch)
@@ -466,8 +501,10 @@ class WorkerTasklet(Tasklet):
             self.context.metric_collector.flush()
             epoch += 1
         mem.close()
+        if credits:                                        # stopped inside a lease: the rest goes back to the budget
+            self.sender.send_mini_batch_return_msg(credits)
         if pending_progress is not None:                   # stopped between a batch and its next sync
-            self.sender.send_progress_msg(pending_progress)
+            self.sender.send_progress_msg(pending_progress, max(1, pending_n))
         if self.use_task_units and not idle_left:
             self.context.task_units.leave(self.job_id)
         result = {"num_batches": total_batches, "num_epochs": epoch, "trainer": type(self.trainer).__name__}

@@ -345,3 +345,78 @@ def test_task_unit_scheduling_follows_the_scheduler_unless_overridden(scheduler,
         assert (js.et_master.task_units.num_waits > 0) == expect_units
     finally:
         js.stop(kill=True)
+
+
+@pytest.mark.parametrize("slack,want", [(0, 3), (1, 4), (2, 8)])
+def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
+    """-mini_batch_grant_size: random interleavings of lease requests, idle syncs, deletions and partial hand-backs.
+    Grants never exceed the budget, the budget is used up exactly when nothing is handed back after the close, the
+    first batch of a lease respects the SSP bound (a running worker is at most slack + want - 1 ahead of the slowest),
+    leases taper at the end, and somebody can always run."""
+    import random
+    from harmony_b200.dolphin.master import MiniBatchController
+
+    class Sender:
+        def __init__(self):
+            self.msgs = []
+
+        def send_mini_batch_control_msg(self, w, stop, granted=1):
+            self.msgs.append((w, stop, granted))
+    for seed in range(25):
+        rng = random.Random(1000 + seed)
+        snd = Sender()
+        total = 6 * 20
+        c = MiniBatchController(6, 20, slack, snd)
+        workers = [f"w{i}" for i in range(4)]
+        waiting, stopped, idle_req = set(), set(), set()
+        credits = {w: 0 for w in workers}
+        ran = 0
+        handed_back_after_close = 0
+        last_grants = []
+        for _ in range(3000):
+            for w, stop, g in snd.msgs:
+                if w in waiting:
+                    waiting.discard(w)
+                    if stop:
+                        stopped.add(w)
+                    elif w not in idle_req:
+                        assert 1 <= g <= want
+                        credits[w] += g
+                        last_grants.append(g)
+                    idle_req.discard(w)
+            snd.msgs.clear()
+            active = [w for w in workers if w not in stopped]
+            if not active:
+                break
+            runnable = [w for w in active if w not in waiting]
+            assert runnable or c._closed, "every active worker is blocked: SSP deadlock"
+            if not runnable:
+                continue
+            w = rng.choice(runnable)
+            r = rng.random()
+            if credits[w] > 0 and r < 0.9:                   # run one leased mini-batch
+                credits[w] -= 1
+                ran += 1
+            elif credits[w] > 0 and r < 0.95:                # its data migrated away in the middle of the lease
+                if c._closed:
+                    handed_back_after_close += credits[w]
+                c.on_return(w, credits[w]); credits[w] = 0
+                c.on_idle_sync(w); waiting.add(w); idle_req.add(w)
+            elif credits[w] > 0 and len(active) > 1:         # a plan deletes the worker in the middle of the lease
+                if c._closed:
+                    handed_back_after_close += credits[w]
+                c.on_return(w, credits[w]); credits[w] = 0
+                c.on_worker_deleted(w); stopped.add(w)
+            elif credits[w] == 0:
+                c.on_sync(w, want); waiting.add(w)
+            prog = dict(c._progress)
+            if len(prog) > 1 and not c._closed:              # (the close releases every blocked request)
+                lo = min(prog.values())
+                # a running lease started within the SSP bound; a blocked request (its lease is counted already) may
+                # reach one lease further
+                assert all(p - lo <= slack + want - 1 for x, p in prog.items() if x not in c._blocked), (prog, c._blocked)
+                assert max(prog.values()) - lo <= slack + 2 * want - 1, prog
+            assert c.num_mini_batches_done <= total
+        assert not [w for w in workers if w not in stopped], "job did not finish"
+        assert ran + handed_back_after_close == total, (ran, handed_back_after_close, total)
+        assert last_grants[-1] == 1                           # the tail of the budget is spread batch by batch

@@ -49,6 +49,16 @@ def test_addvector_validates_under_server_reconfiguration(optimizer):
         assert any("(S: 2, W: 2) -> (S: 3, W: 2)" in m for m in res.messages), res.messages
 
 
+@pytest.mark.parametrize("optimizer", ["DeleteOneWorkerOptimizer", "AddOneWorkerOptimizer", "ExchangeOneOptimizer"])
+def test_addvector_with_minibatch_leases_stays_exact_under_worker_reconfiguration(optimizer):
+    """-mini_batch_grant_size 3: a worker removed in the middle of a lease hands the unused part back, a worker whose
+    blocks leave idles without holding credits, the tail of the budget is granted batch by batch -- AddVector's
+    validation (every granted mini-batch applied exactly once, budget used up exactly) still holds."""
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, _args(optimizer, epochs=8) + ["-mini_batch_grant_size", "3"])
+    assert res.ok, res.messages
+    assert any("(S: 2, W: 2) -> " in m for m in res.messages), res.messages
+
+
 def test_addinteger_standalone():
     res = ETDolphinLauncher.launch(examples.ADD_INTEGER, _args("EmptyPlanOptimizer", epochs=2))
     assert res.ok
