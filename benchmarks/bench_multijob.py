@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="dataset size multiplier")
     ap.add_argument("--epochs", type=int, default=6)
     ap.add_argument("--repartition_after_s", type=float, default=0.2)
+    ap.add_argument("--extra", default="", help="comma-separated flags added to every job, e.g. "
+                                                "--extra=-mini_batch_grant_size,4,-task_unit_scheduling,off")
     a = ap.parse_args()
     import numpy as np
     from helpers import write_lda_sample, write_mlr_sample, write_nmf_sample
@@ -51,7 +53,7 @@ def main():
                                   "chkp_commit_path": tmp + "/c"})).start()
     nb = 8
     common = ["-max_num_epochs", str(a.epochs), "-num_mini_batches", str(nb * a.executors),
-              "-num_worker_blocks", str(nb * a.executors), "-num_server_blocks", "64", "-port", str(port)]
+              "-num_worker_blocks", str(nb * a.executors), "-num_server_blocks", "64", "-port", str(port)] + [x for x in a.extra.split(",") if x]
     jobs = [
         ("MLR-0", mlr, ["-input", d_mlr, "-classes", str(C), "-features", str(F), "-step_size", "0.01"] + common),
         ("NMF-1", nmf, ["-input", d_nmf, "-rank", "64", "-features", "2000", "-step_size", "0.001", "-decay_rate", "1.0"] + common),
@@ -104,7 +106,7 @@ def main():
             per_job[name]["mini_batches_per_s"] = round(per_job[name]["mini_batches"] / per_job[name]["finished_at_s"], 2)
     out = {"metric": "makespan of 4 concurrent jobs (MLR+NMF+LDA+MLR) with one elastic re-partition",
            "value": round(makespan, 3), "unit": "s", "higher_is_better": False, "n_executors": a.executors,
-           "backend": js.backend, "scheduler": a.scheduler, "jobs": per_job, "migration": mig,
+           "backend": js.backend, "scheduler": a.scheduler, "extra_flags": a.extra, "jobs": per_job, "migration": mig,
            "total_mini_batches_per_s": round(sum(j["mini_batches"] or 0 for j in per_job.values()) / makespan, 2)}
     print(json.dumps(out), flush=True)
     js.stop(kill=True)
