@@ -250,9 +250,11 @@ class WorkerSideMsgSender:
             body["want"] = want
         self._send(body, inline=True)
 
-    def send_mini_batch_return_msg(self, count: int = 1) -> None:
+    def send_mini_batch_return_msg(self, count: Optional[int] = None) -> None:
+        """`count` unused granted mini-batches go back to the budget; None = the whole latest grant (the worker was
+        stopped while waiting for the reply and never saw its size)."""
         body = {"type": "MiniBatchReturnMsg", "worker_id": self.worker_id}
-        if count != 1:
+        if count is not None:
             body["count"] = count
         self._send(body, inline=True)
 

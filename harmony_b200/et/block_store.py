@@ -60,6 +60,22 @@ class Block:
         return [self.update(k, d) for k, d in zip(keys, deltas)]
 
 
+class BlockSnapshot(list):
+    """The (key, value) items of one block at one version: a list shared by every reader until the block changes
+    (read-only by convention).  Carries what batch caches key on, so a trainer need not walk the items."""
+
+    __slots__ = ("block_id", "version", "_min_key")
+
+    def __init__(self, items, block_id: int, version: int) -> None:
+        super().__init__(items)
+        self.block_id, self.version, self._min_key = block_id, version, None
+
+    def min_key(self):
+        if self._min_key is None and len(self):
+            self._min_key = min(k for k, _ in self)
+        return self._min_key
+
+
 class DictBlock(Block):
     """Generic key-value block (hash map + update function) for non-dense tables."""
 
@@ -68,11 +84,14 @@ class DictBlock(Block):
         self._fn = update_fn
         self._map: Dict[Any, Any] = {}
         self._lock = threading.RLock()
+        self._version = 0                      # bumped by every mutation: validates the shared snapshot
+        self._snap: Optional[BlockSnapshot] = None
 
     def put(self, key, value):
         with self._lock:
             old = self._map.get(key)
             self._map[key] = value
+            self._version += 1
             return old
 
     def put_if_absent(self, key, value):
@@ -80,6 +99,7 @@ class DictBlock(Block):
             if key in self._map:
                 return self._map[key]
             self._map[key] = value
+            self._version += 1
             return None
 
     def get(self, key):
@@ -90,10 +110,12 @@ class DictBlock(Block):
         with self._lock:
             if key not in self._map:
                 self._map[key] = self._fn.init_value(key)
+                self._version += 1
             return self._map[key]
 
     def remove(self, key):
         with self._lock:
+            self._version += 1
             return self._map.pop(key, None)
 
     def update(self, key, delta):
@@ -101,11 +123,20 @@ class DictBlock(Block):
             old = self._map[key] if key in self._map else self._fn.init_value(key)
             new = self._fn.update_value(key, old, delta)
             self._map[key] = new
+            self._version += 1
             return new
 
     def items(self):
         with self._lock:
             return iter(list(self._map.items()))
+
+    def items_snapshot(self) -> BlockSnapshot:
+        """The items as a list that is rebuilt only after a mutation: the training loop reads every input block once
+        per epoch and the data never changes, so epochs after the first copy nothing."""
+        with self._lock:
+            if self._snap is None or self._snap.version != self._version:
+                self._snap = BlockSnapshot(self._map.items(), self.block_id, self._version)
+            return self._snap
 
     def num_items(self):
         with self._lock:
@@ -119,10 +150,13 @@ class DictBlock(Block):
         with self._lock:
             for k, v in zip(keys, values):
                 self._map[k] = v
+            self._version += 1
 
     def clear(self):
         with self._lock:
             self._map.clear()
+            self._version += 1
+            self._snap = None
 
 
 class DenseBlock(Block):
@@ -340,4 +374,7 @@ class Tablet:
 
     def get_data_in_block(self, block_id: int) -> List[Tuple[Any, Any]]:
         b = self._store.try_get(block_id)
-        return list(b.items()) if b is not None else []
+        if b is None:
+            return []
+        snap = getattr(b, "items_snapshot", None)
+        return snap() if snap is not None else list(b.items())

@@ -124,7 +124,8 @@ class MLRDeviceTrainer(Trainer):
 
     def set_mini_batch_data(self, mini_batch) -> None:
         if self.ship is not None:
-            self._batch = self._ship_steps[self._ship_first_key[min(k for k, _ in mini_batch)]]
+            mk = getattr(mini_batch, "min_key", None)           # O(1) on a block snapshot (cached)
+            self._batch = self._ship_steps[self._ship_first_key[mk() if mk else min(k for k, _ in mini_batch)]]
             return
         self._batch = self._to_device_batch(mini_batch)
 

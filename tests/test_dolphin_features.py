@@ -420,3 +420,22 @@ def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
         assert not [w for w in workers if w not in stopped], "job did not finish"
         assert ran + handed_back_after_close == total, (ran, handed_back_after_close, total)
         assert last_grants[-1] == 1                           # the tail of the budget is spread batch by batch
+
+
+def test_return_message_distinguishes_one_batch_from_the_whole_grant():
+    """Regression: a worker stopped with ONE unused leased batch must hand back 1, not 'my whole latest grant'."""
+    from harmony_b200.dolphin.worker import WorkerSideMsgSender
+
+    class Ctx:
+        class executor:
+            executor_id = "e0"
+        sent = []
+
+        def send_to_driver(self, payload, inline=False):
+            self.sent.append(payload["dolphin"])
+    ctx = Ctx()
+    s = WorkerSideMsgSender(ctx, "job")
+    s.send_mini_batch_return_msg(1)
+    s.send_mini_batch_return_msg(2)
+    s.send_mini_batch_return_msg()
+    assert [m.get("count") for m in ctx.sent] == [1, 2, None]

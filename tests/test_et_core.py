@@ -316,3 +316,25 @@ def test_task_unit_barriers_with_uneven_workers_never_deadlock():
         assert len(done) == 12, f"{12 - len(done)} workers are stuck at a unit barrier"
     finally:
         master.close()
+
+
+def test_block_snapshot_is_shared_until_the_block_changes():
+    """The training loop reads every input block once per epoch: the item list is rebuilt only after a mutation."""
+    from harmony_b200.et.block_store import BlockSnapshot, DictBlock
+    from harmony_b200.et.update_function import make_update_function
+    b = DictBlock(3, make_update_function("add"))
+    for k in (7, 5, 9):
+        b.put(k, k * 10)
+    s1 = b.items_snapshot()
+    assert isinstance(s1, BlockSnapshot) and sorted(s1) == [(5, 50), (7, 70), (9, 90)]
+    assert s1.block_id == 3 and s1.min_key() == 5
+    assert b.items_snapshot() is s1                           # no copy while nothing changes
+    b.get(7); b.get_or_init(7); b.put_if_absent(7, 1)         # reads and no-op writes keep it valid
+    assert b.items_snapshot() is s1
+    for mutate in (lambda: b.put(11, 1), lambda: b.update(5, 1), lambda: b.remove(9), lambda: b.get_or_init(42),
+                   lambda: b.put_if_absent(43, 1), lambda: b.import_items([1], [2]), lambda: b.clear()):
+        before = b.items_snapshot()
+        mutate()
+        after = b.items_snapshot()
+        assert after is not before and sorted(after) == sorted(b.items())
+    assert b.items_snapshot().min_key() is None               # empty block
