@@ -256,8 +256,12 @@ class MiniBatchController:
         grant -- it was stopped while waiting for the reply and never saw the size)."""
         with self._lock:
             n = self._grant.get(worker_id, 1) if count is None else count
-            if not self._closed and n > 0:
+            if n > 0:
                 self._count = max(0, self._count - n)
+                # handed back after the budget had been used up (the stopped worker had asked for the very last
+                # batches): reopen, so that a worker that has not been told to stop yet runs them
+                if self._closed and self._count < self.total:
+                    self._closed = False
 
     def on_worker_deleted(self, worker_id: str) -> None:
         with self._lock:

@@ -452,6 +452,9 @@ class WorkerTasklet(Tasklet):
                         break
                     credits -= 1                             # this mini-batch is already granted
                 else:
+                    if self._abort.is_set():                 # stopped during the last batch: nothing more to ask for
+                        stop = True
+                        break
                     # SYNC (void unit): SSP clock + stop flag; carries the progress of the previous mini-batch(es)
                     done, n_done, pending_progress, pending_n = pending_progress, pending_n, None, 0
                     if self.mini_batch_barrier.await_(done, want=grant_size, progress_count=max(1, n_done)):

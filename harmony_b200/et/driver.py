@@ -565,7 +565,7 @@ class GlobalTaskUnitScheduler:
     def _release(self, key, waiters) -> None:
         for ex, tasklet_id in waiters:
             self._m.send(ex, {"type": "TaskUnitReady", "tasklet_id": tasklet_id, "job_id": key[0],
-                              "unit_name": key[1], "seq": key[2]})
+                              "unit_name": key[1], "seq": key[2], "inline": True})
 
 
 # ==========================================================================================

@@ -188,7 +188,7 @@ class LocalTaskUnitScheduler:
             self._ready[key] = ev
         self._ex.send_to_driver({"type": "TaskUnitWait", "tasklet_id": tasklet_id,
                                  "executor_id": self._ex.executor_id, "job_id": unit.job_id,
-                                 "unit_name": unit.unit_name, "seq": unit.seq})
+                                 "unit_name": unit.unit_name, "seq": unit.seq, "inline": True})
         ev.wait()
         self._sems[unit.resource].acquire()
 

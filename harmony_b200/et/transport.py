@@ -179,10 +179,18 @@ class TcpTransport(Transport):
                 if kind == "msg":
                     with self._lock:
                         ib = self._inboxes.get(frame["dst"])
+                    msg = frame["msg"]
                     if ib is None:
                         LOG.warning("dropping message for unknown local endpoint %s", frame["dst"])
+                    elif msg.get("inline"):
+                        # the sender vouches that the handler never blocks (per-mini-batch sync / grant): run it on
+                        # this connection's reader thread -- per-sender order is kept, the inbox hop is saved
+                        try:
+                            ib.handler(msg)
+                        except Exception:  # noqa: BLE001
+                            LOG.exception("[%s] handler failed for message type %s", ib.endpoint_id, msg.get("type"))
                     else:
-                        ib.q.put(frame["msg"])
+                        ib.q.put(msg)
                 elif kind == "ns_register":
                     with self._lock:
                         self._registry[frame["id"]] = tuple(frame["addr"])

@@ -291,6 +291,7 @@ def test_minibatch_controller_random_schedules_keep_the_ssp_invariants(slack):
         waiting, granted, stopped = set(), {w: 0 for w in workers}, set()
         idle_req = set()                                         # pending requests that were idle syncs (not grants)
         joined_late = False
+        ever_closed = False
         for _ in range(400):
             # deliver control messages
             for w, stop in snd.msgs:
@@ -322,7 +323,8 @@ def test_minibatch_controller_random_schedules_keep_the_ssp_invariants(slack):
             else:
                 c.on_sync(w); waiting.add(w)
             prog = {x: p for x, p in c._progress.items()}
-            if len(prog) > 1:
+            ever_closed = ever_closed or c._closed           # the close releases every blocked request; a late
+            if len(prog) > 1 and not ever_closed:            # hand-back may reopen the budget after that
                 assert max(prog.values()) - min(prog.values()) <= slack + 1, prog
             assert c.num_mini_batches_done <= total_epochs * nmb + len(workers)
         assert sum(granted.values()) <= total_epochs * nmb
@@ -350,7 +352,8 @@ def test_task_unit_scheduling_follows_the_scheduler_unless_overridden(scheduler,
 @pytest.mark.parametrize("slack,want", [(0, 3), (1, 4), (2, 8)])
 def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
     """-mini_batch_grant_size: random interleavings of lease requests, idle syncs, deletions and partial hand-backs.
-    Grants never exceed the budget, the budget is used up exactly when nothing is handed back after the close, the
+    Grants never exceed the budget, the budget is used up exactly (batches handed back after the close are granted
+    again while somebody still asks), the
     first batch of a lease respects the SSP bound (a running worker is at most slack + want - 1 ahead of the slowest),
     leases taper at the end, and somebody can always run."""
     import random
@@ -371,6 +374,7 @@ def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
         waiting, stopped, idle_req = set(), set(), set()
         credits = {w: 0 for w in workers}
         ran = 0
+        ever_closed = False
         handed_back_after_close = 0
         last_grants = []
         for _ in range(3000):
@@ -410,7 +414,8 @@ def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
             elif credits[w] == 0:
                 c.on_sync(w, want); waiting.add(w)
             prog = dict(c._progress)
-            if len(prog) > 1 and not c._closed:              # (the close releases every blocked request)
+            ever_closed = ever_closed or c._closed
+            if len(prog) > 1 and not ever_closed:            # (the close releases every blocked request)
                 lo = min(prog.values())
                 # a running lease started within the SSP bound; a blocked request (its lease is counted already) may
                 # reach one lease further
@@ -418,7 +423,8 @@ def test_minibatch_leases_keep_budget_clock_and_liveness(slack, want):
                 assert max(prog.values()) - lo <= slack + 2 * want - 1, prog
             assert c.num_mini_batches_done <= total
         assert not [w for w in workers if w not in stopped], "job did not finish"
-        assert ran + handed_back_after_close == total, (ran, handed_back_after_close, total)
+        # batches handed back after the close are granted again if somebody still asks (the budget reopens)
+        assert total - handed_back_after_close <= ran <= total, (ran, handed_back_after_close, total)
         assert last_grants[-1] == 1                           # the tail of the budget is spread batch by batch
 
 
@@ -439,3 +445,28 @@ def test_return_message_distinguishes_one_batch_from_the_whole_grant():
     s.send_mini_batch_return_msg(2)
     s.send_mini_batch_return_msg()
     assert [m.get("count") for m in ctx.sent] == [1, 2, None]
+
+
+def test_budget_reopens_when_the_last_batch_is_handed_back():
+    """Regression (flaky live test): the worker that asked for the very last mini-batch is removed by a plan before
+    running it -- the hand-back arrives after the close and must let a remaining worker run that batch."""
+    from harmony_b200.dolphin.master import MiniBatchController
+
+    class Sender:
+        def __init__(self):
+            self.msgs = []
+
+        def send_mini_batch_control_msg(self, w, stop):
+            self.msgs.append((w, stop))
+    snd = Sender()
+    c = MiniBatchController(1, 2, 10, snd)
+    c.on_sync("w0")
+    c.on_sync("w1")                       # the last unit of the budget: closes
+    assert c._closed and snd.msgs == [("w0", False), ("w1", False)]
+    c.on_return("w1")                     # w1 was stopped before running it
+    c.on_worker_deleted("w1")
+    assert not c._closed and c.num_mini_batches_done == 1
+    c.on_sync("w0")                       # w0 finished its batch and asks again: it gets the handed-back one
+    assert snd.msgs[-1] == ("w0", False) and c._closed and c.num_mini_batches_done == 2
+    c.on_sync("w0")
+    assert snd.msgs[-1] == ("w0", True)
