@@ -73,14 +73,22 @@ class ETDolphinLauncher:
         num_workers = int(conf.get("num_dolphin_workers", 1))
         num_servers = int(conf.get("num_servers", 1))
         colocated = num_servers == 0
-        transport = LocalTransport()
         # -backend auto|host|device: on a GPU box the stand-alone job also runs on HBM tables + fused kernels
         import itertools
-        from ..et.launcher import detect_backend, make_executor
+        from ..et.launcher import SubprocessLauncher, detect_backend, make_executor
         backend = detect_backend(conf.get("backend", "auto"))
         conf = conf.with_values(backend=backend)
-        ordinal = itertools.count()
-        launcher = InProcessLauncher(lambda eid, tr, ec_, did: make_executor(eid, tr, ec_, did, backend, next(ordinal)))
+        if conf.get("executor_mode", "inproc") == "process":
+            # one OS process per executor (per GPU on the device backend), TCP control plane -- the layout of the job
+            # server's `-executor_mode process`; the optimizer's plans (add / delete / switch executors) run over it
+            from ..et.transport import TcpTransport
+            transport = TcpTransport("127.0.0.1", 0, None)
+            launcher = SubprocessLauncher(transport.address, backend=backend)
+        else:
+            transport = LocalTransport()
+            ordinal = itertools.count()
+            launcher = InProcessLauncher(
+                lambda eid, tr, ec_, did: make_executor(eid, tr, ec_, did, backend, next(ordinal)))
         master = ETMaster(transport, launcher, chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
                           chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
         messages: List[str] = []

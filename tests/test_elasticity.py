@@ -59,6 +59,18 @@ def test_addvector_with_minibatch_leases_stays_exact_under_worker_reconfiguratio
     assert any("(S: 2, W: 2) -> " in m for m in res.messages), res.messages
 
 
+@pytest.mark.parametrize("optimizer", ["DeleteOneWorkerOptimizer", "AddOneWorkerOptimizer", "ExchangeOneOptimizer",
+                                       "AddOneServerOptimizer"])
+def test_addvector_reconfigures_over_executor_processes(optimizer):
+    """The same live plans with one OS process per executor and the TCP control plane (`-executor_mode process`, the
+    one-process-per-GPU layout): executors are allocated / stopped as processes, tasklets start and stop remotely,
+    deferred master messages and hand-backs cross sockets -- the sums stay exact."""
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, _args(optimizer) + ["-executor_mode", "process",
+                                                                           "-backend", "host"])
+    assert res.ok, res.messages
+    assert any("(S: 2, W: 2) -> " in m for m in res.messages), res.messages
+
+
 def test_addinteger_standalone():
     res = ETDolphinLauncher.launch(examples.ADD_INTEGER, _args("EmptyPlanOptimizer", epochs=2))
     assert res.ok
