@@ -470,3 +470,41 @@ def test_budget_reopens_when_the_last_batch_is_handed_back():
     assert snd.msgs[-1] == ("w0", False) and c._closed and c.num_mini_batches_done == 2
     c.on_sync("w0")
     assert snd.msgs[-1] == ("w0", True)
+
+
+def test_killed_executor_process_fails_the_job_fast():
+    """Failure detection with real processes: SIGKILL one executor of a running stand-alone job (`-executor_mode
+    process`); the launcher's monitor turns the exit into an executor failure, the job fails within seconds instead
+    of hanging on its barriers, and no executor process is left behind."""
+    import signal
+    import subprocess
+    import threading
+    import time
+    from harmony_b200.mlapps import examples
+    data = examples.write_dummy_input(48)
+    args = ["-input", data, "-num_dolphin_workers", "2", "-num_servers", "1", "-max_num_epochs", "200",
+            "-num_mini_batches", "8", "-num_worker_blocks", "8", "-num_server_blocks", "8", "-num_keys", "20",
+            "-vector_size", "4", "-compute_time_ms", "40", "-executor_mode", "process", "-backend", "host"]
+    killed = {}
+
+    def killer():
+        deadline = time.time() + 60
+        while time.time() < deadline:
+            kids = subprocess.run(["pgrep", "-P", str(os.getpid()), "-f", "executor_main"], capture_output=True,
+                                  text=True).stdout.split()
+            if len(kids) >= 3:
+                break
+            time.sleep(0.2)
+        time.sleep(2.0)                                   # let the training loop start
+        killed["pid"], killed["at"] = int(kids[0]), time.time()
+        os.kill(killed["pid"], signal.SIGKILL)            # an exact PID: one of this test's own executor children
+    threading.Thread(target=killer, daemon=True).start()
+    res = ETDolphinLauncher.launch(examples.ADD_VECTOR, args)
+    done = time.time()
+    assert killed, "the executors never came up"
+    assert not res.ok
+    assert done - killed["at"] < 20, "the job did not fail fast"
+    time.sleep(0.5)
+    left = subprocess.run(["pgrep", "-P", str(os.getpid()), "-f", "executor_main"], capture_output=True,
+                          text=True).stdout.split()
+    assert not left, left
