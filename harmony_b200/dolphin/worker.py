@@ -132,7 +132,12 @@ class CachedModelAccessor(ETModelAccessor):
             with self._lock:
                 keys = list(self._cache)
             if keys:
-                vals = self.table.multi_get_or_init(keys).get(timeout=600)
+                try:
+                    vals = self.table.multi_get_or_init(keys).get(timeout=600)
+                except Exception as e:  # noqa: BLE001
+                    # the table went away under a refresh (job teardown): the cache keeps its last values
+                    LOG.debug("model cache refresh failed: %s", e)
+                    continue
                 with self._lock:
                     for k, v in zip(keys, vals):
                         self._cache[k] = v
@@ -394,6 +399,14 @@ class WorkerTasklet(Tasklet):
         return time.perf_counter() - t0
 
     def run(self) -> Any:
+        try:
+            return self._train()
+        finally:
+            close = getattr(getattr(self, "accessor", None), "close", None)
+            if close is not None:
+                close()                   # the cached accessor's refresh thread ends with its tasklet
+
+    def _train(self) -> Any:
         ex_id = self.context.executor.executor_id
         # the trainer is built on the tasklet's own thread, AFTER the runtime registered the tasklet: a trainer
         # that rendezvouses with its peers in the constructor (ship mode) needs the master's replies routed to it
