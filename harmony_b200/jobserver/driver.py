@@ -13,6 +13,7 @@ asks for) and `FifoExclusiveScheduler` (queues jobs when the pool is busy).
 from __future__ import annotations
 
 import importlib
+import collections
 import itertools
 import logging
 import threading
@@ -260,6 +261,9 @@ class JobServerDriver:
     scheduler hook-up, job dispatch and bookkeeping.  Reference:
     jobserver/src/main/java/edu/snu/cay/jobserver/driver/JobServerDriver.java:80-109,125-145,178-214,222-266."""
 
+    MAX_CLIENT_MESSAGES = 20000
+    MAX_FINISHED_JOBS = 2000
+
     def __init__(self, et_master: ETMaster, conf: Configuration,
                  client_sink: Optional[Callable[[str], None]] = None) -> None:
         self.et_master = et_master
@@ -278,7 +282,8 @@ class JobServerDriver:
         self._job_counter = itertools.count()
         self._lock = threading.Condition()
         self._client_sink = client_sink
-        self.client_messages: List[str] = []
+        # a server runs for weeks: progress lines and finished-job records are bounded histories, not logs
+        self.client_messages: "collections.deque[str]" = collections.deque(maxlen=self.MAX_CLIENT_MESSAGES)
         self.deferred_evaluations: List[Callable[[], None]] = []
         self.job_entity_builders: Dict[str, Callable[..., JobEntity]] = {}
         et_master.custom_handlers["TaskletCustom"] = self._on_tasklet_custom
@@ -327,6 +332,10 @@ class JobServerDriver:
             self._active_jobs.discard(job_id)
             self.job_results[job_id] = (ok, result)
             self.job_finish_times[job_id] = time.time()
+            while len(self.job_results) > self.MAX_FINISHED_JOBS:      # dicts keep insertion order: oldest first
+                old_id = next(iter(self.job_results))
+                self.job_results.pop(old_id)
+                self.job_finish_times.pop(old_id, None)
             self._lock.notify_all()
 
     def running_jobs(self) -> List[str]:
