@@ -682,6 +682,10 @@ class AllocatedExecutor:
         self._m.send(self.id, {"type": "TaskletStart", "conf": conf.to_dict()})
         return rt
 
+    def forget_tasklet(self, tasklet_id: str) -> None:
+        with self._lock:
+            self._tasklets.pop(tasklet_id, None)
+
     def get_running_tasklets(self) -> Dict[str, RunningTasklet]:
         with self._lock:
             return {k: v for k, v in self._tasklets.items() if not v.is_done()}
@@ -1125,6 +1129,14 @@ class ETMaster:
                 rt = self._tasklets.get((m["executor_id"], m["tasklet_id"]))
             if rt is not None:
                 rt.on_status(m)
+                if m["status"] in ("Done", "Failed"):
+                    # the handle (and its result) lives on with whoever holds it; the registries of a long-running
+                    # driver only keep live tasklets
+                    with self._lock:
+                        self._tasklets.pop((m["executor_id"], m["tasklet_id"]), None)
+                    ae = self.executors.get(m["executor_id"])
+                    if ae is not None:
+                        ae.forget_tasklet(m["tasklet_id"])
         elif t == "TaskletCustom":
             with self._lock:
                 rt = self._tasklets.get((m["executor_id"], m["tasklet_id"]))
