@@ -529,6 +529,8 @@ class GlobalTaskUnitScheduler:
     def on_job_finish(self, job_id: str) -> None:
         with self._lock:
             self._job_size.pop(job_id, None)
+            for k in [k for k in self._waiting if k[0] == job_id]:      # barriers a failed job never completed
+                self._waiting.pop(k, None)
 
     def on_job_resize(self, job_id: str, num_executors: int) -> None:
         with self._lock:
