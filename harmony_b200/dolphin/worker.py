@@ -550,6 +550,8 @@ class WorkerTasklet(Tasklet):
 class ServerTasklet(Tasklet):
     """Servers are passive shard owners: the tasklet idles until closed."""
 
+    passive = True          # parks on a latch: takes no tasklet slot (et/tasklet.py)
+
     def __init__(self, context) -> None:
         super().__init__(context)
         self._latch = threading.Event()

@@ -25,7 +25,11 @@ def main(argv=None) -> int:
     a = ap.parse_args(argv)
     import faulthandler
     import signal
-    faulthandler.register(signal.SIGUSR1, all_threads=True)     # `kill -USR1 <pid>` dumps every thread's stack
+    # `kill -USR1 <pid>` dumps every thread's stack: to stderr, or to $HB_DUMP_DIR/<executor id>.stacks (several
+    # executors dumping into one inherited stderr interleave their lines)
+    dump_dir = os.environ.get("HB_DUMP_DIR")
+    dump_file = open(os.path.join(dump_dir, f"{a.id}.stacks"), "w") if dump_dir else sys.stderr
+    faulthandler.register(signal.SIGUSR1, file=dump_file, all_threads=True)
     logging.basicConfig(level=logging.INFO, format=f"%(asctime)s %(levelname)s [{a.id}] %(name)s | %(message)s")
     host, port = a.driver.rsplit(":", 1)
     transport = TcpTransport("127.0.0.1", 0, (host, int(port)))

@@ -104,6 +104,11 @@ class TaskletRuntime:
                          name=f"{self._ex.executor_id}-tasklet-{conf.tasklet_id}").start()
 
     def _run_slot(self, tasklet_id: str, tasklet: Tasklet) -> None:
+        if getattr(tasklet, "passive", False):
+            # a tasklet that only parks (the servers' idle latch) must not hold an execution slot: with one server
+            # tasklet per job on every executor, a handful of jobs would starve every worker tasklet
+            self._run(tasklet_id, tasklet)
+            return
         with self._slots:
             self._run(tasklet_id, tasklet)
 

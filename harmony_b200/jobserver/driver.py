@@ -224,6 +224,25 @@ class JobDispatcher:
 
     def __init__(self, driver: "JobServerDriver") -> None:
         self._d = driver
+        # admission: a job starts only when EVERY executor it runs on has a free tasklet slot.  The slots are taken
+        # all-or-nothing -- two jobs that each hold a slot on one executor and wait for the other's (their workers
+        # parked at the INIT barrier) would deadlock the pool.
+        self._slots_cv = threading.Condition()
+        self._jobs_on: Dict[str, int] = {}
+        self.slots_per_executor = max(4, int(driver.conf.get("executor_num_tasklets", 4)))
+
+    def _admit(self, executors: Sequence[AllocatedExecutor]) -> None:
+        ids = [e.id for e in executors]
+        with self._slots_cv:
+            self._slots_cv.wait_for(lambda: all(self._jobs_on.get(i, 0) < self.slots_per_executor for i in ids))
+            for i in ids:
+                self._jobs_on[i] = self._jobs_on.get(i, 0) + 1
+
+    def _release(self, executors: Sequence[AllocatedExecutor]) -> None:
+        with self._slots_cv:
+            for e in executors:
+                self._jobs_on[e.id] = max(0, self._jobs_on.get(e.id, 0) - 1)
+            self._slots_cv.notify_all()
 
     def execute_job(self, job: JobEntity, executors: Sequence[AllocatedExecutor]) -> None:
         self._d.mark_job_active(job.get_job_id())
@@ -233,6 +252,7 @@ class JobDispatcher:
     def _run(self, job: JobEntity, executors: List[AllocatedExecutor]) -> None:
         d = self._d
         job_id = job.get_job_id()
+        self._admit(executors)
         d.send_to_client(f"Start executing a job. JobId: {job_id}")
         ok, result = False, None
         try:
@@ -251,6 +271,7 @@ class JobDispatcher:
                 job.cleanup()
             except Exception:  # noqa: BLE001
                 LOG.exception("cleanup of %s failed", job_id)
+            self._release(executors)
             d.remove_job_master(job_id, ok, result)
             d.send_to_client(f"Job {'finished' if ok else 'FAILED'}. JobId: {job_id}")
             d.scheduler.on_job_finish(len(executors), job)

@@ -42,3 +42,13 @@ class RendezvousTrainer(FailingTrainer):
 
     def summary(self):
         return {"group": [list(x) for x in self.seen]}
+
+
+from harmony_b200.et.tasklet import Tasklet as _Tasklet  # noqa: E402
+
+
+class EchoTasklet(_Tasklet):
+    """Returns its `value` parameter (a tasklet that needs an execution slot, for the runtime tests)."""
+
+    def run(self):
+        return self.context.params.get("value")

@@ -508,3 +508,74 @@ def test_killed_executor_process_fails_the_job_fast():
     left = subprocess.run(["pgrep", "-P", str(os.getpid()), "-f", "executor_main"], capture_output=True,
                           text=True).stdout.split()
     assert not left, left
+
+
+def test_more_concurrent_jobs_than_tasklet_slots_never_deadlock():
+    """Regression (rare hang with >= 4 concurrent jobs): every job puts a server tasklet (idle latch) and a worker
+    tasklet on every executor.  The idle servers take no execution slot, and a job is admitted only when all of its
+    executors have a free slot (all-or-nothing), so jobs beyond the slot count queue instead of deadlocking at their
+    INIT barriers."""
+    tmp = tempfile.mkdtemp(prefix="hbslots")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=60)
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 2, "port": port})).start()
+    try:
+        assert js.driver.dispatcher.slots_per_executor == 4
+        n = 7
+        for _ in range(n):
+            assert DolphinJobLauncher.submit_job(mlr.APP_PATH, mlr.APP, _args(data, port, ["-max_num_epochs", "2"]),
+                                                 port=port).startswith("true")
+        for j in range(n):
+            ok, res = js.driver.wait_job(f"MLR-{j}", timeout=120)
+            assert ok, res
+        assert all(v == 0 for v in js.driver.dispatcher._jobs_on.values())
+    finally:
+        js.stop(kill=True)
+
+
+def test_parked_server_tasklets_take_no_execution_slot_and_admission_is_all_or_nothing():
+    """The two halves of the fix, deterministically: (1) with every slot's worth of idle server tasklets parked on an
+    executor, a worker tasklet still starts; (2) the dispatcher never lets a job hold a slot on one executor while it
+    waits for another."""
+    import threading
+    import time
+    from harmony_b200.et import local_cluster
+    from harmony_b200.et.config import TaskletConfiguration
+    master, execs, launcher = local_cluster(1)
+    try:
+        ex = execs[0]
+        slots = launcher.executors[ex.id].conf.num_tasklets
+        parked = [ex.submit_tasklet(TaskletConfiguration(f"srv{i}", "harmony_b200.dolphin.worker:ServerTasklet", None, {}))
+                  for i in range(slots + 2)]
+        time.sleep(0.3)
+        rt = ex.submit_tasklet(TaskletConfiguration("work", "helpers:EchoTasklet", None, {"value": 7}))
+        assert rt.get_task_result(timeout=10).result == 7
+        for p in parked:
+            p.stop()
+    finally:
+        master.close()
+
+    from harmony_b200.jobserver.driver import JobDispatcher
+
+    class Drv:
+        conf = {"executor_num_tasklets": 4}
+
+    class Ex:
+        def __init__(self, i):
+            self.id = i
+    d = JobDispatcher(Drv())
+    d.slots_per_executor = 1
+    a, b = Ex("a"), Ex("b")
+    d._admit([a])                                   # job 1 runs on a
+    got = []
+    t = threading.Thread(target=lambda: (d._admit([a, b]), got.append(1)), daemon=True)   # job 2 wants a AND b
+    t.start()
+    time.sleep(0.2)
+    assert not got and d._jobs_on.get("b", 0) == 0  # it waits WITHOUT holding b
+    d._admit([b])                                   # so job 3 (only b) can start
+    d._release([a])
+    time.sleep(0.2)
+    assert not got                                  # b is taken now: job 2 still waits, still holds nothing
+    d._release([b])
+    t.join(5)
+    assert got and d._jobs_on == {"a": 1, "b": 1}
