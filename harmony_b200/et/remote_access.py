@@ -154,7 +154,10 @@ class CommManager:
     `block_id % num_threads`, which yields per-block FIFO execution."""
 
     def __init__(self, num_threads: int, queue_size: int, name: str) -> None:
-        self._queues = [queue.Queue(maxsize=max(1, queue_size)) for _ in range(max(1, num_threads))]
+        # `queue_size` is a soft limit (a warning): ops are enqueued by the executor's inbox thread, and an inbox that
+        # blocks on a full queue can no longer deliver the ownership update the queued ops are waiting for
+        self._queues = [queue.Queue() for _ in range(max(1, num_threads))]
+        self._soft_limit, self._warned, self._name = max(1, queue_size), False, name
         self._threads = []
         self._closed = False
         for i, q in enumerate(self._queues):
@@ -163,7 +166,12 @@ class CommManager:
             self._threads.append(t)
 
     def enqueue(self, block_id: int, fn: Callable[[], None]) -> None:
-        self._queues[block_id % len(self._queues)].put(fn)
+        q = self._queues[block_id % len(self._queues)]
+        if not self._warned and q.qsize() >= self._soft_limit:
+            self._warned = True
+            LOG.warning("%s: more than %d table ops queued on one comm thread (slow or migrating block?)",
+                        self._name, self._soft_limit)
+        q.put(fn)
 
     def _run(self, q: "queue.Queue") -> None:
         while True:
