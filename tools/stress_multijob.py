@@ -2,6 +2,7 @@
 thread's harmony_b200 frames and exits 3 when an iteration exceeds 60 s (hang detector for the control plane).
 
     python tools/stress_multijob.py [SchedulerImpl|FifoExclusiveScheduler|PackingScheduler] [iterations]
+    HB_STRESS_EXECUTOR_MODE=process HB_STRESS_BACKEND=host python tools/stress_multijob.py ...   (one process per executor)
 """
 import sys, logging, threading, time, traceback, os, tempfile, socket
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,7 +37,8 @@ for it in range(int(sys.argv[2]) if len(sys.argv)>2 else 6):
       (lasso,["-input",tmp+"/sample_lasso","-features","10","-features_per_partition","5","-lambda","0.5","-step_size","1.0","-max_num_epochs","3","-num_mini_batches","4","-num_worker_blocks","4"]),
       (gbt,["-input",tmp+"/sample_gbt","-metadata_path",tmp+"/sample_gbt.meta","-features","784","-step_size","0.1","-max_num_epochs","1","-num_mini_batches","4","-num_worker_blocks","4","-max_depth_of_tree","2"])]
     deadline[0]=time.time()+60
-    js=JobServer(Configuration({"num_executors":4,"port":port,"scheduler":sched})).start()
+    js=JobServer(Configuration({"num_executors":4,"port":port,"scheduler":sched,"backend":os.environ.get("HB_STRESS_BACKEND","auto"),
+                                "executor_mode":os.environ.get("HB_STRESS_EXECUTOR_MODE","inproc")})).start()
     t=time.time(); names=[]
     for i,(app,a) in enumerate(subs):
         r=DolphinJobLauncher.submit_job(app.APP_PATH, app.APP, a+P, port=port); names.append(r.split("JobId: ")[-1].strip())
