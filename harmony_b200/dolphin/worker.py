@@ -427,6 +427,12 @@ class WorkerTasklet(Tasklet):
         # -mini_batch_grant_size k: one sync leases up to k mini-batches (k - 1 driver round trips less; the SSP
         # staleness bound widens by k - 1); 1 = the reference's sync per mini-batch
         grant_size = max(1, int(self.context.params.get("mini_batch_grant_size", 1)))
+        if grant_size > 1 and self.use_task_units:
+            # the unit barriers need the job's workers in lock-step (same unit, same sequence number); a lease lets
+            # one worker run ahead while a peer is SSP-blocked at its sync -- the two waits would deadlock
+            LOG.warning("[%s] -mini_batch_grant_size %d ignored: task-unit co-scheduling is on for this job "
+                        "(-task_unit_scheduling off, or an exclusive scheduler, enables leases)", self.job_id, grant_size)
+            grant_size = 1
         credits = 0                # granted mini-batches not started yet
         idle_left = False          # True while this worker has left the unit barriers because it holds no data
         flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
@@ -532,11 +538,16 @@ class WorkerTasklet(Tasklet):
             on_stopped = getattr(self.trainer, "on_worker_stopped", None)
             if on_stopped is not None:
                 on_stopped()
-            return {**result, "stopped": True, **self.trainer.summary()}
+            return {**result, "stopped": True, **self._summary(total_batches)}
         self.global_barrier.await_()                       # RUN -> CLEANUP barrier
-        summary = self.trainer.summary()
+        summary = self._summary(total_batches)
         self.trainer.cleanup()
         return {**result, **summary}
+
+    def _summary(self, total_batches: int) -> Dict[str, float]:
+        # "last batch" numbers exist only on a worker that ran a batch: with fewer mini-batches than workers (or
+        # leases) some worker of a short job legitimately trains on none
+        return self.trainer.summary() if total_batches > 0 else {}
 
     def close(self) -> None:
         """Graceful stop: the loop ends at the next mini-batch boundary (a batch in flight completes)."""

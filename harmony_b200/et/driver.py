@@ -760,7 +760,7 @@ class AllocatedTable:
             if conf.chkp_path:
                 self._m.chkp_master.load_from_path(conf.chkp_path, self).chain(fut, done)
             elif conf.input_path:
-                self._m.control.load(conf.table_id, ids, conf.input_path).chain(fut, done)
+                self._m.control.load(conf.table_id, self._loaders(ids), conf.input_path).chain(fut, done)
             else:
                 done()
 
@@ -802,9 +802,15 @@ class AllocatedTable:
         self._m.control.init_table(conf, ids, self.block_manager.get_ownership_status()).chain(fut, after_init)
         return fut
 
+    def _loaders(self, ids: Set[str]) -> Set[str]:
+        """The executors that read the input splits: those that own a block (a table with fewer blocks than
+        associators leaves some without one, and the none-key loader draws its keys from the local blocks)."""
+        owners = {e for e in ids if self.block_manager.get_num_blocks(e) > 0}
+        return owners or set(ids)
+
     def load(self, executors: Sequence[AllocatedExecutor], input_path: str) -> ResultFuture:
         self.sm.check_state("INITIALIZED")
-        return self._m.control.load(self.table_id, {e.id for e in executors}, input_path)
+        return self._m.control.load(self.table_id, self._loaders({e.id for e in executors}), input_path)
 
     # ---- subscription / association ----
     def subscribe(self, executors: Sequence[AllocatedExecutor]) -> ResultFuture:

@@ -579,3 +579,27 @@ def test_parked_server_tasklets_take_no_execution_slot_and_admission_is_all_or_n
     d._release([b])
     t.join(5)
     assert got and d._jobs_on == {"a": 1, "b": 1}
+
+
+def test_worker_that_trains_on_no_batch_does_not_fail_the_job_and_leases_yield_to_unit_barriers(tmp_path):
+    """Two soak regressions in one job: (1) fewer mini-batches than workers -- the worker that ran no batch has no
+    'last batch' summary to report (Lasso / GBT summaries used to raise); (2) -mini_batch_grant_size with task-unit
+    co-scheduling on (shared-pool scheduler): leases are ignored (they would deadlock the per-unit barriers), the job
+    still completes."""
+    from harmony_b200.common.samples import write_lasso_sample
+    from harmony_b200.mlapps import lasso
+    data = write_lasso_sample(str(tmp_path / "sample_lasso"))
+    port = _free_port()
+    js = JobServer(Configuration({"num_executors": 3, "port": port})).start()
+    try:
+        args = ["-input", data, "-features", "10", "-features_per_partition", "5", "-lambda", "0.5", "-step_size", "1.0",
+                "-max_num_epochs", "3", "-num_mini_batches", "2", "-num_worker_blocks", "2", "-mini_batch_grant_size", "3",
+                "-port", str(port)]
+        assert DolphinJobLauncher.submit_job(lasso.APP_PATH, lasso.APP, args, port=port).startswith("true")
+        ok, res = js.driver.wait_job("Lasso-0", timeout=120)
+        assert ok, res
+        assert sorted(r["num_batches"] for r in res)[0] == 0          # somebody trained on nothing ...
+        assert sum(r["num_batches"] for r in res) == 6                # ... and the budget was still used up exactly
+        assert js.et_master.task_units.num_waits > 0                  # unit barriers were on (leases were not)
+    finally:
+        js.stop(kill=True)

@@ -30,7 +30,7 @@ tmp=write_all(tempfile.mkdtemp())
 sched=sys.argv[1] if len(sys.argv)>1 else "SchedulerImpl"
 for it in range(int(sys.argv[2]) if len(sys.argv)>2 else 6):
     s=socket.socket(); s.bind(("127.0.0.1",0)); port=s.getsockname()[1]; s.close()
-    P=["-port",str(port)]
+    P=["-port",str(port)]+[x for x in os.environ.get("HB_STRESS_EXTRA","").split(",") if x]   # e.g. -mini_batch_grant_size,3
     subs=[(mlr,["-input",tmp+"/sample_mlr","-classes","10","-features","784","-max_num_epochs","2","-num_mini_batches","8","-num_worker_blocks","8","-step_size","0.01"]),
       (nmf,["-input",tmp+"/sample_nmf","-rank","8","-features","100","-step_size","0.01","-max_num_epochs","3","-num_mini_batches","8","-num_worker_blocks","8"]),
       (lda,["-input",tmp+"/sample_lda","-num_topics","10","-num_vocabs","17935","-max_num_epochs","2","-num_mini_batches","8","-num_worker_blocks","8"]),
