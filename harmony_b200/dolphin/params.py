@@ -55,7 +55,8 @@ DOLPHIN = [
     P("job_priority", str, "normal", "normal | high: CUDA stream priority of the job's tasklets on shared GPUs", "worker"),
     P("mini_batch_grant_size", int, 1, "mini-batches leased per SSP sync (1 = one driver round trip per mini-batch, "
                                        "as the reference; k > 1 saves k - 1 of them and widens the staleness bound by "
-                                       "k - 1; leases taper to 1 as the budget runs out)", "worker"),
+                                       "k - 1; leases taper to 1 as the budget runs out; ignored while the job's task-unit "
+                                       "barriers are on)", "worker"),
     P("task_unit_scheduling", str, "auto", "on | off | auto: per-phase global barriers that interleave the phases of "
                                            "co-located jobs (one driver round trip per phase); auto = on unless the "
                                            "job server's scheduler runs jobs exclusively", "worker"),
