@@ -547,7 +547,13 @@ class WorkerTasklet(Tasklet):
     def _summary(self, total_batches: int) -> Dict[str, float]:
         # "last batch" numbers exist only on a worker that ran a batch: with fewer mini-batches than workers (or
         # leases) some worker of a short job legitimately trains on none
-        return self.trainer.summary() if total_batches > 0 else {}
+        if total_batches > 0:
+            return self.trainer.summary()
+        try:
+            return self.trainer.summary()
+        except Exception as e:  # noqa: BLE001
+            LOG.debug("[%s] no summary from a worker that ran no mini-batch: %s", self.job_id, e)
+            return {}
 
     def close(self) -> None:
         """Graceful stop: the loop ends at the next mini-batch boundary (a batch in flight completes)."""
