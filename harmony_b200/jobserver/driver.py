@@ -231,10 +231,13 @@ class JobDispatcher:
         self._jobs_on: Dict[str, int] = {}
         self.slots_per_executor = max(4, int(driver.conf.get("executor_num_tasklets", 4)))
 
-    def _admit(self, executors: Sequence[AllocatedExecutor]) -> None:
+    def _admit(self, executors: Sequence[AllocatedExecutor], job_id: str = "") -> None:
         ids = [e.id for e in executors]
+        free = lambda: all(self._jobs_on.get(i, 0) < self.slots_per_executor for i in ids)  # noqa: E731
         with self._slots_cv:
-            self._slots_cv.wait_for(lambda: all(self._jobs_on.get(i, 0) < self.slots_per_executor for i in ids))
+            if not free() and job_id:
+                self._d.send_to_client(f"Waiting for a free tasklet slot on every executor. JobId: {job_id}")
+            self._slots_cv.wait_for(free)
             for i in ids:
                 self._jobs_on[i] = self._jobs_on.get(i, 0) + 1
 
@@ -252,7 +255,7 @@ class JobDispatcher:
     def _run(self, job: JobEntity, executors: List[AllocatedExecutor]) -> None:
         d = self._d
         job_id = job.get_job_id()
-        self._admit(executors)
+        self._admit(executors, job_id)
         d.send_to_client(f"Start executing a job. JobId: {job_id}")
         ok, result = False, None
         try:
