@@ -255,8 +255,15 @@ class PregelLauncher:
     @staticmethod
     def launch(app: PregelApp, argv: Sequence[str]):
         conf = parse_conf(app, argv)
-        transport = LocalTransport()
-        master = ETMaster(transport, InProcessLauncher())
+        if conf.get("executor_mode", "inproc") == "process":
+            # one OS process per Pregel worker over the TCP control plane (the Dolphin launcher's `-executor_mode process`)
+            from ..et.launcher import SubprocessLauncher
+            from ..et.transport import TcpTransport
+            transport = TcpTransport("127.0.0.1", 0, None)
+            master = ETMaster(transport, SubprocessLauncher(transport.address, backend="host"))
+        else:
+            transport = LocalTransport()
+            master = ETMaster(transport, InProcessLauncher())
         ok, results, pm = False, None, None
         try:
             execs = master.add_executors(int(conf.get("num_pregel_workers", 1)), ExecutorConfiguration()).get(120)

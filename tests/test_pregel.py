@@ -5,6 +5,7 @@ import socket
 import tempfile
 
 import numpy as np
+import pytest
 
 from harmony_b200.pregel import apps
 from harmony_b200.pregel.runtime import PregelJobLauncher, PregelLauncher
@@ -21,10 +22,13 @@ def _graph(tmp, weighted):
     return path, adj
 
 
-def test_pagerank_matches_power_iteration():
+@pytest.mark.parametrize("mode", ["inproc", "process"])
+def test_pagerank_matches_power_iteration(mode):
+    """`process`: one OS process per Pregel worker, vertex / message tables and superstep control over TCP."""
     tmp = tempfile.mkdtemp(prefix="hbpr")
     path, adj = _graph(tmp, weighted=False)
-    ok, results, pm = PregelLauncher.launch(apps.PAGERANK, ["-input", path, "-num_pregel_workers", "2"])
+    ok, results, pm = PregelLauncher.launch(apps.PAGERANK, ["-input", path, "-num_pregel_workers", "2",
+                                                            "-executor_mode", mode])
     assert ok
     vals = {}
     for r in results:
