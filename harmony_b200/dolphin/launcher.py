@@ -52,6 +52,7 @@ class LauncherResult:
 
     def __init__(self, ok: bool, results: Any, messages: List[str], master: Optional[DolphinMaster]) -> None:
         self.ok, self.results, self.messages, self.dolphin_master = ok, results, messages, master
+        self.eval_results: Optional[List[Any]] = None     # -offline_model_eval: one entry per evaluation worker
 
     @property
     def status(self) -> str:
@@ -94,7 +95,7 @@ class ETDolphinLauncher:
         messages: List[str] = []
         receiver = ETDolphinMetricReceiver()
         master.metrics.receivers.append(receiver)
-        ok, results, dm = False, None, None
+        ok, results, dm, eval_results = False, None, None, None
         try:
             ec = ExecutorConfiguration(num_tasklets=4, chkp_temp_path=conf.get("chkp_temp_path", "/tmp/chkp"),
                                        chkp_commit_path=conf.get("chkp_commit_path", "/tmp/chkp/commit"))
@@ -137,13 +138,52 @@ class ETDolphinLauncher:
             finally:
                 if orchestrator is not None:
                     orchestrator.stop()
+            if conf.get("offline_model_eval"):
+                eval_results = _offline_evaluation(master, dm, workers, server_tc, worker_tc, local_tc)
             ok = True
         except BaseException:  # noqa: BLE001
             LOG.exception("stand-alone job failed")
         finally:
             master.close()
             transport.close()
-        return LauncherResult(ok, results, messages, dm)
+        res = LauncherResult(ok, results, messages, dm)
+        res.eval_results = eval_results
+        return res
+
+
+def _offline_evaluation(master: ETMaster, dm: DolphinMaster, execs, server_tc, worker_tc, local_tc) -> List[Any]:
+    """-offline_model_eval on a stand-alone job: after training, replay the per-epoch model checkpoints oldest first
+    and evaluate each against the input checkpoint / -test_data_path (ETDolphinLauncher.java:342-378,
+    ModelChkpManager.java:221-272; same replay as the job server's deferred evaluation)."""
+    ck = dm.chkp_manager
+    for tc in (server_tc, local_tc, worker_tc):          # the training tables make room for the restored ones
+        if tc is not None and master.has_table(tc.table_id):
+            master.get_table(tc.table_id).drop().get(timeout=120)
+    restored: List[str] = []
+
+    def drop_restored() -> None:
+        for tid in restored:
+            if master.has_table(tid):
+                master.get_table(tid).drop().get(timeout=120)
+        restored.clear()
+
+    def restore(i: int) -> bool:
+        drop_restored()
+        if i >= ck.num_chkps():
+            return False
+        master.create_table_from_chkp(ck.model_chkps[i], execs, table_id=server_tc.table_id).get(timeout=600)
+        restored.append(server_tc.table_id)
+        if local_tc is not None and i < len(ck.local_chkps):
+            master.create_table_from_chkp(ck.local_chkps[i], execs, table_id=local_tc.table_id).get(timeout=600)
+            restored.append(local_tc.table_id)
+        if not master.has_table(worker_tc.table_id) and ck.input_chkp:
+            master.create_table_from_chkp(ck.input_chkp, execs, table_id=worker_tc.table_id).get(timeout=600)
+        return True
+    out = dm.evaluate(execs, restore)
+    drop_restored()
+    if master.has_table(worker_tc.table_id):
+        master.get_table(worker_tc.table_id).drop().get(timeout=120)
+    return out
 
 
 def main_submit(app_path: str, app: ETDolphinConfiguration, argv: Sequence[str]) -> int:

@@ -603,3 +603,21 @@ def test_worker_that_trains_on_no_batch_does_not_fail_the_job_and_leases_yield_t
         assert js.et_master.task_units.num_waits > 0                  # unit barriers were on (leases were not)
     finally:
         js.stop(kill=True)
+
+
+def test_standalone_offline_model_evaluation_replays_every_epoch_checkpoint():
+    """`run_mlr.sh ... -offline_model_eval true`: after training the stand-alone launcher replays the per-epoch
+    checkpoints oldest first and evaluates each (one "Model eval progress" line and one metric set per epoch)."""
+    tmp = tempfile.mkdtemp(prefix="hbeval")
+    data = write_mlr_sample(os.path.join(tmp, "sample_mlr"), n=80)
+    test = write_mlr_sample(os.path.join(tmp, "sample_mlr_test"), n=40, seed=7)
+    res = ETDolphinLauncher.launch(mlr.APP, ["-input", data, "-test_data_path", test, "-max_num_epochs", "3",
+                                             "-num_mini_batches", "4", "-num_worker_blocks", "4", "-num_server_blocks", "8",
+                                             "-step_size", "0.05", "-classes", "4", "-features", "64",
+                                             "-num_dolphin_workers", "2", "-num_servers", "1",
+                                             "-offline_model_eval", "true",
+                                             "-chkp_temp_path", tmp + "/t", "-chkp_commit_path", tmp + "/c"])
+    assert res.ok, res.messages
+    assert [m for m in res.messages if m.startswith("Model eval progress")] == \
+        [f"Model eval progress: [{i}], JobId: MLR-0" for i in (1, 2, 3)]
+    assert res.eval_results is not None and len(res.eval_results) == 2
