@@ -562,7 +562,9 @@ class DolphinMaster:
         self.mini_batch_controller = MiniBatchController(epochs, nmb, int(p.get("clock_slack", 0)), self.sender)
         on_epoch = None
         if p.get("offline_model_eval"):
-            on_epoch = lambda e: self._m.pool.submit(self.chkp_manager.create_checkpoint)  # noqa: E731
+            self._chkp_futs: List[Any] = []
+            on_epoch = lambda e: self._chkp_futs.append(  # noqa: E731
+                self._m.pool.submit(self.chkp_manager.create_checkpoint))
         self.progress_tracker = BatchProgressTracker(self.job_id, epochs, nmb, self.report, on_epoch)
         self.metric_manager.start_metric_collection()
         for ex in workers:
@@ -592,6 +594,13 @@ class DolphinMaster:
             raise RuntimeError(f"job {self.job_id}: worker tasklets failed: " +
                                "; ".join(f"{r.executor_id}: {r.error}" for r in failed))
         if p.get("offline_model_eval"):
+            # the per-epoch checkpoints run on the driver pool: let the last ones finish before anybody evaluates
+            # (or drops the tables they are reading)
+            for f in getattr(self, "_chkp_futs", []):
+                try:
+                    f.result(timeout=600)
+                except Exception as e:  # noqa: BLE001
+                    LOG.warning("[%s] a per-epoch checkpoint failed: %s", self.job_id, e)
             self.chkp_manager.checkpoint_input()
         return [r.result for r in results]
 
