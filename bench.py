@@ -1,25 +1,37 @@
 #!/usr/bin/env python
-"""Headline benchmark: MLR 1M-feature x 1000-class, model sharded over N B200s (BASELINE.json).
+"""Headline benchmark: MLR 1M-feature x 1000-class, model sharded over N B200s (BASELINE.json config 2).
 
-Metric: mini-batches/sec, whole box (N workers, one mini-batch per worker per step), device
-timed, max over ranks.  Every GPU is both a shard owner and a worker (the co-located mode of the
-reference job server, DolphinJobEntity.java:80-82).  One step of one worker =
-  PULL  rows of the mini-batch's features from the owners' HBM (fused with the sparse dot + softmax)
-  PUSH  one reduce-add row per distinct feature into the owners' HBM (fused with `w += delta`)
-  SSP   device clock publish/wait (clock_slack, default 0 like the reference)
-Weak scaling: per-GPU work (one mini-batch of --batch instances) is fixed as N grows.
+Metric: mini-batches/sec, whole box (N workers, one mini-batch per worker per step), device timed
+(CUDA events), max over ranks.  Every GPU is both a shard owner and a worker (the co-located mode of the
+reference job server, DolphinJobEntity.java:80-82).  Weak scaling: per-GPU work (one mini-batch of
+--batch instances) is fixed as N grows.
+
+BASELINE.json's headline string says "MLR 1M x 1M": a 1M-feature x 1M-class fp32 model is 4 TB, more than
+the 1.44 TB of HBM of an 8xB200 box, so the shape that is run is the one BASELINE.json's config list names
+(1M features x 1000 classes, 3.81 GiB); `config.interpretation` says so in every result line.
+
+Both data-plane modes run at EVERY N and both land in the result line (`modes`):
+  pull : PS pull/push -- workers read / reduce-add 4 KB model rows in the owners' HBM over NVLink
+  ship : owners compute the sparse dot; only [B, C] activations cross NVLink, as NVLS (multimem)
+         reduce-scatter / all-gather fused into the kernels (models/mlr_ship.py)
+The headline `value` is the better mode's median over --repeats timed regions of --steps steps each.
+Two NCCL comparators run in the same process afterwards and give `vs_baseline`:
+  nccl_rs_ag     : the same kernels with NCCL reduce_scatter / all_gather of the [B, C] activations
+  nccl_allreduce : replicated model, dense-gradient all-reduce (the baseline BASELINE.json names)
 
   python bench.py --gpus 1 --steps 20 --warmup 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
       --master-port P bench.py --gpus N --steps K --warmup W
   --impl reference : the unmodified reference (Java/REEF; not installable here -> "unavailable")
-  --impl nccl      : NCCL all-reduce baseline of the same app (replicated model, dense gradient)
+  --impl nccl      : only the NCCL arms
+  --config nmf|lda|multijob|dense : the other BASELINE configs (benchmarks/*.py) behind the same entry point
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -35,31 +47,35 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="harmony", choices=["harmony", "reference", "nccl"])
+    ap.add_argument("--config", default="mlr", choices=["mlr", "nmf", "lda", "multijob", "dense"])
     ap.add_argument("--features", type=int, default=1_000_000)
     ap.add_argument("--classes", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=4096, help="instances per mini-batch per worker")
     ap.add_argument("--nnz", type=int, default=100, help="non-zeros per instance")
     ap.add_argument("--num_server_blocks", type=int, default=1024)
     ap.add_argument("--step_size", type=float, default=1e-4)
+    ap.add_argument("--lambda", dest="lam", type=float, default=0.0, help="L2 regularisation (lazy scale)")
     ap.add_argument("--clock_slack", type=int, default=0)
     ap.add_argument("--distinct_batches", type=int, default=4)
     ap.add_argument("--zipf", type=float, default=0.0)
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of --steps steps (median reported)")
     ap.add_argument("--no_e2e", action="store_true")
-    ap.add_argument("--ship_phases", action="store_true",
-                    help="ship mode: also time the five parts of a step (partial fwd / barrier / softmax+bcast / "
-                         "barrier / update) with CUDA events, outside the headline region")
-    ap.add_argument("--mode", default="auto", choices=["auto", "pull", "ship"],
-                    help="pull: workers read/reduce model rows over NVLink (PS pull/push); "
-                         "ship: owners compute the sparse dot, only [B,C] activations cross NVLink; "
-                         "auto: ship when N > 1")
-    return ap.parse_args()
+    ap.add_argument("--no_nccl", action="store_true", help="skip the in-process NCCL comparators")
+    ap.add_argument("--ship_impl", default="v2", choices=["v1", "v2"],
+                    help="v2: NVLS multimem + tile flags (3 launches); v1: round-1 peer stores + device barriers")
+    ap.add_argument("--no_nvls", action="store_true", help="ship v2 over unicast peer loads/stores")
+    ap.add_argument("--mode", default="both", choices=["both", "auto", "pull", "ship"])
+    args, rest = ap.parse_known_args()
+    args.rest = rest
+    return args
 
 
 class ClockSampler:
-    """nvidia-smi SM clocks + throttle reasons sampled DURING the timed region."""
+    """SM clocks + throttle reasons sampled DURING the timed region (NVML in-process, nvidia-smi fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index: int) -> None:
         self.gpu = gpu_index
@@ -67,12 +83,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
-    # NVML bit masks of nvmlDeviceGetCurrentClocksEventReasons (nvml.h)
-    NVML_REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
-
     def _nvml_sampler(self):
-        """Fast path: in-process NVML queries (~0.1 ms each) so even a 15 ms timed region gets several samples.
-        Returns a zero-argument callable producing one sample in the nvidia-smi column layout, or None."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -91,7 +102,7 @@ class ClockSampler:
                 flag = lambda nm: "Active" if mask & self.NVML_REASONS[nm] else "Not Active"  # noqa: E731
                 return [str(sm), str(mx), f"{pw:.1f}", flag("hw_slowdown"), flag("hw_thermal_slowdown"),
                         flag("sw_thermal_slowdown"), flag("sw_power_cap")]
-            sample()                      # fail here, not in the loop
+            sample()
             return sample
         except Exception:  # noqa: BLE001
             return None
@@ -117,6 +128,7 @@ class ClockSampler:
                 self._stop.wait(0.003 if fast else 0.1)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
+        return self
 
     def stop(self):
         self._stop.set()
@@ -124,6 +136,7 @@ class ClockSampler:
             self._t.join(timeout=6)
         sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
         mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
@@ -131,12 +144,13 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples), "source": getattr(self, "source", None)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.samples),
+                "source": getattr(self, "source", None)}
 
 
 def reference_arm(args):
     """The reference is 100% Java 8 / Maven / Apache REEF (no setup.py / pyproject): it cannot be
-    pip-installed into baseline/_ref and there is no JDK in the image (see DESIGN.md)."""
+    pip-installed into baseline/_ref and there is no JDK in the image (see DESIGN.md section 6)."""
     ok = os.path.isdir(os.path.join(ROOT, "baseline", "_ref")) and any(
         n.endswith(".jar") for _, _, fs in os.walk(os.path.join(ROOT, "baseline", "_ref")) for n in fs)
     if not ok or subprocess.run(["which", "java"], capture_output=True).returncode != 0:
@@ -148,10 +162,40 @@ def reference_arm(args):
     return 0
 
 
+def other_config(args):
+    """BASELINE configs 3-5 + the dense tcgen05 path live in benchmarks/*.py; run them behind this entry point
+    (same flags, same one-JSON-line contract) so that the driver can reach them."""
+    import runpy
+    script = {"nmf": "bench_nmf.py", "lda": "bench_lda.py", "multijob": "bench_multijob.py",
+              "dense": "bench_dense.py"}[args.config]
+    path = os.path.join(ROOT, "benchmarks", script)
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    if args.config == "multijob":
+        argv = ["--executors", str(args.gpus)] + args.rest
+    else:
+        argv = ["--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + args.rest
+        if args.impl == "nccl":
+            argv += ["--impl", "nccl"]
+    sys.argv = [path] + argv
+    runpy.run_path(path, run_name="__main__")
+    return 0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config != "mlr":
+        return other_config(args)
 
     import numpy as np
     import torch
@@ -169,12 +213,14 @@ def main():
     from harmony_b200 import ops
     from harmony_b200.et.config import TableConfiguration
     from harmony_b200.et.device_table import DeviceTable
-    from harmony_b200.models.mlr import MLRDeviceModel, synthetic_batch
+    from harmony_b200.models.mlr import MLRBatch, MLRDeviceModel, synthetic_batch
+    from harmony_b200.models.mlr_ship import MLRShipModel, MLRShipModelV1, RoutedBatch, route_batches
     from harmony_b200.parallel.device_clock import DeviceClock
     from harmony_b200.parallel.peer import PeerArena, PeerGroup
 
+    nat = ops.native()
     group = PeerGroup.from_env()
-    F, C, B = args.features, args.classes, args.batch
+    F, C, B, K, R = args.features, args.classes, args.batch, args.steps, max(1, args.repeats)
 
     def barrier_sync():
         torch.cuda.synchronize(dev)
@@ -189,143 +235,223 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # synthetic input blocks (one block == one mini-batch), pinned on the host + resident in HBM
-    host_batches = [synthetic_batch(B, F, C, args.nnz, seed=1000 * rank + i, zipf=args.zipf).pin()
-                    for i in range(args.distinct_batches)]
-    dev_batches = [hb.to(dev) for hb in host_batches]
-    h2d_bytes = host_batches[0].nbytes()
+    def measure(step, batches, warmup, steps, repeats, stats=None):
+        """`repeats` timed regions of exactly `steps` steps, each bracketed by barrier + synchronize on both sides,
+        timed with CUDA events on the launching stream, max over ranks.  Returns (list of ms per region,
+        clocks sampled during the regions, launches of ONE region)."""
+        for i in range(warmup):
+            step(batches[i % len(batches)])
+        barrier_sync()
+        sampler = ClockSampler(local_rank).start() if rank == 0 else None
+        regions, launches = [], 0
+        for _ in range(repeats):
+            if stats is not None:
+                stats.zero_()
+            ops.reset_launches()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier_sync()
+            ev0.record()
+            for i in range(steps):
+                step(batches[i % len(batches)])
+            ev1.record()
+            barrier_sync()
+            regions.append(max_over_ranks(ev0.elapsed_time(ev1)))
+            launches = ops.launches()
+        return regions, (sampler.stop() if sampler else None), launches
 
-    mode = args.mode if args.mode != "auto" else ("ship" if world > 1 else "pull")
-    if args.impl != "harmony":
-        mode = "n/a"
-    if args.impl == "harmony":
-        arena = PeerArena(local_rank, group, segment_bytes=2 << 30)
-        conf = TableConfiguration(table_id="model_table0", dense=True, capacity=F, row_dim=C,
-                                  num_total_blocks=args.num_server_blocks, is_ordered=False, backend="device",
-                                  update_function={"name": "add", "params": {"init": "gaussian", "std": 0.001,
-                                                                              "seed": 42}})
-        table = DeviceTable(conf, arena, group)
-        model = MLRDeviceModel(table, C, args.step_size, max_batch=B)
-        clock = DeviceClock(arena, group, slack=args.clock_slack)
-        if mode == "ship":
-            from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
-            ship = MLRShipModel(table, arena, group, clock, C, args.step_size, B)
-            # 2-D partition of the input: every rank derives its owner-side slices of ALL workers'
-            # blocks (same synthetic seeds on every rank: no exchange needed for the benchmark)
-            routed_host = []
-            for i in range(args.distinct_batches):
-                allw = [host_batches[i] if r == rank else
-                        synthetic_batch(B, F, C, args.nnz, seed=1000 * r + i, zipf=args.zipf) for r in range(world)]
-                routed_host.append(route_batches(table, allw, rank).pin())
-            host_batches = routed_host
-            dev_batches = [rb.to(dev) for rb in host_batches]
-            h2d_bytes = host_batches[0].nbytes()
-            model.stats = ship.stats
+    def summarise(regions, steps):
+        per = sorted(r / steps for r in regions)
+        med = statistics.median(per)
+        return {"ms_per_step": round(med, 4), "ms_min": round(per[0], 4), "ms_max": round(per[-1], 4),
+                "value": round(world / (med / 1e3), 3), "regions": len(per)}
 
-            def step(batch):
-                ship.step(batch)
-            parallelism = (f"ps-sharded-model x{world} (co-located), owner-side sparse dot; [B,C] activations "
-                           f"reduce-scattered / all-gathered over peer memory; {args.num_server_blocks} blocks")
+    # ---------------- model + synthetic input (one block == one mini-batch), pinned host + resident HBM ------------
+    arena = PeerArena(local_rank, group, segment_bytes=2 << 30)
+    conf = TableConfiguration(table_id="model_table0", dense=True, capacity=F, row_dim=C,
+                              num_total_blocks=args.num_server_blocks, is_ordered=False, backend="device",
+                              update_function={"name": "add", "params": {"init": "gaussian", "std": 0.001, "seed": 42}})
+    table = DeviceTable(conf, arena, group)
+    stride = table.row_stride
+    row_bytes = stride * 4
+    host_pull = [synthetic_batch(B, F, C, args.nnz, seed=1000 * rank + i, zipf=args.zipf).pin()
+                 for i in range(args.distinct_batches)]
+    host_ship = []
+    for i in range(args.distinct_batches):      # every rank derives its owner-side slices of ALL workers' blocks
+        allw = [host_pull[i] if r == rank else synthetic_batch(B, F, C, args.nnz, seed=1000 * r + i, zipf=args.zipf)
+                for r in range(world)]
+        host_ship.append(route_batches(table, allw, rank).pin())
+    want = {"both": ["ship", "pull"], "auto": ["ship"] if world > 1 else ["pull"], "pull": ["pull"],
+            "ship": ["ship"]}[args.mode]
+    if args.impl == "nccl":
+        want = []
+
+    modes, runners = {}, {}
+    # ---------------- ship mode ----------------
+    if "ship" in want or args.impl == "nccl" or not args.no_nccl:
+        dev_ship = [rb.to(dev) for rb in host_ship]
+    if "ship" in want:
+        clock_s = DeviceClock(arena, group, slack=0)
+        if args.ship_impl == "v2" and stride <= 1024:
+            ship = MLRShipModel(table, arena, group, None, C, args.step_size, B, multicast=not args.no_nvls,
+                                lam=args.lam)
         else:
-            def step(batch):
-                clock.wait()
-                model.forward(batch, True)
-                model.backward_push(batch)
-                clock.tick()
-            parallelism = (f"ps-sharded-model x{world} (co-located workers), rows pulled / pushed over peer "
-                           f"memory; {args.num_server_blocks} blocks")
-    else:  # NCCL all-reduce baseline: replicated model, dense gradient all-reduce, dense SGD update
-        arena = PeerArena(local_rank, PeerGroup(0, 1, None), segment_bytes=2 << 30)
-        one = PeerGroup(0, 1, None)
-        conf = TableConfiguration(table_id="model_replica", dense=True, capacity=F, row_dim=C,
-                                  num_total_blocks=1, is_ordered=True, backend="device",
-                                  update_function={"name": "add", "params": {"init": "gaussian", "std": 0.001,
-                                                                              "seed": 42}})
-        table = DeviceTable(conf, arena, one)
-        gconf = TableConfiguration(table_id="grad_replica", dense=True, capacity=F, row_dim=C, num_total_blocks=1,
-                                   is_ordered=True, backend="device", update_function="add")
-        gtable = DeviceTable(gconf, arena, one)
-        model = MLRDeviceModel(table, C, args.step_size, max_batch=B)
-        gmodel = MLRDeviceModel(gtable, C, args.step_size, max_batch=B)
-        gmodel._D = model._D
-        W, G = table.local_block(0), gtable.local_block(0)
+            ship = MLRShipModelV1(table, arena, group, clock_s, C, args.step_size, B)
+        regions, clocks, launches = measure(ship.step, dev_ship, args.warmup, K, R, ship.stats)
+        if hasattr(ship, "check"):
+            ship.check()
+        clock_s.check()
+        m = summarise(regions, K)
+        uniq_o = int(np.mean([hb.routed.uniq_feat.numel() for hb in host_ship]))
+        nnz_o = int(np.mean([hb.routed.csr_col.numel() for hb in host_ship]))
+        # K1: row gathers + P store; K2: P read by the switch + D landing; K3: row read-modify-write (D re-reads hit L2)
+        hbm = (nnz_o + 2 * uniq_o + 3 * world * B) * row_bytes
+        egress = (world - 1) * B * row_bytes + (B * row_bytes if world > 1 else 0)
+        m.update({"clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(float(ship.stats[0]) / (K * B), 5),
+                  "impl": args.ship_impl if stride <= 1024 else "v1", "nvls_multicast": bool(getattr(ship, "nvls", False)),
+                  "hbm_bytes_per_step_per_gpu": int(hbm), "nvlink_egress_bytes_per_step_per_gpu": int(egress),
+                  "parallelism": (f"ps-sharded-model x{world} (co-located), owner-side sparse dot; [B,C] activations "
+                                  f"reduce-scattered (multimem.ld_reduce) / all-gathered (multimem.st) in the kernels")})
+        reps = min(K, 5)                    # serialised per-kernel timing, outside the headline regions
+        acc = {}
+        for i in range(reps):
+            barrier_sync()
+            for k, v in ship.step_timed(dev_ship[i % len(dev_ship)]).items():
+                acc[k] = acc.get(k, 0.0) + v
+        m["phases_serialised_ms"] = {k: round(max_over_ranks(v / reps), 4) for k, v in sorted(acc.items())}
+        modes["ship"], runners["ship"] = m, (ship.step, host_ship, ship.stats)
 
-        def step(batch):
-            G.zero_()
-            model.forward(batch, True)
-            gmodel.backward_push(batch)           # dense local gradient (pre-scaled by -step)
-            if world > 1:
-                dist.all_reduce(G)
-            W.add_(G)
-        clock = None
-        parallelism = f"dp{world} replicated model + NCCL all-reduce of the dense gradient"
+    # ---------------- pull mode ----------------
+    if "pull" in want:
+        dev_pull = [hb.to(dev) for hb in host_pull]
+        model = MLRDeviceModel(table, C, args.step_size, lam=args.lam, max_batch=B)
+        clock_p = DeviceClock(arena, group, slack=args.clock_slack)
 
-    # ---------------- device-timed run ----------------
-    for i in range(args.warmup):
-        step(dev_batches[i % len(dev_batches)])
-    barrier_sync()
-    ops.reset_launches()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    model.stats.zero_()
-    barrier_sync()
-    ev0.record()
-    for i in range(args.steps):
-        step(dev_batches[i % len(dev_batches)])
-    ev1.record()
-    barrier_sync()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = ops.launches()
-    clocks = sampler.stop() if rank == 0 else None
-    if clock is not None:
-        clock.check()
-    loss_dev = float(model.stats[0]) / max(1, args.steps * B)
-
-    # ---------------- per-phase device timing (outside the headline region) ----------------
-    phase = None
-    if args.impl == "harmony" and mode == "pull":
+        def pull_step(batch):
+            clock_p.wait()
+            model.step(batch, B * world)
+            clock_p.tick()
+        regions, clocks, launches = measure(pull_step, dev_pull, args.warmup, K, R, model.stats)
+        clock_p.check()
+        m = summarise(regions, K)
+        uniq = int(np.mean([hb.uniq_feat.numel() for hb in host_pull]))
+        nnz = B * args.nnz
+        remote = (world - 1) / world
+        m.update({"clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(float(model.stats[0]) / (K * B), 5),
+                  "hbm_bytes_per_step_per_gpu": int((nnz + 2 * uniq) * row_bytes + 2 * B * row_bytes),
+                  "nvlink_egress_bytes_per_step_per_gpu": int(uniq * row_bytes * remote),
+                  "nvlink_ingress_bytes_per_step_per_gpu": int(nnz * row_bytes * remote),
+                  "parallelism": f"ps-sharded-model x{world} (co-located workers), 4 KB rows pulled / pushed over peer memory"})
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t_pull = t_push = 0.0
-        reps = min(args.steps, 10)
+        reps = min(K, 5)
         for i in range(reps):
-            b = dev_batches[i % len(dev_batches)]
+            b = dev_pull[i % len(dev_pull)]
             barrier_sync()
             evs[0].record(); model.forward(b, True); evs[1].record(); model.backward_push(b); evs[2].record()
             torch.cuda.synchronize(dev)
             t_pull += evs[0].elapsed_time(evs[1]); t_push += evs[1].elapsed_time(evs[2])
-        phase = {"pull_fwd_ms": max_over_ranks(t_pull / reps), "bwd_push_ms": max_over_ranks(t_push / reps)}
-    elif args.impl == "harmony" and mode == "ship" and args.ship_phases:
-        reps = min(args.steps, 10)
-        acc = {}
-        for i in range(reps):
-            barrier_sync()
-            for k, v in ship.step_timed(dev_batches[i % len(dev_batches)]).items():
-                acc[k] = acc.get(k, 0.0) + v
-        phase = {k: max_over_ranks(v / reps) for k, v in sorted(acc.items())}
+        pf, bp = max_over_ranks(t_pull / reps), max_over_ranks(t_push / reps)
+        m["phases_serialised_ms"] = {"pull_fwd_ms": round(pf, 4), "bwd_push_ms": round(bp, 4)}
+        m["pull_GBps_per_gpu"] = round(nnz * row_bytes / (pf / 1e3) / 1e9, 1)
+        m["push_GBps_per_gpu"] = round(uniq * row_bytes / (bp / 1e3) / 1e9, 1)
+        if world > 1:
+            m["pull_nvlink_GBps_per_gpu"] = round(nnz * row_bytes * remote / (pf / 1e3) / 1e9, 1)
+            m["push_nvlink_GBps_per_gpu"] = round(uniq * row_bytes * remote / (bp / 1e3) / 1e9, 1)
+            m["pull_nvlink_frac_of_770"] = round(m["pull_nvlink_GBps_per_gpu"] / 770.0, 3)
+            m["push_nvlink_frac_of_770"] = round(m["push_nvlink_GBps_per_gpu"] / 770.0, 3)
+        modes["pull"], runners["pull"] = m, (pull_step, host_pull, model.stats)
 
-    # ---------------- end-to-end: pinned host -> H2D every step, loss D2H every step ----------------
+    hbm_peak, peak_src = peaks()
+    for m in modes.values():
+        m["hbm_GBps_per_gpu"] = round(m["hbm_bytes_per_step_per_gpu"] / (m["ms_per_step"] / 1e3) / 1e9, 1)
+        m[f"hbm_frac_of_{peak_src}"] = round(m["hbm_GBps_per_gpu"] / hbm_peak, 3)
+        if world > 1:
+            m["nvlink_egress_GBps_per_gpu"] = round(m["nvlink_egress_bytes_per_step_per_gpu"] / (m["ms_per_step"] / 1e3) / 1e9, 1)
+            m["nvlink_egress_frac_of_770"] = round(m["nvlink_egress_GBps_per_gpu"] / 770.0, 3)
+
+    # ---------------- NCCL comparators (same process, same clocks, same box) ----------------
+    baselines = {}
+    if not args.no_nccl or args.impl == "nccl":
+        rows = world * B
+        P = torch.zeros((rows, stride), device=dev)
+        Lb = torch.zeros((B, stride), device=dev) if world > 1 else P
+        Dl = torch.zeros((B, stride), device=dev)
+        Dall = torch.zeros((rows, stride), device=dev) if world > 1 else Dl
+        stats_n = torch.zeros(2, device=dev)
+        err_n = torch.zeros(1, dtype=torch.int32, device=dev)
+        lptr = torch.tensor([Lb.data_ptr()], dtype=torch.int64, device=dev)
+        dptr = torch.tensor([Dl.data_ptr()], dtype=torch.int64, device=dev)
+
+        def nccl_rs_ag_step(rb):
+            bp_, rpb, st_, _dim, mode_ = table.view()
+            r = rb.routed
+            nat.ship_forward(bp_, rpb, st_, C, mode_, r.csr_ptr, r.csr_col, r.csr_val, world, B, 32, P.data_ptr(), 0,
+                             None, 0)
+            if world > 1:
+                dist.reduce_scatter_tensor(Lb, P)
+            nat.ship_softmax(0, lptr, 0, 0, dptr, 0, st_, rb.labels, C, args.step_size, 1.0, 32, 0, 0, None, stats_n,
+                             err_n)
+            if world > 1:
+                dist.all_gather_into_tensor(Dall, Dl)
+            nat.mlr_backward_push(bp_, rpb, st_, C, mode_, r.uniq_feat, r.feat_ptr, r.samp, r.xval, Dall, False)
+            ops.count_launch(3)
+        if stride <= 1024:
+            regions, clocks, launches = measure(nccl_rs_ag_step, dev_ship, args.warmup, K, min(R, 3), stats_n)
+            b = summarise(regions, K)
+            b.update({"clocks": clocks, "what": "same three kernels, NCCL reduce_scatter + all_gather of the [B,C] "
+                                                "activations between them (2 NCCL calls per step)"})
+            baselines["nccl_rs_ag"] = b
+        del P, Lb, Dl, Dall
+
+        # dense-gradient all-reduce (the baseline BASELINE.json names): replicated model, local dense gradient
+        one = PeerGroup(0, 1, None)
+        arena1 = PeerArena(local_rank, one, segment_bytes=2 << 30, kind="ipc")
+        mk = lambda tid, init: DeviceTable(TableConfiguration(  # noqa: E731
+            table_id=tid, dense=True, capacity=F, row_dim=C, num_total_blocks=1, is_ordered=True, backend="device",
+            update_function={"name": "add", "params": init}), arena1, one)
+        wt = mk("model_replica", {"init": "gaussian", "std": 0.001, "seed": 42})
+        gt = mk("grad_replica", {})
+        wm = MLRDeviceModel(wt, C, args.step_size, max_batch=B)
+        gm = MLRDeviceModel(gt, C, args.step_size, max_batch=B)
+        gm._D = wm._D
+        Wd, Gd = wt.local_block(0), gt.local_block(0)
+        dev_pull_n = [hb.to(dev) for hb in host_pull]
+
+        def nccl_allreduce_step(batch):
+            Gd.zero_()
+            wm.forward(batch, True)
+            gm.backward_push(batch)           # dense local gradient (pre-scaled by -step)
+            if world > 1:
+                dist.all_reduce(Gd)
+            Wd.add_(Gd)
+        ks = max(2, min(K, 5))
+        regions, clocks, _ = measure(nccl_allreduce_step, dev_pull_n, 2, ks, 2, wm.stats)
+        b = summarise(regions, ks)
+        b.update({"clocks": clocks, "steps": ks, "what": "dp replicated model + NCCL all-reduce of the dense "
+                                                          f"{F * row_bytes / 2**30:.2f} GiB gradient + dense W += G"})
+        baselines["nccl_allreduce"] = b
+        wt.close(); gt.close(); arena1.close()
+
+    # ---------------- headline + end-to-end (pinned host -> H2D every step, loss D2H every step) ----------------
+    if modes:
+        head = min(modes, key=lambda k: modes[k]["ms_per_step"])
+    else:
+        head = None
     e2e = None
-    if not args.no_e2e:
-        from harmony_b200.models.mlr import MLRBatch
+    if head is not None and not args.no_e2e:
+        step, host_batches, stats = runners[head]
 
         def rebuild(views):
-            if mode == "ship":
-                from harmony_b200.models.mlr_ship import RoutedBatch
-                return RoutedBatch(MLRBatch(*views[:8]), views[8])
-            return MLRBatch(*views)
+            return RoutedBatch(MLRBatch(*views[:8]), views[8]) if head == "ship" else MLRBatch(*views)
         maxn = [max(t.numel() for t in ts) for ts in zip(*[hb.tensors() for hb in host_batches])]
         staging = [[torch.empty(n, dtype=t.dtype, device=dev) for n, t in zip(maxn, host_batches[0].tensors())]
                    for _ in range(2)]                       # double-buffered device staging
-
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
         ready = [torch.cuda.Event(), torch.cuda.Event()]
+        h2d_bytes = host_batches[0].nbytes()
 
         def prefetch(i):
-            """H2D of step i's inputs from pinned host memory on the copy stream (double buffered: the
-            buffer was last read by step i-2, whose loss has already been read back => it is free)."""
             hbt = host_batches[i % len(host_batches)]
             views = []
             with torch.cuda.stream(copy_stream):
@@ -342,51 +468,60 @@ def main():
             for i in range(n):
                 views = nxt
                 main_stream.wait_event(ready[i % 2])        # this step's inputs have landed
-                model.stats.zero_()
+                stats.zero_()
                 step(rebuild(views))
                 if i + 1 < n:
                     nxt = prefetch(i + 1)                   # overlaps with the kernels of step i
-                last = float(model.stats.cpu()[0])          # D2H of this step's loss (syncs the step)
+                last = float(stats.cpu()[0])                # D2H of this step's loss (syncs the step)
             return last
         e2e_run(max(3, args.warmup))
-        barrier_sync()
-        t0 = time.perf_counter()
-        last_loss = e2e_run(args.steps)
-        barrier_sync()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        e2e = {"value": round(world * args.steps / (e2e_ms / 1e3), 3), "unit": "mini-batches/s",
+        times = []
+        for _ in range(min(R, 3)):
+            barrier_sync()
+            t0 = time.perf_counter()
+            last_loss = e2e_run(K)
+            barrier_sync()
+            times.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+        e2e_ms = statistics.median(times)
+        e2e = {"value": round(world * K / (e2e_ms / 1e3), 3), "unit": "mini-batches/s", "mode": head,
                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 8,
-               "ms_per_step": round(e2e_ms / args.steps, 4), "last_loss_per_instance": round(last_loss / B, 5)}
+               "ms_per_step": round(e2e_ms / K, 4), "last_loss_per_instance": round(last_loss / B, 5),
+               "api": "MLRShipModel.step(RoutedBatch)" if head == "ship" else "MLRDeviceModel.step(MLRBatch)"}
 
     if rank == 0:
-        value = world * args.steps / (ms / 1e3)
-        uniq = int(np.mean([(hb.routed if mode == "ship" else hb).uniq_feat.numel() for hb in host_batches]))
-        nnz = B * args.nnz
-        row_bytes = table.row_stride * 4
-        remote_frac = (world - 1) / world
+        best_nccl = max((b["value"] for b in baselines.values()), default=None)
+        if head is not None:
+            h = modes[head]
+            value, ms, clocks, launches = h["value"], h["ms_per_step"], h["clocks"], h["gpu_launches"]
+        else:       # --impl nccl
+            k = max(baselines, key=lambda n: baselines[n]["value"])
+            value, ms, clocks, launches = baselines[k]["value"], baselines[k]["ms_per_step"], baselines[k]["clocks"], 3 * K
         out = {
             "metric": "mini-batches/sec (whole box, device-timed, max over ranks), MLR 1M-feature x 1000-class",
-            "value": round(value, 3), "unit": "mini-batches/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": args.impl,
+            "value": value, "unit": "mini-batches/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (round(value / best_nccl, 3) if best_nccl and head is not None else None),
+            "dtype": "fp32", "data": "synthetic", "impl": args.impl,
             "config": {"model": f"MLR {F}-feature x {C}-class (fp32 master weights, {F * row_bytes / 2**30:.2f} GiB sharded)",
+                       "interpretation": "BASELINE.json headline 'MLR 1Mx1M' = its config-list entry 'MLR 1M-feature "
+                                         "1000-class' (a 1Mx1M fp32 model is 4 TB > the box's 1.44 TB of HBM)",
                        "global_batch": B * world, "batch_per_worker": B, "nnz_per_instance": args.nnz,
-                       "seq_len": None, "parallelism": parallelism, "mode": mode,
-                       "clock_slack": 0 if mode == "ship" else args.clock_slack,
-                       "l2_flush": "inputs larger than L2: ~%.2f GB of model rows touched per step per GPU vs 126 MB L2"
-                                   % ((nnz + uniq) * row_bytes / 1e9),
+                       "seq_len": None, "mode": head, "parallelism": modes[head]["parallelism"] if head else "nccl",
+                       "clock_slack": 0 if head == "ship" else args.clock_slack, "lambda": args.lam,
+                       "arena": arena.kind, "num_server_blocks": args.num_server_blocks,
+                       "timing": f"median of {R} regions of {K} steps; CUDA events; max over ranks",
+                       "l2_flush": "inputs larger than L2: >= %.2f GB of model rows touched per step per GPU vs 126 MB L2"
+                                   % (min(m["hbm_bytes_per_step_per_gpu"] for m in modes.values()) / 1e9 if modes else 0.0),
                        "sgd": "step_size %.1e, decay_rate 0.9 / decay_period 5 epochs (applied per epoch)" % args.step_size},
-            "clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(loss_dev, 5),
-            "phases": None if phase is None else {k: round(v, 4) for k, v in phase.items()}
-            if "pull_fwd_ms" not in phase else {
-                "pull_fwd_ms": round(phase["pull_fwd_ms"], 4), "bwd_push_ms": round(phase["bwd_push_ms"], 4),
-                "pull_GBps_per_gpu": round(nnz * row_bytes / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
-                "push_GBps_per_gpu": round(uniq * row_bytes / (phase["bwd_push_ms"] / 1e3) / 1e9, 1),
-                "pull_nvlink_GBps_per_gpu": round(nnz * row_bytes * remote_frac / (phase["pull_fwd_ms"] / 1e3) / 1e9, 1),
-                "push_nvlink_GBps_per_gpu": round(uniq * row_bytes * remote_frac / (phase["bwd_push_ms"] / 1e3) / 1e9, 1)},
-            "nvlink_bytes_per_step_per_gpu": int((2 * B * world * row_bytes if mode == "ship"
-                                                   else (nnz + uniq) * row_bytes) * remote_frac),
+            "clocks": clocks, "gpu_launches": launches,
+            "vs_baseline_what": "value / best in-process NCCL arm (BASELINE.md publishes no number; the reference is "
+                                "Java/REEF and cannot run here)",
+            "modes": modes, "baselines": baselines,
         }
+        if head is not None:
+            out["loss_per_instance"] = modes[head]["loss_per_instance"]
+            for bname, b in baselines.items():
+                out[f"vs_{bname}"] = round(value / b["value"], 3)
         if e2e is not None:
             out["e2e"] = e2e
         print(json.dumps(out))

@@ -9,8 +9,10 @@ gains four messages:
     TablePeerMap        driver -> executors : every owner's slab locations + IPC handles
     TableQuiesce/Resume driver -> executors : batch-granular access gate of ONE table (the device
                                               twin of the per-block ownership locks)
-    DeviceMoveRecv      driver -> receiver  : allocate slabs, P2P bulk copy on the side stream
-    DeviceOwnershipFlip driver -> executors : rewrite pointer-table entries, free old slabs
+    DeviceMoveAlloc     driver -> receiver  : allocate the slabs of a LIST of blocks
+    DeviceMoveSend      driver -> sender    : one bulk-TMA launch: old -> new slabs over NVLink + local snapshots
+    DeviceOwnershipFlip driver -> executors : rewrite pointer-table entries (one launch) + fence; nobody is stopped
+    DeviceMoveDrain     driver -> sender    : forward late updates (new += old - snapshot), free the old slabs
 
 Reference parity: Tables.initTable (Tables.java:79-133), OwnershipCache.update
 (OwnershipCache.java:195-244), MigrationExecutor (MigrationExecutor.java:134-414).
@@ -94,7 +96,7 @@ class DeviceBlock(Block):
     def multi_put(self, keys, values):
         import torch
         self._t.put_rows(torch.as_tensor(np.asarray(keys), dtype=torch.int64, device=self._t.device),
-                         torch.as_tensor(np.asarray(values), device=self._t.device).float())
+                         torch.as_tensor(np.asarray(values), device=self._t.device))   # put_rows keeps int32 bit-exact
 
     def put(self, key, value):
         old = self.get(key)
@@ -216,7 +218,7 @@ class DeviceTableImpl(TableImpl):
 
     def multi_put(self, keys, values) -> ResultFuture:
         t = self.device_table
-        self._gated(lambda: t.put_rows(self._keys(keys), self._vals(values).float()))
+        self._gated(lambda: t.put_rows(self._keys(keys), self._vals(values)))   # int32 tables: bit-exact path
         import torch
         torch.cuda.synchronize(t.device)
         return CompletedFuture(None)
@@ -309,29 +311,51 @@ class DeviceExecutor(Executor):
             comps.gate.release_write()
         self.send_to_driver({"type": "TableResumeAck", "op_id": m["op_id"], "table_id": m["table_id"]})
 
-    def _on_DeviceMoveRecv(self, m):
+    # ---- live device migration: alloc (receiver) / send (sender) / flip (everyone) / drain (sender) ----
+    def _on_DeviceMoveAlloc(self, m):
         self._cuda()
         comps = self.tables.get_components(m["table_id"])
-        locs = {b: comps.dtable.recv_block(b, self.device_ctx.side_stream) for b in m["block_ids"]}
-        self.send_to_driver({"type": "DeviceMoveRecvAck", "op_id": m["op_id"], "table_id": m["table_id"],
+        locs = comps.dtable.alloc_recv(m["block_ids"])
+        self.send_to_driver({"type": "DeviceMoveAllocAck", "op_id": m["op_id"], "table_id": m["table_id"],
                              "locs": locs})
+
+    def _on_DeviceMoveAbort(self, m):
+        self._cuda()
+        comps = self.tables.try_get_components(m["table_id"])
+        if comps is not None:
+            comps.dtable.abort_recv(m["block_ids"])
+        self.send_to_driver({"type": "DeviceMoveAbortAck", "op_id": m["op_id"], "table_id": m["table_id"]})
+
+    def _on_DeviceMoveSend(self, m):
+        self._cuda()
+        comps = self.tables.get_components(m["table_id"])
+        locs = {int(b): tuple(loc) for b, loc in m["locs"].items()}
+        ms = comps.dtable.send_blocks(locs, self.device_ctx.side_stream)
+        self.send_to_driver({"type": "DeviceMoveSendAck", "op_id": m["op_id"], "table_id": m["table_id"],
+                             "copy_ms": ms, "bytes": len(locs) * comps.dtable.block_bytes})
 
     def _on_DeviceOwnershipFlip(self, m):
         self._cuda()
         comps = self.tables.try_get_components(m["table_id"])
         if comps is not None:
-            for b, loc in m["locs"].items():
-                b = int(b)
+            locs = {int(b): tuple(loc) for b, loc in m["locs"].items()}
+            comps.dtable.flip_blocks(locs, m["new_owner"])       # one launch + fence; nobody is stopped
+            for b in locs:
                 old = comps.ownership.owners()[b]
-                comps.dtable.flip_block(b, m["new_owner"], tuple(loc))
-                # the device gate already excludes accessors: update the cache without the latch
                 comps.ownership._owners[b] = m["new_owner"]
                 with comps.ownership._meta_lock:
                     comps.ownership._num_blocks[old] = comps.ownership._num_blocks.get(old, 1) - 1
                     comps.ownership._num_blocks[m["new_owner"]] = comps.ownership._num_blocks.get(m["new_owner"], 0) + 1
             comps.block_store.sync_with_table()
-            self._sync_device()
         self.send_to_driver({"type": "DeviceOwnershipFlipAck", "op_id": m["op_id"], "table_id": m["table_id"]})
+
+    def _on_DeviceMoveDrain(self, m):
+        self._cuda()
+        comps = self.tables.get_components(m["table_id"])
+        n = comps.dtable.drain_blocks(m["block_ids"], self.device_ctx.side_stream)
+        comps.block_store.sync_with_table()
+        self.send_to_driver({"type": "DeviceMoveDrainAck", "op_id": m["op_id"], "table_id": m["table_id"],
+                             "forwarded": n})
 
     def close(self) -> None:
         super().close()

@@ -28,8 +28,6 @@ from .config import TableConfiguration
 from .partitioner import PART_HASHED, PART_ORDERED
 from .update_function import DEV_ADAGRAD, make_update_function
 
-_CHECK_KEYS = bool(os.environ.get("HB_CHECK_KEYS"))
-
 
 def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
@@ -74,9 +72,11 @@ class DeviceTable:
             if self.owners[b] == self.self_key:
                 self._alloc_block(b)
         # pointer table lives in the arena too (so that a migrating peer can flip it remotely)
-        self._ptr_tbl_ptr, tsi, toff = arena.alloc(self.num_blocks * 8)
-        self.block_ptrs = arena.tensor(self._ptr_tbl_ptr, [self.num_blocks], torch.int64)
-        self.block_ptrs.zero_()
+        # + 2 guard words written by hb::row_ptr when a kernel meets an out-of-range key (count, last key)
+        self._ptr_tbl_ptr, tsi, toff = arena.alloc((self.num_blocks + 2) * 8)
+        self._view_ptrs = arena.tensor(self._ptr_tbl_ptr, [self.num_blocks + 2], torch.int64)
+        self._view_ptrs.zero_()
+        self.block_ptrs = self._view_ptrs[: self.num_blocks]
         self._ptr_tbl_loc = (self.self_key, tsi, toff)
         self._peer_tbl_ptrs: Dict[Any, int] = {}
         if collective:
@@ -116,7 +116,7 @@ class DeviceTable:
         torch.cuda.synchronize(self.device)
 
     def ptrs_complete(self) -> bool:
-        return bool((self.block_ptrs != 0).all().item())
+        return bool((self.block_ptrs != 0).all().item())   # (guard words excluded: block_ptrs is the [:num_blocks] view)
 
     def _key_base_stride(self, b: int) -> Tuple[int, int]:
         return (b * self.rows_per_block, 1) if self.mode == PART_ORDERED else (b, self.num_blocks)
@@ -136,7 +136,7 @@ class DeviceTable:
     # ---- views ----
     def view(self) -> Tuple[torch.Tensor, int, int, int, int]:
         """(block_ptrs, rows_per_block, row_stride, row_dim, mode): the kernel-side TableView."""
-        return self.block_ptrs, self.rows_per_block, self.row_stride, self.row_dim, self.mode
+        return self._view_ptrs, self.rows_per_block, self.row_stride, self.row_dim, self.mode
 
     def local_block_ids(self) -> List[int]:
         return sorted(self._local_ptr)
@@ -154,18 +154,20 @@ class DeviceTable:
         return len(self._local_ptr) * self.block_bytes
 
     # ---- data plane ----
-    def _check_keys(self, keys: torch.Tensor) -> None:
-        """HB_CHECK_KEYS=1: validate keys before a kernel turns them into raw HBM addresses (costs a device sync per
-        call; the loaders already reject out-of-range indices, so this is a debugging aid for library users)."""
-        if _CHECK_KEYS and keys.numel():
-            lo, hi = int(keys.min()), int(keys.max())
-            if lo < 0 or hi >= self.conf.capacity:
-                raise IndexError(f"table {self.conf.table_id}: key range [{lo}, {hi}] outside [0, {self.conf.capacity})")
+    def check(self) -> None:
+        """Raise if any kernel of this GPU met an out-of-range key since the last check.  The kernels bounds-check
+        every key against the slab range in `hb::row_ptr` (count + clamp to key 0, no sync on the hot path); this
+        reads the two guard words behind the pointer table (one small D2H copy) and resets them."""
+        g = self._view_ptrs[self.num_blocks:].cpu()
+        if int(g[0]) != 0:
+            self._view_ptrs[self.num_blocks:].zero_()
+            raise IndexError(f"table {self.conf.table_id}: {int(g[0])} out-of-range key(s) reached a kernel "
+                             f"(last: {int(g[1])}, valid: [0, {self.conf.capacity})); they were clamped to key 0")
+
 
     def pull(self, keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """K1: gather rows by key from whichever GPU owns them."""
         from ..ops import count_launch
-        self._check_keys(keys)
         if out is None:
             out = torch.empty((keys.numel(), self.row_dim), dtype=self.torch_dtype, device=self.device)
         self._n.table_pull(*self.view(), keys, out)
@@ -178,94 +180,164 @@ class DeviceTable:
         fn = self.update_fn.device_fn
         assert fn is not None, f"update function {self.update_fn.name} has no device implementation"
         p = self.update_fn.device_params()
-        self._check_keys(keys)
         self._n.table_push(*self.view(), keys, deltas, fn, p["step"], p["lo"], p["hi"], p["eps"])
         count_launch()
 
     def push_sparse_i32(self, keys: torch.Tensor, topics: torch.Tensor, deltas: torch.Tensor) -> None:
         """K2+K5: LDA sparse (row, topic, delta) triples with clamp>=0 and nnz bookkeeping."""
         from ..ops import count_launch
-        self._check_keys(keys)
         self._n.table_push_sparse_i32(*self.view(), keys, topics, deltas, self.row_dim - 1)
         count_launch()
 
     def put_rows(self, keys: torch.Tensor, values: torch.Tensor) -> None:
+        """ASSIGN rows.  int32 tables (LDA counts) take a bit-exact integer path: converting the counts to float
+        and storing them through the float kernel would write IEEE-754 bit patterns into the int32 slab."""
         from ..ops import count_launch
-        self._check_keys(keys)
-        self._n.table_push(*self.view(), keys, values.contiguous(), 3, 0.0, 0.0, 0.0, 0.0)
+        if self.torch_dtype == torch.int32:
+            vals = (values.round() if values.is_floating_point() else values).to(torch.int32)
+            self._n.table_put_i32(*self.view(), keys, vals.contiguous())
+        else:
+            self._n.table_push(*self.view(), keys, values.float().contiguous(), 3, 0.0, 0.0, 0.0, 0.0)
         count_launch()
 
     def scale_local(self, factor: float) -> None:
-        """Owner-side decay of the local shard (L2 term of MLR applied at the owner)."""
-        for b in self._local_ptr:
-            self.local_block(b).mul_(factor)
-
-    # ---- elasticity: block migration (collective over the group) ----
-    def migrate_block(self, block: int, dst_rank: int, stream: Optional[torch.cuda.Stream] = None) -> None:
-        """Move `block` to `dst_rank`: slab copy by the receiver on a side stream, then the
-        pointer flip on every GPU.  Callers quiesce accessors of THIS table at a mini-batch
-        boundary (other jobs keep running; the copy overlaps their compute)."""
+        """Owner-side decay of the local shard (dense L2 term of MLR applied at the owner): ONE launch over the
+        list of local slabs.  BSP trainers avoid even that with the lazy scale (models/mlr.py)."""
         from ..ops import count_launch
-        src_rank = self.owners[block]
-        if src_rank == dst_rank:
+        if not self._local_ptr:
             return
-        new_loc = None
-        if self.rank == dst_rank:
-            p, si, off = self.arena.alloc(self.block_bytes)
-            new_loc = (self.self_key, si, off, self.arena.segment_info(si))
-        infos = self.group.all_gather_object(new_loc)
-        rr, si, off, handle = infos[dst_rank]
-        if self.rank == dst_rank:
-            src_va = int(self.block_ptrs[block].item())
-            s = stream or torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                self._n.migrate_copy(src_va, p, self.block_bytes)
-                count_launch()
-            s.synchronize()
-            self._local_ptr[block] = p
-        self.group.barrier()          # data has landed at the receiver
-        self.arena.map_peer(rr, si, handle)
-        new_va = self.arena.resolve(rr, si, off)
-        self.block_ptrs[block] = new_va   # ownership flip (local table of this GPU)
-        self._loc[block] = (rr, si, off)
-        self.owners[block] = dst_rank
-        torch.cuda.synchronize(self.device)
-        self.group.barrier()          # nobody references the old slab any more
-        if self.rank == src_rank:
-            self.arena.free(self._local_ptr.pop(block))
+        ptrs = torch.tensor([self._local_ptr[b] for b in sorted(self._local_ptr)], dtype=torch.int64,
+                            device=self.device)
+        self._n.scale_blocks(ptrs, self.block_bytes, float(factor))
+        count_launch()
 
-    # ---- non-collective migration primitives (driven by the job-server protocol) ----
-    def recv_block(self, block: int, stream: Optional[torch.cuda.Stream] = None) -> Tuple[Any, int, int, Dict[str, Any]]:
-        """Receiver half: allocate a slab and bulk-copy the block from its current owner's HBM
-        (peer mapping) on a side stream.  Returns the new location to broadcast."""
+    # ---- elasticity: LIVE block migration (no accessor is stopped) -------------------------------------------
+    # alloc (receiver) -> send (sender: ONE bulk-TMA launch for the whole list: old -> new over NVLink + old -> local
+    # snapshot) -> flip (every GPU: one launch rewrites its pointer-table entries, then a fence = the kernels that
+    # could still hold the old addresses have drained) -> drain (sender: new += old - snapshot, frees both).
+    # Pushes that race with the copy land either in the new slab (after the flip) or in the old one; the latter are
+    # forwarded by the drain, so additive update functions lose nothing (MigrationExecutor.java:134-295 gets the same
+    # guarantee by latching the block; redirected stale accesses = RemoteAccessOpHandler.java:225-231).
+    def alloc_recv(self, blocks: Sequence[int]) -> Dict[int, Tuple[Any, int, int, Dict[str, Any]]]:
+        """Receiver: allocate the slabs of `blocks`; returns block -> (owner key, segment, offset, segment info)."""
+        self._pending_recv = getattr(self, "_pending_recv", {})
+        locs, done = {}, []
+        try:
+            for b in blocks:
+                p, si, off = self.arena.alloc(self.block_bytes)
+                self._pending_recv[int(b)] = p
+                done.append(int(b))
+                locs[int(b)] = (self.self_key, si, off, self.arena.segment_info(si))
+        except Exception:
+            self.abort_recv(done)
+            raise
+        return locs
+
+    def abort_recv(self, blocks: Sequence[int]) -> None:
+        for b in blocks:
+            p = getattr(self, "_pending_recv", {}).pop(int(b), None)
+            if p is not None:
+                self.arena.free(p)
+
+    def _resolve_locs(self, locs) -> Dict[int, int]:
+        out = {}
+        for b, (rr, si, off, handle) in locs.items():
+            self.arena.map_peer(rr, si, handle)
+            out[int(b)] = self.arena.resolve(rr, si, off)
+        return out
+
+    def _i64(self, xs) -> torch.Tensor:
+        return torch.tensor(list(xs), dtype=torch.int64, device=self.device)
+
+    def send_blocks(self, locs, stream: Optional[torch.cuda.Stream] = None) -> float:
+        """Sender: bulk-copy the listed local blocks into their new slabs (peer HBM) and into local snapshots, in
+        one launch on the side stream.  Returns the device time of the copy in milliseconds."""
         from ..ops import count_launch
-        src_va = int(self.block_ptrs[block].item())
-        p, si, off = self.arena.alloc(self.block_bytes)
+        new_va = self._resolve_locs(locs)
+        blocks = sorted(new_va)
+        self._mig = getattr(self, "_mig", {})
+        snaps = {b: self.arena.alloc(self.block_bytes)[0] for b in blocks}
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
         s = stream or torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(s):
-            self._n.migrate_copy(src_va, p, self.block_bytes)
+            e0.record()
+            self._n.migrate_bulk(self._i64(self._local_ptr[b] for b in blocks), self._i64(new_va[b] for b in blocks),
+                                 self._i64(snaps[b] for b in blocks), self.block_bytes, err)
+            e1.record()
             count_launch()
         s.synchronize()
-        self._pending_recv = getattr(self, "_pending_recv", {})
-        self._pending_recv[block] = p
-        return (self.self_key, si, off, self.arena.segment_info(si))
+        if int(err.item()) != 0:
+            for p in snaps.values():
+                self.arena.free(p)
+            raise RuntimeError("bulk migration copy timed out on an mbarrier")
+        for b in blocks:
+            self._mig[b] = (self._local_ptr[b], snaps[b], new_va[b])
+        return e0.elapsed_time(e1)
 
-    def flip_block(self, block: int, new_owner: Any, loc: Tuple[Any, int, int, Any]) -> None:
-        """Ownership flip on THIS GPU: map the new slab, rewrite the pointer-table entry, release
-        the old slab when this GPU was the previous owner."""
-        rr, si, off, handle = loc
-        self.arena.map_peer(rr, si, handle)
-        old_owner = self.owners[block]
-        self.block_ptrs[block] = self.arena.resolve(rr, si, off)
-        torch.cuda.synchronize(self.device)
-        self._loc[block] = (rr, si, off)
-        self.owners[block] = new_owner
-        if new_owner == self.self_key:
-            self._local_ptr[block] = getattr(self, "_pending_recv", {}).pop(block)
-        elif old_owner == self.self_key and block in self._local_ptr:
-            self.arena.free(self._local_ptr.pop(block))
+    def flip_blocks(self, locs, new_owner: Any) -> None:
+        """Every GPU: rewrite the pointer-table entries of the moved blocks (one launch, st.release), then fence."""
+        from ..ops import count_launch
+        new_va = self._resolve_locs(locs)
+        blocks = sorted(new_va)
+        cur = torch.cuda.current_stream(self.device)
+        self._n.flip_blocks(self._view_ptrs, torch.tensor(blocks, dtype=torch.int32, device=self.device),
+                            self._i64(new_va[b] for b in blocks))
+        count_launch()
+        cur.synchronize()                        # the new addresses are in HBM: kernels starting from now on use them
+        torch.cuda.synchronize(self.device)      # fence: every kernel that may have read an old address has finished
+        for b in blocks:
+            rr, si, off, _h = locs[b] if b in locs else locs[str(b)]
+            self._loc[b] = (rr, si, off)
+            self.owners[b] = new_owner
+            if new_owner == self.self_key:
+                self._local_ptr[b] = self._pending_recv.pop(b)
+            elif b in self._local_ptr:
+                self._local_ptr.pop(b)          # the old slab now only lives in self._mig until the drain
+
+    def drain_blocks(self, blocks: Sequence[int], stream: Optional[torch.cuda.Stream] = None) -> int:
+        """Sender, after EVERY GPU has flipped: forward what still landed in the old slabs (new += old - snapshot),
+        then free the old slabs and the snapshots.  Returns the number of forwarded elements."""
+        from ..ops import count_launch
+        blocks = [int(b) for b in blocks if int(b) in getattr(self, "_mig", {})]
+        if not blocks:
+            return 0
+        fw = torch.zeros(1, dtype=torch.int64, device=self.device)
+        s = stream or torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(s):
+            self._n.migrate_drain(self._i64(self._mig[b][0] for b in blocks), self._i64(self._mig[b][1] for b in blocks),
+                                  self._i64(self._mig[b][2] for b in blocks), self.block_bytes,
+                                  self.torch_dtype == torch.int32, fw)
+            count_launch()
+        s.synchronize()
+        for b in blocks:
+            old, snap, _new = self._mig.pop(b)
+            self.arena.free(old)
+            self.arena.free(snap)
+        return int(fw.item())
+
+    def migrate_blocks(self, blocks: Sequence[int], dst_rank: Any, stream: Optional[torch.cuda.Stream] = None
+                       ) -> Dict[str, float]:
+        """SPMD form of the live move (collective over the group; ONE object exchange for the whole list)."""
+        blocks = [int(b) for b in blocks if self.owners[int(b)] != dst_rank]
+        if not blocks:
+            return {"blocks": 0}
+        src_rank = self.owners[blocks[0]]
+        assert all(self.owners[b] == src_rank for b in blocks), "one sender per migrate_blocks call"
+        locs = self.alloc_recv(blocks) if self.self_key == dst_rank else None
+        locs = next(x for x in self.group.all_gather_object(locs) if x is not None)
+        copy_ms = self.send_blocks(locs, stream) if self.self_key == src_rank else 0.0
+        self.group.barrier()                 # the copies have landed
+        self.flip_blocks(locs, dst_rank)
+        self.group.barrier()                 # every GPU flipped and fenced
+        forwarded = self.drain_blocks(blocks, stream) if self.self_key == src_rank else 0
+        self.group.barrier()
+        return {"blocks": len(blocks), "bytes": len(blocks) * self.block_bytes, "copy_ms": copy_ms,
+                "forwarded_elements": forwarded}
+
+    def migrate_block(self, block: int, dst_rank: Any, stream: Optional[torch.cuda.Stream] = None) -> None:
+        self.migrate_blocks([block], dst_rank, stream)
 
     # ---- host import / export (checkpoint, tests) ----
     def export_block(self, b: int) -> Tuple[np.ndarray, np.ndarray]:

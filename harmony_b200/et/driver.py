@@ -902,28 +902,37 @@ class AllocatedTable:
         return fut
 
     def _device_move(self, src: str, dst: str, blocks: List[int]) -> ResultFuture:
-        """Device migration: quiesce the table's accessors at a mini-batch boundary, let the
-        receiver bulk-copy the slabs over NVLink on its side stream, flip every pointer table,
-        resume.  Other tables / jobs keep running during the copy."""
+        """Live device migration of a LIST of blocks -- no accessor is stopped:
+        alloc at the receiver -> ONE bulk-TMA copy launch at the sender (new slabs over NVLink + local snapshots) ->
+        every executor flips its pointer-table entries and fences -> the sender forwards what still landed in the
+        old slabs (new += old - snapshot) and frees them.  Other blocks / tables / jobs never notice."""
         out: ResultFuture = ResultFuture()
         subs = self._m.subscriptions.get_subscribers(self.table_id) | self.block_manager.get_associator_ids()
         ctl = self._m.control
+        stats: Dict[str, Any] = {}
 
-        def step_resume(_):
-            ctl.fan_out(subs, {"type": "TableResume", "table_id": self.table_id}).chain(
-                out, lambda _: out.on_completed(MigrationResult(True, "device migration completed", list(blocks))))
-
-        def abort(exc):
-            """A step failed (e.g. the receiver's arena is full): nothing was flipped yet, so release the blocks and
-            let the quiesced accessors continue on the old owner."""
+        def release(exc, free_at_dst: bool):
             LOG.error("device migration of %s blocks %s -> %s failed: %s", self.table_id, src, dst, exc)
             for b in blocks:
                 self.block_manager.release_block_from_move(b)
-            ctl.fan_out(subs, {"type": "TableResume", "table_id": self.table_id}).add_listener(
-                lambda _: out.on_failed(exc))
+            if free_at_dst:
+                ctl.fan_out({dst}, {"type": "DeviceMoveAbort", "table_id": self.table_id,
+                                    "block_ids": list(blocks)}).add_listener(lambda _: out.on_failed(exc))
+            else:
+                out.on_failed(exc)
 
-        def step_flip(acks):
-            locs = acks[0]["locs"]
+        def step_done(acks):
+            stats["forwarded"] = sum(a.get("forwarded", 0) for a in acks)
+            res = MigrationResult(True, "device migration completed", list(blocks))
+            res.stats = dict(stats)
+            out.on_completed(res)
+
+        def step_drain(_):
+            ctl.fan_out({src}, {"type": "DeviceMoveDrain", "table_id": self.table_id,
+                                "block_ids": list(blocks)}).chain(out, step_done)
+
+        def step_flip(locs, acks):
+            stats.update({"copy_ms": acks[0].get("copy_ms"), "bytes": acks[0].get("bytes")})
             for b in blocks:
                 self.block_manager.update_owner(b, src, dst)
                 self.block_manager.release_block_from_move(b)
@@ -934,12 +943,14 @@ class AllocatedTable:
                 di["blocks"][b] = (key, si, off)
                 di["handles"][si] = seg_info
             ctl.fan_out(subs, {"type": "DeviceOwnershipFlip", "table_id": self.table_id, "locs": locs,
-                               "new_owner": dst, "old_owner": src}).chain(out, step_resume)
+                               "new_owner": dst, "old_owner": src}).chain(out, step_drain)
 
-        def step_copy(_):
-            ctl.fan_out({dst}, {"type": "DeviceMoveRecv", "table_id": self.table_id,
-                                "block_ids": list(blocks)}).chain(out, step_flip, on_error=abort)
-        ctl.fan_out(subs, {"type": "TableQuiesce", "table_id": self.table_id}).chain(out, step_copy, on_error=abort)
+        def step_send(acks):
+            locs = acks[0]["locs"]
+            ctl.fan_out({src}, {"type": "DeviceMoveSend", "table_id": self.table_id, "locs": locs}).chain(
+                out, lambda a: step_flip(locs, a), on_error=lambda e: release(e, True))
+        ctl.fan_out({dst}, {"type": "DeviceMoveAlloc", "table_id": self.table_id,
+                            "block_ids": list(blocks)}).chain(out, step_send, on_error=lambda e: release(e, False))
         return out
 
     def get_partition_info(self) -> Dict[str, Set[int]]:
@@ -1107,7 +1118,8 @@ class ETMaster:
     def on_message(self, m: Dict[str, Any]) -> None:
         t = m["type"]
         if t in ("TableInitAck", "TableLoadAck", "TableDropAck", "OwnershipSyncAck", "TablePeerMapAck",
-                 "TableQuiesceAck", "TableResumeAck", "DeviceMoveRecvAck", "DeviceOwnershipFlipAck"):
+                 "TableQuiesceAck", "TableResumeAck", "DeviceMoveAllocAck", "DeviceMoveSendAck", "DeviceMoveDrainAck",
+                 "DeviceMoveAbortAck", "DeviceOwnershipFlipAck"):
             self.control.on_ack(m["op_id"], m)
         elif t == "ControlOpFailed":
             LOG.error("control op %s (%s) failed on %s: %s", m["op_id"], m.get("orig_type"), m.get("src"), m["error"])

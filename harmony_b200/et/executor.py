@@ -101,7 +101,8 @@ class Executor:
 
     # control messages the driver fans out and waits on: a failing handler must fail the driver-side future
     _CONTROL_OPS = {"TableInit", "TableLoad", "TableDrop", "OwnershipSync", "TablePeerMap", "TableQuiesce",
-                    "TableResume", "DeviceMoveRecv", "DeviceOwnershipFlip"}
+                    "TableResume", "DeviceMoveAlloc", "DeviceMoveSend", "DeviceMoveDrain", "DeviceMoveAbort",
+                    "DeviceOwnershipFlip"}
 
     def _guarded(self, fn, m: Dict[str, Any]) -> None:
         try:

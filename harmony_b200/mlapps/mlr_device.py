@@ -35,7 +35,8 @@ class MLRDeviceTrainer(Trainer):
         self.comps = model_table.components
         self.num_classes = int(params["classes"])
         self.model = MLRDeviceModel(self.dtable, self.num_classes, float(params["step_size"]),
-                                    float(params.get("lambda", 0.0)))
+                                    float(params.get("lambda", 0.0)),
+                                    lazy_l2=False)   # job-server workers may run SSP-asynchronously: dense decay
         self.decay_rate = float(params.get("decay_rate", 0.9))
         self.decay_period = int(params.get("decay_period", 5))
         self._cache: Dict[Any, Any] = {}

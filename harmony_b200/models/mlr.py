@@ -106,13 +106,20 @@ class MLRDeviceModel:
     """Step functions over a DeviceTable whose row f = class weights of feature f."""
 
     def __init__(self, table: DeviceTable, num_classes: int, step_size: float, lam: float = 0.0,
-                 max_batch: int = 8192) -> None:
+                 max_batch: int = 8192, lazy_l2: bool = True) -> None:
+        """`lazy_l2`: keep the L2 decay as a scalar s with w = s * v (the table stores v): the forward multiplies
+        the logits by s, pushes divide the deltas by the NEXT s, nothing touches the 3.8 GiB shard.  Exact for
+        workers that step in lock-step (BSP: every holder of the table advances s identically); asynchronous
+        workers (SSP slack > 0 through the job server) pass lazy_l2=False and get the dense owner-side decay."""
         from ..ops import native
         self._n = native()
         self.table = table
         self.num_classes = num_classes
         self.step_size = float(step_size)
         self.lam = float(lam)
+        self.lazy_l2 = bool(lazy_l2)
+        self.scale = 1.0           # s: w = s * v
+        self._delta_step = None    # step / s' of the mini-batch in flight (lazy mode)
         self.device = table.device
         self._D = torch.empty((max_batch, table.row_stride), dtype=torch.float32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
@@ -127,8 +134,9 @@ class MLRDeviceModel:
         from ..ops import count_launch
         bp, rpb, stride, _dim, mode = self.table.view()
         D = self._scratch(batch.batch_size) if write_delta else None
+        step = self.step_size if self._delta_step is None else self._delta_step
         self._n.mlr_forward(bp, rpb, stride, self.num_classes, mode, batch.csr_ptr, batch.csr_col,
-                            batch.csr_val, batch.labels, self.step_size, D, self.stats)
+                            batch.csr_val, batch.labels, step, D, self.stats, self.scale)
         count_launch()
 
     def backward_push(self, batch: MLRBatch) -> None:
@@ -140,13 +148,34 @@ class MLRDeviceModel:
         count_launch()
 
     def apply_l2(self, total_batch_instances: int) -> None:
-        if self.lam != 0.0:
+        """Dense owner-side decay (non-lazy mode): W <- (1 - step * lam * B_total) W on the local shard."""
+        if self.lam != 0.0 and not self.lazy_l2:
             self.table.scale_local(1.0 - self.step_size * self.lam * total_batch_instances)
 
     def step(self, batch: MLRBatch, total_batch_instances: Optional[int] = None) -> None:
+        """W' = (1 - c) W + delta, c = step * lam * B_total (MLRTrainer.java:387-397).  Lazy mode: s' = (1 - c) s and
+        v' = v + delta / s' -- the forward sees s, the error rows are pre-scaled by step / s'."""
+        n_inst = total_batch_instances or batch.batch_size
+        if self.lam != 0.0 and self.lazy_l2:
+            s_next = self.scale * (1.0 - self.step_size * self.lam * n_inst)
+            self._delta_step = self.step_size / s_next
+            self.forward(batch, True)
+            self.backward_push(batch)
+            self._delta_step = None
+            self.scale = s_next
+            if self.scale < 1e-3:
+                self.fold_scale()
+            return
         self.forward(batch, True)
         self.backward_push(batch)
-        self.apply_l2(total_batch_instances or batch.batch_size)
+        self.apply_l2(n_inst)
+
+    def fold_scale(self) -> None:
+        """v <- s v, s <- 1 on the local shard (before checkpoints / dense exports, or when s gets small).  Every
+        holder of the table calls it at the same logical point (each folds its own blocks)."""
+        if self.scale != 1.0:
+            self.table.scale_local(self.scale)
+            self.scale = 1.0
 
     def evaluate(self, batch: MLRBatch) -> Tuple[float, float]:
         """(sum loss, accuracy) of the batch under the current model (no update)."""

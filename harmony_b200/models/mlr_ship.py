@@ -72,8 +72,9 @@ def route_batches(table: DeviceTable, worker_batches: Sequence[MLRBatch], rank: 
     return RoutedBatch(routed, worker_batches[rank].labels.clone())
 
 
-class MLRShipModel:
-    """One BSP step of MLR in ship mode: owner-side partial logits reduce-added into the worker's buffer over peer
+class MLRShipModelV1:
+    """(round-1 implementation, kept for A/B runs and for row strides > 1024 floats)
+    One BSP step of MLR in ship mode: owner-side partial logits reduce-added into the worker's buffer over peer
     memory, softmax + error rows stored into every owner's buffer, owner-local row update
     (ops/csrc/mlr_ship_ops.cu).  Same arithmetic as MLRTrainer.java:374-398,475-505."""
 
@@ -149,3 +150,145 @@ class MLRShipModel:
 
     def decay_step(self, rate: float) -> None:
         self.step_size *= rate
+
+
+class MLRShipModel:
+    """Ship mode, second generation (ops/csrc/mlr_nvls_ops.cu): three launches per BSP step and no barrier.
+
+    K2 (softmax) runs on a high-priority side stream NEXT TO K1 (owner-side partial logits) and consumes logit tiles
+    as the owners flag them; the reduce-scatter is `multimem.ld_reduce` and the all-gather `multimem.st` on the
+    multicast mapping of a `SymmetricRegion` (NVLS; unicast peer loads / stores when there is no multicast);
+    K3 (owner-side row update) acquires the "all error rows have landed" counter inside the kernel.
+    Same arithmetic as MLRTrainer.java:374-398,475-505.  `lam` != 0 uses the lazy L2 scale of the table
+    (w = s * v, see `LazyScale`): logits are multiplied by s, deltas divided by the next s, no dense pass."""
+
+    TILE_ROWS = 32
+
+    def __init__(self, table: DeviceTable, arena: PeerArena, group: PeerGroup, clock: Optional[DeviceClock],
+                 num_classes: int, step_size: float, batch_size: int, multicast: bool = True,
+                 lam: float = 0.0) -> None:
+        from ..ops import native
+        from ..parallel.peer import SymmetricRegion
+        self._n = native()
+        self.table, self.arena, self.group, self.clock = table, arena, group, clock
+        self.rank, self.world = group.rank, group.world
+        self.num_classes, self.step_size, self.B = num_classes, float(step_size), int(batch_size)
+        self.lam = float(lam)
+        self.device = table.device
+        stride = table.row_stride
+        if stride > 1024:
+            raise ValueError("MLRShipModel needs row_stride <= 1024 floats; use MLRShipModelV1 for wider rows")
+        self.stride = stride
+        self._n.ship_preload(arena.device)       # lazy kernel loading must not happen while another kernel spins
+        self.n_tiles = -(-self.B // self.TILE_ROWS)
+        rows = self.world * self.B
+        buf = rows * stride * 4
+        self._off_p, self._off_d = 0, buf
+        self._off_pflag = 2 * buf
+        self._off_dcount = self._off_pflag + ((self.n_tiles * 4 + 255) // 256) * 256
+        total = self._off_dcount + 256
+        self.region = SymmetricRegion(arena, group, total, multicast=multicast)
+        reg = self.region
+        reg.tensor(0, [reg.nbytes // 4], torch.int32).zero_()
+        torch.cuda.synchronize(self.device)
+        group.barrier()
+        self.D = reg.tensor(self._off_d, [rows, stride], torch.float32)
+        self.P = reg.tensor(self._off_p, [rows, stride], torch.float32)
+        i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=self.device)  # noqa: E731
+        self.src_ptrs = i64([p + self._off_p for p in reg.peer_ptrs])
+        self.dst_ptrs = i64([p + self._off_d for p in reg.peer_ptrs])
+        self.pflag_ptrs = i64([p + self._off_pflag for p in reg.peer_ptrs])
+        self.dcount_ptrs = i64([p + self._off_dcount for p in reg.peer_ptrs])
+        self.nvls = reg.mc_ptr != 0
+        self.mc_p = reg.mc_ptr + self._off_p if self.nvls else 0
+        self.mc_d = reg.mc_ptr + self._off_d if self.nvls else 0
+        self.tile_done = torch.zeros(self.world * self.n_tiles, dtype=torch.int32, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.epoch = 0
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._ev_in = torch.cuda.Event()
+        self._ev_done = torch.cuda.Event()
+        self.scale = 1.0          # lazy L2 scale s of the model table (w = s * v); identical on every rank (BSP)
+        torch.cuda.synchronize(self.device)
+        group.barrier()
+
+    # launches of one step (also used one by one by `step_timed`)
+    def _k1(self, rb: RoutedBatch) -> None:
+        bp, rpb, stride, _dim, mode = self.table.view()
+        r = rb.routed
+        self._n.ship_forward(bp, rpb, stride, self.num_classes, mode, r.csr_ptr, r.csr_col, r.csr_val, self.world,
+                             self.B, self.TILE_ROWS, self.region.local_ptr + self._off_p, self.tile_done.data_ptr(),
+                             self.pflag_ptrs, self.epoch)
+
+    def _k2(self, rb: RoutedBatch, logit_scale: float, delta_step: float) -> None:
+        self._n.ship_softmax(self.mc_p, self.src_ptrs, self.rank * self.B, self.mc_d, self.dst_ptrs,
+                             self.rank * self.B, self.stride, rb.labels, self.num_classes, delta_step, logit_scale,
+                             self.TILE_ROWS, self.region.local_ptr + self._off_pflag, self.epoch * self.world,
+                             self.dcount_ptrs, self.stats, self.err)
+
+    def _k3(self, rb: RoutedBatch) -> None:
+        bp, rpb, stride, _dim, mode = self.table.view()
+        r = rb.routed
+        self._n.mlr_backward_push(bp, rpb, stride, self.num_classes, mode, r.uniq_feat, r.feat_ptr, r.samp, r.xval,
+                                  self.D, False, self.region.local_ptr + self._off_dcount,
+                                  self.epoch * self.world * self.n_tiles, self.err)
+
+    def _scales(self) -> tuple:
+        """(logit scale, delta step) of this step under the lazy L2 decay: W' = (1 - c) W + delta with
+        c = step * lam * B_total  <=>  s' = s (1 - c), v' = v + delta / s'."""
+        if self.lam == 0.0:
+            return 1.0, self.step_size
+        s_old = self.scale
+        self.scale = s_old * (1.0 - self.step_size * self.lam * self.B * self.world)
+        return s_old, self.step_size / self.scale
+
+    def step(self, rb: RoutedBatch) -> None:
+        from ..ops import count_launch
+        self.epoch += 1
+        ls, ds = self._scales()
+        cur = torch.cuda.current_stream(self.device)
+        self._ev_in.record(cur)
+        self.side.wait_event(self._ev_in)                # this step's inputs are on the device
+        with torch.cuda.stream(self.side):
+            self._k2(rb, ls, ds)                         # resident first: it spins on tile flags while K1 runs
+            self._ev_done.record(self.side)
+        self._k1(rb)
+        self._k3(rb)
+        cur.wait_event(self._ev_done)                    # stats / the next step's inputs are ordered after K2
+        count_launch(3)
+        if self.lam != 0.0 and self.scale < 1e-3:
+            self.renormalize()
+
+    def renormalize(self) -> None:
+        """Fold the lazy scale into the rows (v <- s v, s <- 1): one dense pass every few hundred steps."""
+        self.table.scale_local(self.scale)
+        self.scale = 1.0
+
+    def step_timed(self, rb: RoutedBatch) -> dict:
+        """One step with the three kernels serialised on the current stream and CUDA events around each
+        (bench.py --ship_phases).  No overlap here by construction: it shows what each part costs alone."""
+        self.epoch += 1
+        ls, ds = self._scales()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        self._k1(rb)
+        ev[1].record()
+        self._k2(rb, ls, ds)
+        ev[2].record()
+        self._k3(rb)
+        ev[3].record()
+        torch.cuda.synchronize(self.device)
+        names = ("k1_partial_fwd_ms", "k2_reduce_softmax_bcast_ms", "k3_update_ms")
+        return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+
+    def check(self) -> None:
+        e = int(self.err.item())
+        if e != 0:
+            raise TimeoutError(f"ship-mode flag wait timed out (stage {e}: 2 = logits tile, 3 = error rows)")
+
+    def decay_step(self, rate: float) -> None:
+        self.step_size *= rate
+
+    def close(self) -> None:
+        self.region.close()

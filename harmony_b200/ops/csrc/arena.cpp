@@ -23,7 +23,12 @@ namespace hb {
     TORCH_CHECK(_e == cudaSuccess, "CUDA error ", cudaGetErrorString(_e), " at " #expr);         \
   } while (0)
 
+// vmm.cpp
+std::vector<int64_t> vmm_create(int64_t device, int64_t bytes, int64_t align);
+void vmm_release(int64_t base);
+
 struct Arena {
+  int kind = 0;           // 0 = cudaMalloc segment exported with CUDA IPC, 1 = VMM segment (cuMemCreate, fd shareable)
   char* base = nullptr;
   size_t capacity = 0;
   size_t bump = 0;
@@ -53,12 +58,19 @@ static std::mutex g_mu;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-int64_t arena_create(int64_t device, int64_t bytes) {
+int64_t arena_create(int64_t device, int64_t bytes, int64_t kind, int64_t align) {
   auto* a = new Arena();
   a->device = (int)device;
+  a->kind = (int)kind;
   DeviceScope scope((int)device);
-  a->capacity = align_up((size_t)bytes, 2u << 20);
-  HB_CUDA_CHECK(cudaMalloc((void**)&a->base, a->capacity));
+  if (kind == 1) {
+    auto r = vmm_create(device, bytes, align);
+    a->base = reinterpret_cast<char*>(r[0]);
+    a->capacity = (size_t)r[1];
+  } else {
+    a->capacity = align_up((size_t)bytes, 2u << 20);
+    HB_CUDA_CHECK(cudaMalloc((void**)&a->base, a->capacity));
+  }
   std::lock_guard<std::mutex> g(g_mu);
   int64_t id = reinterpret_cast<int64_t>(a->base);
   g_arenas[id] = a;
@@ -123,7 +135,9 @@ void arena_destroy(int64_t id) {
     a = it->second;
     g_arenas.erase(it);
   }
-  {
+  if (a->kind == 1) {
+    vmm_release(reinterpret_cast<int64_t>(a->base));
+  } else {
     DeviceScope scope(a->device);
     cudaFree(a->base);
   }

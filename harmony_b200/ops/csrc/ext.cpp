@@ -5,7 +5,23 @@
 
 namespace hb {
 // arena.cpp
-int64_t arena_create(int64_t device, int64_t bytes);
+int64_t arena_create(int64_t device, int64_t bytes, int64_t kind, int64_t align);
+// vmm.cpp
+std::vector<bool> vmm_supported(int64_t device);
+int64_t vmm_granularity(int64_t device);
+int64_t vmm_export_fd(int64_t base);
+int64_t vmm_import_fd(int64_t fd, int64_t bytes, int64_t device);
+void vmm_grant(int64_t base, int64_t device);
+void vmm_release(int64_t base);
+int64_t mc_granularity(int64_t world, int64_t bytes, bool recommended);
+std::vector<int64_t> mc_create(int64_t device, int64_t world, int64_t bytes);
+int64_t mc_import(int64_t fd, int64_t device, int64_t world, int64_t bytes);
+void mc_add_device(int64_t id, int64_t device);
+void mc_bind(int64_t id, int64_t mc_offset, int64_t seg_base, int64_t mem_offset, int64_t bytes);
+int64_t mc_map(int64_t id, int64_t device);
+void mc_unmap(int64_t va, int64_t bytes);
+void mc_destroy(int64_t id, int64_t device);
+void close_fd(int64_t fd);
 int64_t arena_alloc(int64_t id, int64_t bytes);
 void arena_free(int64_t id, int64_t ptr);
 std::vector<int64_t> arena_stats(int64_t id);
@@ -29,15 +45,35 @@ void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_d
                double b, int64_t seed, int64_t row_key_base, int64_t key_stride);
 void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes);
 void flip_owner(at::Tensor ptr_tables, int64_t block, at::Tensor new_ptrs);
+void migrate_bulk(at::Tensor src_ptrs, at::Tensor dst_ptrs, c10::optional<at::Tensor> snap_ptrs, int64_t block_bytes,
+                  at::Tensor err);
+void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptrs, int64_t block_bytes, bool is_int,
+                   at::Tensor forwarded);
+void flip_blocks(at::Tensor ptr_table, at::Tensor blocks, at::Tensor new_ptrs);
+void scale_blocks(at::Tensor ptrs, int64_t block_bytes, double factor);
+void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                   at::Tensor keys, at::Tensor values);
 void clock_publish(at::Tensor clock_ptrs, int64_t rank, int64_t value);
 void clock_wait(at::Tensor my_clocks, int64_t min_value, int64_t timeout_cycles, at::Tensor err_flag);
 // mlr_ops.cu
 void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                  int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, at::Tensor labels,
-                 double step, c10::optional<at::Tensor> D, at::Tensor stats);
+                 double step, c10::optional<at::Tensor> D, at::Tensor stats, double logit_scale);
 void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                        int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
-                       at::Tensor xval, at::Tensor D, bool local_rmw);
+                       at::Tensor xval, at::Tensor D, bool local_rmw, int64_t wait_ptr, int64_t wait_target,
+                       c10::optional<at::Tensor> err);
+// mlr_nvls_ops.cu
+void ship_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                  int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, int64_t world, int64_t B,
+                  int64_t tile_rows, int64_t p_ptr, int64_t tile_done_ptr, c10::optional<at::Tensor> pflag_ptrs,
+                  int64_t epoch);
+void ship_softmax(int64_t src_mc, c10::optional<at::Tensor> src_ptrs, int64_t src_row0, int64_t dst_mc,
+                  c10::optional<at::Tensor> dst_ptrs, int64_t dst_row0, int64_t stride, at::Tensor labels,
+                  int64_t num_classes, double step, double logit_scale, int64_t tile_rows, int64_t pflag_ptr,
+                  int64_t pflag_target, c10::optional<at::Tensor> dcount_ptrs, at::Tensor stats, at::Tensor err);
+void wait_count(int64_t ptr, int64_t target, at::Tensor err);
+void ship_preload(int64_t device);
 // nmf_ops.cu
 void nmf_batch(at::Tensor csr_ptr, at::Tensor col_slot, at::Tensor val, at::Tensor L, at::Tensor l_row,
                at::Tensor Rst, at::Tensor Gst, int64_t rank, double step, double lambda, double lo, double hi,
@@ -80,7 +116,23 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor> group_by_feature(at::
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "harmony_b200 native runtime (sm_100a)";
-  m.def("arena_create", &hb::arena_create);
+  m.def("arena_create", &hb::arena_create, py::arg("device"), py::arg("bytes"), py::arg("kind") = 0,
+        py::arg("align") = 0);
+  m.def("vmm_supported", &hb::vmm_supported);
+  m.def("vmm_granularity", &hb::vmm_granularity);
+  m.def("vmm_export_fd", &hb::vmm_export_fd);
+  m.def("vmm_import_fd", &hb::vmm_import_fd);
+  m.def("vmm_grant", &hb::vmm_grant);
+  m.def("vmm_release", &hb::vmm_release);
+  m.def("mc_granularity", &hb::mc_granularity);
+  m.def("mc_create", &hb::mc_create);
+  m.def("mc_import", &hb::mc_import);
+  m.def("mc_add_device", &hb::mc_add_device);
+  m.def("mc_bind", &hb::mc_bind);
+  m.def("mc_map", &hb::mc_map);
+  m.def("mc_unmap", &hb::mc_unmap);
+  m.def("mc_destroy", &hb::mc_destroy);
+  m.def("close_fd", &hb::close_fd);
   m.def("arena_alloc", &hb::arena_alloc);
   m.def("arena_free", &hb::arena_free);
   m.def("arena_stats", &hb::arena_stats);
@@ -97,12 +149,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("init_slab", &hb::init_slab);
   m.def("migrate_copy", &hb::migrate_copy);
   m.def("flip_owner", &hb::flip_owner);
+  m.def("migrate_bulk", &hb::migrate_bulk);
+  m.def("migrate_drain", &hb::migrate_drain);
+  m.def("flip_blocks", &hb::flip_blocks);
+  m.def("scale_blocks", &hb::scale_blocks);
+  m.def("table_put_i32", &hb::table_put_i32);
   m.def("clock_publish", &hb::clock_publish);
   m.def("clock_wait", &hb::clock_wait);
-  m.def("mlr_forward", &hb::mlr_forward);
+  m.def("mlr_forward", &hb::mlr_forward, py::arg("block_ptrs"), py::arg("rows_per_block"), py::arg("row_stride"),
+        py::arg("num_classes"), py::arg("mode"), py::arg("csr_ptr"), py::arg("csr_col"), py::arg("csr_val"),
+        py::arg("labels"), py::arg("step"), py::arg("D"), py::arg("stats"), py::arg("logit_scale") = 1.0);
   m.def("mlr_backward_push", &hb::mlr_backward_push, py::arg("block_ptrs"), py::arg("rows_per_block"),
         py::arg("row_stride"), py::arg("num_classes"), py::arg("mode"), py::arg("uniq_feat"), py::arg("feat_ptr"),
-        py::arg("samp"), py::arg("xval"), py::arg("D"), py::arg("local_rmw") = false);
+        py::arg("samp"), py::arg("xval"), py::arg("D"), py::arg("local_rmw") = false, py::arg("wait_ptr") = 0,
+        py::arg("wait_target") = 0, py::arg("err") = py::none());
+  m.def("ship_forward", &hb::ship_forward);
+  m.def("ship_softmax", &hb::ship_softmax);
+  m.def("wait_count", &hb::wait_count);
+  m.def("ship_preload", &hb::ship_preload);
   m.def("nmf_batch", &hb::nmf_batch);
   m.def("lda_sample", &hb::lda_sample);
   m.def("mlr_partial_forward", &hb::mlr_partial_forward);

@@ -18,7 +18,9 @@ namespace hb {
 enum PartitionMode : int { PART_ORDERED = 0, PART_HASHED = 1 };
 
 struct TableView {
-  const long long* __restrict__ block_ptrs;  // [num_blocks] VA of each block's row 0
+  // [num_blocks + 2]: VA of each block's row 0, then two guard words maintained by row_ptr():
+  //   [num_blocks] = number of out-of-range keys seen, [num_blocks + 1] = the last offending key
+  const long long* __restrict__ block_ptrs;
   int num_blocks;
   int rows_per_block;   // capacity (rows) of every block slab
   int row_stride;       // elements between consecutive rows (padded to 32 elements)
@@ -27,8 +29,17 @@ struct TableView {
 };
 
 // key -> element pointer of the row. Works for any 4-byte element type.
+// An out-of-range key would become a wild HBM (possibly peer) address: it is counted in the guard words of the
+// pointer table and clamped to key 0, so the access stays inside the table and DeviceTable.check() raises later
+// (no device sync on the hot path; cost = one 64-bit compare per row).
 template <typename T>
 __device__ __forceinline__ T* row_ptr(const TableView& t, long long key) {
+  if ((unsigned long long)key >= (unsigned long long)t.num_blocks * (unsigned long long)t.rows_per_block) {
+    long long* guard = const_cast<long long*>(t.block_ptrs) + t.num_blocks;
+    atomicAdd(reinterpret_cast<unsigned long long*>(guard), 1ULL);
+    guard[1] = key;
+    key = 0;
+  }
   int blk, slot;
   if (t.mode == PART_ORDERED) {
     blk = (int)(key / t.rows_per_block);
@@ -120,6 +131,38 @@ __device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+static constexpr long long HB_SPIN_TIMEOUT = 4000000000LL;   // ~2 s of SM clocks: raise, never hang the GPU
+
+// ---- multimem (NVLS) primitives: the address must be a multicast mapping -------------------------------
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f4(const float* mc) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin until *p >= target (wrap-safe).  Returns false on timeout after raising `err`.
+__device__ __forceinline__ bool spin_until_ge(const unsigned* p, unsigned target, int* err, int code) {
+  const long long t0 = clock64();
+  while ((int)(ld_acquire_sys_u32(p) - target) < 0) {
+    if (clock64() - t0 > HB_SPIN_TIMEOUT) { atomicExch(err, code); return false; }
+    __nanosleep(40);
+  }
+  return true;
+}
+
 
 // ---- reductions ---------------------------------------------------------------------------
 __device__ __forceinline__ float warp_max(float v) {

@@ -100,7 +100,7 @@ void lasso_cd(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride,
   TORCH_CHECK(B * 4 <= 200 * 1024, "lasso mini-batch too large for the shared-memory prediction vector");
   TableView v;
   v.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
-  v.num_blocks = (int)block_ptrs.numel(); v.rows_per_block = (int)rows_per_block; v.row_stride = (int)row_stride;
+  v.num_blocks = (int)block_ptrs.numel() - 2; /* two guard words follow the pointers */ v.rows_per_block = (int)rows_per_block; v.row_stride = (int)row_stride;
   v.row_dim = (int)row_dim; v.mode = (int)mode;
   size_t smem = (size_t)B * 4;
   C10_CUDA_CHECK(cudaFuncSetAttribute(lasso_cd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

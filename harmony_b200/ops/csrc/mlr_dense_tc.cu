@@ -483,7 +483,7 @@ void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int
   cudaFuncSetAttribute(dense_gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   TableView W;
   W.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
-  W.num_blocks = (int)block_ptrs.numel();
+  W.num_blocks = (int)block_ptrs.numel() - 2;   // two guard words follow the pointers
   W.rows_per_block = (int)rows_per_block;
   W.row_stride = (int)row_stride;
   W.row_dim = (int)n_classes;

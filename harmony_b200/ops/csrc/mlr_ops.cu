@@ -39,7 +39,7 @@ template <int VEC, bool WRITE_D>
 __global__ void __launch_bounds__(MLR_THREADS) mlr_fwd_kernel(
     TableView W, const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
     const float* __restrict__ csr_val, const int* __restrict__ labels, int B, int C, float step,
-    float* __restrict__ D, int d_stride, float* __restrict__ stats) {
+    float* __restrict__ D, int d_stride, float* __restrict__ stats, float lscale) {
   __shared__ const float* s_row[MLR_THREADS];
   __shared__ float s_val[MLR_THREADS];
   __shared__ float s_red[32];
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(MLR_THREADS) mlr_fwd_kernel(
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int c0 = 4 * (tid + k * MLR_THREADS);
-      l[k][0] = acc[k].x; l[k][1] = acc[k].y; l[k][2] = acc[k].z; l[k][3] = acc[k].w;
+      // lazy L2 decay: the table stores v with w = lscale * v (models/mlr.py LazyScale)
+      l[k][0] = acc[k].x * lscale; l[k][1] = acc[k].y * lscale; l[k][2] = acc[k].z * lscale; l[k][3] = acc[k].w * lscale;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (c0 + e >= C) l[k][e] = -INFINITY;
@@ -155,8 +156,12 @@ template <int VEC, bool LOCAL_RMW>
 __global__ void __launch_bounds__(MLR_THREADS) mlr_bwd_push_kernel(
     TableView W, const int* __restrict__ uniq_feat, const int* __restrict__ feat_ptr,
     const int* __restrict__ samp, const float* __restrict__ xval, int U, const float* __restrict__ D,
-    int d_stride) {
+    int d_stride, const unsigned* __restrict__ wait_ptr, unsigned wait_target, int* __restrict__ err) {
   const int tid = threadIdx.x;
+  if (wait_ptr != nullptr) {       // ship mode: every worker's error rows have landed in D (acquire)
+    if (tid == 0) spin_until_ge(wait_ptr, wait_target, err, 3);
+    __syncthreads();
+  }
   const uint64_t pol_keep = l2_policy_evict_last();    // D is re-read ~nnz/B times: keep it in L2
   const uint64_t pol_stream = l2_policy_evict_first(); // model rows are touched once per step
   for (int u = blockIdx.x; u < U; u += gridDim.x) {
@@ -222,7 +227,11 @@ template <int NV>
 __global__ void __launch_bounds__(256) mlr_bwd_push_warp_kernel(
     TableView W, const int* __restrict__ uniq_feat, const int* __restrict__ feat_ptr,
     const int* __restrict__ samp, const float* __restrict__ xval, int U, const float* __restrict__ D,
-    int d_stride) {
+    int d_stride, const unsigned* __restrict__ wait_ptr, unsigned wait_target, int* __restrict__ err) {
+  if (wait_ptr != nullptr) {       // ship mode: every worker's error rows have landed in D (acquire)
+    if (threadIdx.x == 0) spin_until_ge(wait_ptr, wait_target, err, 3);
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -270,11 +279,22 @@ __global__ void __launch_bounds__(256) mlr_bwd_push_warp_kernel(
 }
 
 // ---- host side ---------------------------------------------------------------------------------
+// Force-load the backward kernels (see ship_preload in mlr_nvls_ops.cu: lazy loading vs. spinning kernels).
+void mlr_preload_bwd() {
+  cudaFuncAttributes a;
+#define HB_TOUCH(K) C10_CUDA_CHECK(cudaFuncGetAttributes(&a, K))
+  HB_TOUCH(mlr_bwd_push_warp_kernel<1>); HB_TOUCH(mlr_bwd_push_warp_kernel<2>);
+  HB_TOUCH(mlr_bwd_push_warp_kernel<4>); HB_TOUCH(mlr_bwd_push_warp_kernel<8>);
+  HB_TOUCH((mlr_bwd_push_kernel<1, false>)); HB_TOUCH((mlr_bwd_push_kernel<2, false>));
+  HB_TOUCH((mlr_bwd_push_kernel<4, false>));
+#undef HB_TOUCH
+}
+
 static TableView mlr_view(const at::Tensor& block_ptrs, int64_t rows_per_block, int64_t row_stride,
                           int64_t row_dim, int64_t mode) {
   TableView v;
   v.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
-  v.num_blocks = (int)block_ptrs.numel();
+  v.num_blocks = (int)block_ptrs.numel() - 2;   // two guard words follow the pointers
   v.rows_per_block = (int)rows_per_block;
   v.row_stride = (int)row_stride;
   v.row_dim = (int)row_dim;
@@ -285,7 +305,7 @@ static TableView mlr_view(const at::Tensor& block_ptrs, int64_t rows_per_block, 
 // D: [B, d_stride] float32 scratch (d_stride == row_stride); stats: float32[2] (loss, #correct)
 void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                  int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, at::Tensor labels,
-                 double step, c10::optional<at::Tensor> D, at::Tensor stats) {
+                 double step, c10::optional<at::Tensor> D, at::Tensor stats, double logit_scale) {
   c10::cuda::CUDAGuard guard(block_ptrs.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TableView W = mlr_view(block_ptrs, rows_per_block, row_stride, num_classes, mode);
@@ -306,10 +326,12 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
 #define LAUNCH_FWD(V)                                                                                      \
   if (dptr) mlr_fwd_kernel<V, true><<<grid, MLR_THREADS, 0, stream>>>(                                     \
         W, csr_ptr.data_ptr<int>(), csr_col.data_ptr<int>(), csr_val.data_ptr<float>(),                    \
-        labels.data_ptr<int>(), B, (int)num_classes, (float)step, dptr, d_stride, stats.data_ptr<float>()); \
+        labels.data_ptr<int>(), B, (int)num_classes, (float)step, dptr, d_stride, stats.data_ptr<float>(), \
+        (float)logit_scale);                                                                               \
   else mlr_fwd_kernel<V, false><<<grid, MLR_THREADS, 0, stream>>>(                                         \
         W, csr_ptr.data_ptr<int>(), csr_col.data_ptr<int>(), csr_val.data_ptr<float>(),                    \
-        labels.data_ptr<int>(), B, (int)num_classes, (float)step, nullptr, d_stride, stats.data_ptr<float>());
+        labels.data_ptr<int>(), B, (int)num_classes, (float)step, nullptr, d_stride, stats.data_ptr<float>(), \
+        (float)logit_scale);
   if (vec <= 1) { LAUNCH_FWD(1) } else if (vec == 2) { LAUNCH_FWD(2) } else { LAUNCH_FWD(4) }
 #undef LAUNCH_FWD
   C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -317,8 +339,12 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
 
 void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
                        int64_t mode, at::Tensor uniq_feat, at::Tensor feat_ptr, at::Tensor samp,
-                       at::Tensor xval, at::Tensor D, bool local_rmw) {
+                       at::Tensor xval, at::Tensor D, bool local_rmw, int64_t wait_ptr, int64_t wait_target,
+                       c10::optional<at::Tensor> err) {
   c10::cuda::CUDAGuard guard(block_ptrs.device());
+  const unsigned* wp = reinterpret_cast<const unsigned*>(wait_ptr);
+  int* ep = err.has_value() ? err->data_ptr<int>() : nullptr;
+  TORCH_CHECK(wp == nullptr || ep != nullptr, "a wait needs an error flag");
   auto stream = at::cuda::getCurrentCUDAStream();
   TableView W = mlr_view(block_ptrs, rows_per_block, row_stride, num_classes, mode);
   const int U = (int)uniq_feat.numel();
@@ -332,7 +358,7 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
 #define LAUNCH_BW(NVv)                                                                             \
     mlr_bwd_push_warp_kernel<NVv><<<gridw, 256, 0, stream>>>(                                      \
         W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),               \
-        xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);
+        xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride, wp, (unsigned)wait_target, ep);
     if (nv <= 1) { LAUNCH_BW(1) } else if (nv <= 2) { LAUNCH_BW(2) } else if (nv <= 4) { LAUNCH_BW(4) } else { LAUNCH_BW(8) }
 #undef LAUNCH_BW
     C10_CUDA_KERNEL_LAUNCH_CHECK();
@@ -343,10 +369,10 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
 #define LAUNCH_BWD(V)                                                                               \
   if (local_rmw) mlr_bwd_push_kernel<V, true><<<grid, MLR_THREADS, 0, stream>>>(                    \
       W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),                 \
-      xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);                             \
+      xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride, wp, (unsigned)wait_target, ep);                             \
   else mlr_bwd_push_kernel<V, false><<<grid, MLR_THREADS, 0, stream>>>(                             \
       W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),                 \
-      xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride);
+      xval.data_ptr<float>(), U, D.data_ptr<float>(), (int)row_stride, wp, (unsigned)wait_target, ep);
   if (vec <= 1) { LAUNCH_BWD(1) } else if (vec == 2) { LAUNCH_BWD(2) } else { LAUNCH_BWD(4) }
 #undef LAUNCH_BWD
   C10_CUDA_KERNEL_LAUNCH_CHECK();

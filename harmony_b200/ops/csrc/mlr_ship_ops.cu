@@ -220,7 +220,7 @@ static TableView ship_view(const at::Tensor& block_ptrs, int64_t rows_per_block,
                            int64_t row_dim, int64_t mode) {
   TableView v;
   v.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
-  v.num_blocks = (int)block_ptrs.numel();
+  v.num_blocks = (int)block_ptrs.numel() - 2;   // two guard words follow the pointers
   v.rows_per_block = (int)rows_per_block;
   v.row_stride = (int)row_stride;
   v.row_dim = (int)row_dim;

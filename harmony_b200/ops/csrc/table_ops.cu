@@ -33,7 +33,7 @@ struct UpdateParams {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pull_rows_kernel(TableView t, const long long* __restrict__ keys,
                                                         int n, float* __restrict__ out, int out_stride,
-                                                        int vec_ok) {
+                                                        int out_width, int vec_ok) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int vec = t.row_stride >> 2;  // float4 per row (stride is a multiple of 32 floats)
@@ -43,11 +43,11 @@ __global__ void __launch_bounds__(256) pull_rows_kernel(TableView t, const long 
 #pragma unroll 4
     for (int v = lane; v < vec; v += 32) {
       float4 x = ld_stream_f4(src + 4 * v);
-      if (vec_ok && 4 * v + 3 < out_stride) {
+      if (vec_ok && 4 * v + 3 < out_width) {
         *reinterpret_cast<float4*>(dst + 4 * v) = x;
       } else {
         float xs[4] = {x.x, x.y, x.z, x.w};
-        for (int e = 0; e < 4; ++e) if (4 * v + e < out_stride) dst[4 * v + e] = xs[e];
+        for (int e = 0; e < 4; ++e) if (4 * v + e < out_width) dst[4 * v + e] = xs[e];
       }
     }
   }
@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) push_rows_kernel(TableView t, const long 
 // Row layout int[K+1], last element = number of non-zero topics.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pull_rows_i32_kernel(TableView t, const long long* __restrict__ keys,
-                                                            int n, int* __restrict__ out, int out_stride) {
+                                                            int n, int* __restrict__ out, int out_stride,
+                                                            int out_width) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int vec = t.row_stride >> 2;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) pull_rows_i32_kernel(TableView t, const l
     for (int v = lane; v < vec; v += 32) {
       int4 x = ld_stream_i4(src + 4 * v);
       int xs[4] = {x.x, x.y, x.z, x.w};
-      for (int e = 0; e < 4; ++e) if (4 * v + e < out_stride) dst[4 * v + e] = xs[e];
+      for (int e = 0; e < 4; ++e) if (4 * v + e < out_width) dst[4 * v + e] = xs[e];
     }
   }
 }
@@ -205,6 +206,171 @@ __global__ void __launch_bounds__(512) migrate_copy_kernel(const int4* __restric
   for (; i < n_vec; i += stride) dst[i] = ld_stream_i4(reinterpret_cast<const int*>(src + i));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Live block migration, second generation (K10): a LIST of blocks moves in ONE launch with the
+// bulk-copy engine (cp.async.bulk = TMA 1-D, SASS UBLKCP), run by the SENDER on its side stream:
+//     old slab (local HBM) --TMA--> shared-memory stage --TMA--> new slab (peer HBM over NVLink)
+//                                                      \--TMA--> snapshot (local HBM)
+// One elected thread per CTA drives a ring of MIG_STAGES x MIG_CHUNK bytes (4 x 48 KB in flight per
+// SM); the other threads idle.  Accessors are NOT stopped: pushes that still land in the old slab
+// after its bytes were read (stale pointer, in-flight kernels) are forwarded later by
+// migrate_drain_kernel as  new += old - snapshot  -- exact for the additive update functions.
+// Reference: MigrationExecutor.java:134-295 (ownership-first move; redirected stale accesses).
+// ------------------------------------------------------------------------------------------
+static constexpr int MIG_CHUNK = 48 * 1024;
+static constexpr int MIG_STAGES = 4;
+
+__device__ __forceinline__ void mig_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mig_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mig_mbar_wait(uint32_t bar, uint32_t parity) {
+  for (long long it = 0; it < 400000000LL; ++it) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;     // bounded: a lost transaction must not hang the GPU
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+
+// work item = (block, chunk); item i -> block i / chunks_per_block.  snap_ptrs may be null (plain copy).
+__global__ void __launch_bounds__(128) migrate_bulk_kernel(const long long* __restrict__ src_ptrs,
+                                                           const long long* __restrict__ dst_ptrs,
+                                                           const long long* __restrict__ snap_ptrs, int n_blocks,
+                                                           long long block_bytes, int* __restrict__ err) {
+  extern __shared__ __align__(128) unsigned char mig_smem[];
+  __shared__ __align__(8) unsigned long long mig_bar[MIG_STAGES];
+  if (threadIdx.x != 0) return;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(mig_smem);
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(mig_bar);
+  for (int s = 0; s < MIG_STAGES; ++s) mig_mbar_init(bar0 + 8 * s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  const long long chunks_per_block = (block_bytes + MIG_CHUNK - 1) / MIG_CHUNK;
+  const long long n_items = chunks_per_block * n_blocks;
+  // software pipeline over this CTA's items: issue load(i + STAGES - 1) before storing item i
+  long long issued = 0, done = 0;
+  long long next_item = blockIdx.x;
+  long long item_of[MIG_STAGES];
+  auto item_geom = [&](long long it, const char*& src, char*& dst, char*& snap, uint32_t& bytes) {
+    const long long b = it / chunks_per_block, c = it - b * chunks_per_block;
+    const long long off = c * MIG_CHUNK;
+    bytes = (uint32_t)min((long long)MIG_CHUNK, block_bytes - off);
+    src = reinterpret_cast<const char*>(src_ptrs[b]) + off;
+    dst = reinterpret_cast<char*>(dst_ptrs[b]) + off;
+    snap = snap_ptrs ? reinterpret_cast<char*>(snap_ptrs[b]) + off : nullptr;
+  };
+  while (true) {
+    // fill the ring
+    while (next_item < n_items && issued - done < MIG_STAGES) {
+      const int s = (int)(issued % MIG_STAGES);
+      if (issued >= MIG_STAGES) {
+        // the stage's previous stores must have finished READING shared memory before it is overwritten
+        asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(MIG_STAGES - 1) : "memory");
+      }
+      const char* src; char* dst; char* snap; uint32_t bytes;
+      item_geom(next_item, src, dst, snap, bytes);
+      mig_mbar_expect_tx(bar0 + 8 * s, bytes);
+      bulk_g2s(smem0 + s * MIG_CHUNK, src, bytes, bar0 + 8 * s);
+      item_of[s] = next_item;
+      ++issued;
+      next_item += gridDim.x;
+    }
+    if (done == issued) break;
+    const int s = (int)(done % MIG_STAGES);
+    if (!mig_mbar_wait(bar0 + 8 * s, (uint32_t)((done / MIG_STAGES) & 1))) { atomicExch(err, 4); return; }
+    const char* src; char* dst; char* snap; uint32_t bytes;
+    item_geom(item_of[s], src, dst, snap, bytes);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    bulk_s2g(dst, smem0 + s * MIG_CHUNK, bytes);
+    if (snap) bulk_s2g(snap, smem0 + s * MIG_CHUNK, bytes);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    ++done;
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete (not just read) before exit
+  __threadfence_system();
+}
+
+// new += old - snapshot for every element that changed after it was copied.  IS_INT selects s32 arithmetic.
+template <bool IS_INT>
+__global__ void __launch_bounds__(256) migrate_drain_kernel(const long long* __restrict__ old_ptrs,
+                                                            const long long* __restrict__ snap_ptrs,
+                                                            const long long* __restrict__ new_ptrs, int n_blocks,
+                                                            long long vec_per_block,
+                                                            unsigned long long* __restrict__ forwarded) {
+  const long long total = vec_per_block * n_blocks;
+  unsigned long long mine = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / vec_per_block, v = i - b * vec_per_block;
+    const int4 o = ld_stream_i4(reinterpret_cast<const int*>(old_ptrs[b]) + 4 * v);
+    const int4 s = ld_stream_i4(reinterpret_cast<const int*>(snap_ptrs[b]) + 4 * v);
+    if (o.x == s.x && o.y == s.y && o.z == s.z && o.w == s.w) continue;
+    const int oo[4] = {o.x, o.y, o.z, o.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (oo[e] == ss[e]) continue;
+      ++mine;
+      if (IS_INT) {
+        int* p = reinterpret_cast<int*>(new_ptrs[b]) + 4 * v + e;
+        asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" :: "l"(p), "r"(oo[e] - ss[e]) : "memory");
+      } else {
+        float* p = reinterpret_cast<float*>(new_ptrs[b]) + 4 * v + e;
+        red_add_f32_sys(p, __int_as_float(oo[e]) - __int_as_float(ss[e]));
+      }
+    }
+  }
+  if (mine) atomicAdd(forwarded, mine);
+  __threadfence_system();
+}
+
+// Ownership flip of a LIST of blocks in THIS GPU's pointer table (one launch, release semantics).
+__global__ void flip_blocks_kernel(long long* __restrict__ ptr_table, const int* __restrict__ blocks,
+                                   const long long* __restrict__ new_ptrs, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    asm volatile("st.release.sys.global.b64 [%0], %1;" :: "l"(ptr_table + blocks[i]), "l"(new_ptrs[i]) : "memory");
+  }
+}
+
+// Owner-side decay of a list of local slabs in one launch (dense L2 term; the lazy scale avoids it on BSP paths).
+__global__ void __launch_bounds__(256) scale_blocks_kernel(const long long* __restrict__ ptrs, int n_blocks,
+                                                           long long vec_per_block, float factor) {
+  const long long total = vec_per_block * n_blocks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / vec_per_block, v = i - b * vec_per_block;
+    float4* p = reinterpret_cast<float4*>(ptrs[b]) + v;
+    float4 x = *p;
+    x.x *= factor; x.y *= factor; x.z *= factor; x.w *= factor;
+    *p = x;
+  }
+}
+
+// ASSIGN for int32 tables (checkpoint restore of the LDA model): bit-exact copy, no float conversion.
+__global__ void __launch_bounds__(256) put_rows_i32_kernel(TableView t, const long long* __restrict__ keys, int n,
+                                                           const int* __restrict__ values, int v_stride) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    int* dst = row_ptr<int>(t, keys[i]);
+    const int* src = values + (size_t)i * v_stride;
+    for (int e = lane; e < t.row_dim; e += 32) dst[e] = src[e];
+  }
+}
+
 // Ownership flip: write the new base pointer of `block` into every GPU's pointer table
 // (ptr_tables[g] is the VA of GPU g's table as mapped here) and publish with a system fence.
 __global__ void flip_owner_kernel(const long long* __restrict__ ptr_tables, int n_tables, int block,
@@ -251,7 +417,7 @@ static TableView make_view(const at::Tensor& block_ptrs, int64_t rows_per_block,
   TORCH_CHECK(block_ptrs.is_cuda() && block_ptrs.scalar_type() == at::kLong, "block_ptrs must be cuda int64");
   TableView v;
   v.block_ptrs = reinterpret_cast<const long long*>(block_ptrs.data_ptr<int64_t>());
-  v.num_blocks = (int)block_ptrs.numel();
+  v.num_blocks = (int)block_ptrs.numel() - 2;   // two guard words follow the pointers
   v.rows_per_block = (int)rows_per_block;
   v.row_stride = (int)row_stride;
   v.row_dim = (int)row_dim;
@@ -274,16 +440,17 @@ void table_pull(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_strid
   if (n == 0) return;
   TORCH_CHECK(keys.scalar_type() == at::kLong && keys.is_cuda());
   TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.size(0) == n && out.stride(1) == 1);
+  TORCH_CHECK(out.size(1) <= row_stride, "pull: output rows are wider than the table rows");
   if (out.scalar_type() == at::kFloat) {
     pull_rows_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
         v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, out.data_ptr<float>(),
-        (int)out.stride(0),
+        (int)out.stride(0), (int)out.size(1),
         (int)((out.stride(0) % 4 == 0) && (reinterpret_cast<uintptr_t>(out.data_ptr<float>()) % 16 == 0)));
   } else {
     TORCH_CHECK(out.scalar_type() == at::kInt);
     pull_rows_i32_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
         v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, out.data_ptr<int>(),
-        (int)out.stride(0));
+        (int)out.stride(0), (int)out.size(1));
   }
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
@@ -364,6 +531,84 @@ void migrate_copy(int64_t src_ptr, int64_t dst_ptr, int64_t nbytes) {
   int grid = (int)std::min<long long>((n_vec + 2047) / 2048, 148 * 4);
   migrate_copy_kernel<<<grid, 512, 0, stream>>>(reinterpret_cast<const int4*>(src_ptr),
                                                 reinterpret_cast<int4*>(dst_ptr), n_vec);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void migrate_bulk(at::Tensor src_ptrs, at::Tensor dst_ptrs, c10::optional<at::Tensor> snap_ptrs, int64_t block_bytes,
+                  at::Tensor err) {
+  c10::cuda::CUDAGuard guard(src_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int n = (int)src_ptrs.numel();
+  if (n == 0) return;
+  TORCH_CHECK(block_bytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+  TORCH_CHECK(dst_ptrs.numel() == n && (!snap_ptrs.has_value() || snap_ptrs->numel() == n));
+  const int smem = MIG_STAGES * MIG_CHUNK;
+  // per device (executors of one process drive different GPUs), so set it on every call: it is a cheap host call
+  C10_CUDA_CHECK(cudaFuncSetAttribute(migrate_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const long long items = ((block_bytes + MIG_CHUNK - 1) / MIG_CHUNK) * n;
+  const int grid = (int)std::min<long long>(items, 148);
+  migrate_bulk_kernel<<<grid, 128, smem, stream>>>(
+      reinterpret_cast<const long long*>(src_ptrs.data_ptr<int64_t>()),
+      reinterpret_cast<const long long*>(dst_ptrs.data_ptr<int64_t>()),
+      snap_ptrs.has_value() ? reinterpret_cast<const long long*>(snap_ptrs->data_ptr<int64_t>()) : nullptr, n,
+      (long long)block_bytes, err.data_ptr<int>());
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptrs, int64_t block_bytes, bool is_int,
+                   at::Tensor forwarded) {
+  c10::cuda::CUDAGuard guard(old_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int n = (int)old_ptrs.numel();
+  if (n == 0) return;
+  TORCH_CHECK(forwarded.scalar_type() == at::kLong && block_bytes % 16 == 0);
+  const long long vpb = block_bytes / 16;
+  const int grid = (int)std::min<long long>((vpb * n + 255) / 256, 148 * 16);
+  auto* fw = reinterpret_cast<unsigned long long*>(forwarded.data_ptr<int64_t>());
+  auto* o = reinterpret_cast<const long long*>(old_ptrs.data_ptr<int64_t>());
+  auto* sn = reinterpret_cast<const long long*>(snap_ptrs.data_ptr<int64_t>());
+  auto* nw = reinterpret_cast<const long long*>(new_ptrs.data_ptr<int64_t>());
+  if (is_int) migrate_drain_kernel<true><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw);
+  else migrate_drain_kernel<false><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void flip_blocks(at::Tensor ptr_table, at::Tensor blocks, at::Tensor new_ptrs) {
+  c10::cuda::CUDAGuard guard(ptr_table.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int n = (int)blocks.numel();
+  if (n == 0) return;
+  TORCH_CHECK(blocks.scalar_type() == at::kInt && new_ptrs.scalar_type() == at::kLong && new_ptrs.numel() == n);
+  flip_blocks_kernel<<<(n + 127) / 128, 128, 0, stream>>>(
+      reinterpret_cast<long long*>(ptr_table.data_ptr<int64_t>()), blocks.data_ptr<int>(),
+      reinterpret_cast<const long long*>(new_ptrs.data_ptr<int64_t>()), n);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void scale_blocks(at::Tensor ptrs, int64_t block_bytes, double factor) {
+  c10::cuda::CUDAGuard guard(ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int n = (int)ptrs.numel();
+  if (n == 0) return;
+  const long long vpb = block_bytes / 16;
+  const int grid = (int)std::min<long long>((vpb * n + 255) / 256, 148 * 16);
+  scale_blocks_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const long long*>(ptrs.data_ptr<int64_t>()), n, vpb,
+                                                (float)factor);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
+                   at::Tensor keys, at::Tensor values) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && values.scalar_type() == at::kInt && values.dim() == 2 &&
+              values.size(0) == n && values.stride(1) == 1 && values.size(1) >= row_dim);
+  put_rows_i32_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
+      v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, values.data_ptr<int>(),
+      (int)values.stride(0));
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -1,12 +1,14 @@
 """Host-memory stand-in for `DeviceExecutor`, for CPU tests of the DRIVER side of the device-table protocol.
 
 It speaks exactly the control messages of the HBM backend -- `device_info` in TableInitAck, TablePeerMap,
-TableQuiesce / TableResume, DeviceMoveRecv, DeviceOwnershipFlip (et/device_executor.py) -- but keeps the rows in the
-host dense blocks: "peer memory" is a process-wide registry of executors, the table gate is the write lock of every
-block's ownership lock.  The production GPU code is not involved; what is exercised is AllocatedTable's device paths
+TableQuiesce / TableResume, DeviceMoveAlloc / Send / Drain, DeviceOwnershipFlip (et/device_executor.py) -- but keeps the rows in the
+host dense blocks: "peer memory" is a process-wide registry of executors; the live move keeps a snapshot at the
+sender, fences each moved block through its ownership write lock and forwards late updates at the drain.  The production GPU code is not involved; what is exercised is AllocatedTable's device paths
 (`_exchange_peer_map`, `_device_move` incl. its abort path, late subscribers) and everything above them.
 """
 from typing import Any, Callable, Dict, List
+
+import numpy as np
 
 from harmony_b200.et.config import TableConfiguration
 from harmony_b200.et.executor import Executor
@@ -54,35 +56,64 @@ class EmuDeviceExecutor(Executor):
             unlock()
         self.send_to_driver({"type": "TableResumeAck", "op_id": m["op_id"], "table_id": m["table_id"]})
 
-    def _on_DeviceMoveRecv(self, m):
+    # ---- live migration: alloc / send (+ snapshot) / flip (+ per-block fence) / drain ----
+    def _on_DeviceMoveAlloc(self, m):
         if self.executor_id in EmuDeviceExecutor.fail_recv_on:
             raise MemoryError("emulated: receiver arena is full")
-        comps = self.tables.get_components(m["table_id"])
-        locs = {}
-        for b in m["block_ids"]:
-            owner = comps.ownership.owners()[b]
-            src = EmuDeviceExecutor.registry[owner].tables.get_components(m["table_id"])
-            keys, vals = src.block_store.get(b).export_items()          # the "P2P bulk copy"
-            comps.block_store.put_block(b, keys, vals)
-            locs[b] = (self.executor_id, 0, b, {})
-        self.send_to_driver({"type": "DeviceMoveRecvAck", "op_id": m["op_id"], "table_id": m["table_id"],
+        locs = {b: (self.executor_id, 0, b, {}) for b in m["block_ids"]}
+        self.send_to_driver({"type": "DeviceMoveAllocAck", "op_id": m["op_id"], "table_id": m["table_id"],
                              "locs": locs})
+
+    def _on_DeviceMoveAbort(self, m):
+        self.send_to_driver({"type": "DeviceMoveAbortAck", "op_id": m["op_id"], "table_id": m["table_id"]})
+
+    def _on_DeviceMoveSend(self, m):
+        comps = self.tables.get_components(m["table_id"])
+        self._snap = getattr(self, "_snap", {})
+        for b, loc in m["locs"].items():
+            b = int(b)
+            keys, vals = comps.block_store.get(b).export_items()          # the "bulk copy" + the local snapshot
+            dst = EmuDeviceExecutor.registry[loc[0]].tables.get_components(m["table_id"])
+            dst.block_store.put_block(b, keys, [np.array(v, copy=True) for v in vals])
+            self._snap[(m["table_id"], b)] = {k: np.array(v, copy=True) for k, v in zip(keys, vals)}
+        self.send_to_driver({"type": "DeviceMoveSendAck", "op_id": m["op_id"], "table_id": m["table_id"],
+                             "copy_ms": 0.0, "bytes": 0})
 
     def _on_DeviceOwnershipFlip(self, m):
         comps = self.tables.try_get_components(m["table_id"])
         if comps is not None:
             for b in m["locs"]:
                 b = int(b)
-                old = comps.ownership.owners()[b]
-                # the gate already excludes accessors: update the cache the way DeviceExecutor does (no latch)
-                comps.ownership._owners[b] = m["new_owner"]
-                with comps.ownership._meta_lock:
-                    nb = comps.ownership._num_blocks
-                    nb[old] = nb.get(old, 1) - 1
-                    nb[m["new_owner"]] = nb.get(m["new_owner"], 0) + 1
-                if old == self.executor_id and m["new_owner"] != self.executor_id:
-                    comps.block_store.remove_block(b)
+                # the fence of THIS block: in-flight accessors hold its read lock; nothing else is stopped
+                unlock = comps.ownership.hold_write_lock(b)
+                try:
+                    old = comps.ownership.owners()[b]
+                    comps.ownership._owners[b] = m["new_owner"]
+                    with comps.ownership._meta_lock:
+                        nb = comps.ownership._num_blocks
+                        nb[old] = nb.get(old, 1) - 1
+                        nb[m["new_owner"]] = nb.get(m["new_owner"], 0) + 1
+                finally:
+                    unlock()
         self.send_to_driver({"type": "DeviceOwnershipFlipAck", "op_id": m["op_id"], "table_id": m["table_id"]})
+
+    def _on_DeviceMoveDrain(self, m):
+        comps = self.tables.get_components(m["table_id"])
+        forwarded = 0
+        for b in m["block_ids"]:
+            b = int(b)
+            snap = self._snap.pop((m["table_id"], b))
+            keys, vals = comps.block_store.get(b).export_items()
+            owner = comps.ownership.owners()[b]
+            dst = EmuDeviceExecutor.registry[owner].tables.get_components(m["table_id"])
+            late = [(k, np.asarray(v) - snap[k]) for k, v in zip(keys, vals) if k in snap and np.any(np.asarray(v) != snap[k])]
+            late += [(k, np.asarray(v)) for k, v in zip(keys, vals) if k not in snap]
+            if late:                                                      # new += old - snapshot
+                dst.block_store.get(b).multi_update([k for k, _ in late], [d for _, d in late])
+                forwarded += len(late)
+            comps.block_store.remove_block(b)
+        self.send_to_driver({"type": "DeviceMoveDrainAck", "op_id": m["op_id"], "table_id": m["table_id"],
+                             "forwarded": forwarded})
 
     def shutdown(self):
         EmuDeviceExecutor.registry.pop(self.executor_id, None)

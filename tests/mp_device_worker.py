@@ -1,7 +1,11 @@
-"""Multi-GPU worker (launched by torchrun from test_multigpu.py): validates the peer-memory data
-plane -- IPC mapping, pull / push across GPUs, device clocks, block migration, fused MLR step."""
+"""Multi-GPU worker (launched by torchrun from test_multigpu.py on ALL GPUs of the box): validates the
+peer-memory data plane -- VMM / fd-passed mappings, multicast (NVLS) symmetric regions, pull / push across
+GPUs, device clocks, the fused MLR step in pull mode and in the three ship-mode flavours, ship == pull after
+many steps, LIVE block migration with pushes racing the move, the in-kernel key guard."""
+import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -18,17 +22,24 @@ def main():
     from harmony_b200.et.config import TableConfiguration
     from harmony_b200.et.device_table import DeviceTable
     from harmony_b200.models.mlr import MLRDeviceModel, mlr_reference_step, synthetic_batch
+    from harmony_b200.models.mlr_ship import MLRShipModel, MLRShipModelV1, route_batches
     from harmony_b200.parallel.device_clock import DeviceClock
     from harmony_b200.parallel.peer import PeerArena, PeerGroup
 
+    report = {"world": world}
     group = PeerGroup.from_env()
     arena = PeerArena(lr, group, segment_bytes=256 << 20)
+    report["arena_kind"] = arena.kind
     cap, dim = 10000, 100
     conf = TableConfiguration(table_id="t", dense=True, capacity=cap, row_dim=dim, num_total_blocks=32,
                               is_ordered=False, backend="device",
                               update_function={"name": "add", "params": {"init": "gaussian", "std": 0.01, "seed": 9}})
     table = DeviceTable(conf, arena, group)
     clock = DeviceClock(arena, group)
+
+    def sync():
+        clock.barrier(); torch.cuda.synchronize(); clock.check()
+
     W0 = table.to_dense().clone()
     # every rank must see the same (key-deterministic) initial model
     ref0 = W0.clone(); dist.broadcast(ref0, 0)
@@ -37,7 +48,7 @@ def main():
     # 1. cross-GPU push: every rank adds (rank+1) to every element of every row
     keys = torch.arange(cap, device=dev)
     table.push(keys, torch.full((cap, dim), float(rank + 1), device=dev))
-    clock.barrier(); torch.cuda.synchronize(); clock.check()
+    sync()
     expect = W0 + sum(r + 1 for r in range(world))
     got = table.to_dense()
     assert torch.allclose(got, expect, atol=1e-5), f"push mismatch {(got - expect).abs().max()}"
@@ -48,55 +59,150 @@ def main():
     model = MLRDeviceModel(table, classes, step_size=0.01)
     batch = synthetic_batch(200, cap, classes, 11, seed=100 + rank).to(dev)
     W1 = table.to_dense().clone()
-    clock.barrier(); torch.cuda.synchronize()
+    sync()
     model.step(batch)
-    clock.barrier(); torch.cuda.synchronize(); clock.check()
+    sync()
     Wn, _, _ = mlr_reference_step(W1, batch, classes, 0.01)
     delta = Wn - W1
     dist.all_reduce(delta)
-    got = table.to_dense()
-    err = float((got - (W1 + delta)).abs().max())
+    err = float((table.to_dense() - (W1 + delta)).abs().max())
     assert err < 1e-4, f"mlr multi-gpu mismatch {err}"
     clock.barrier()
 
-    # 2b. "ship the activations" mode computes the same update (dot at the owners, only [B, C] moves)
-    from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
+    # 2b. ship mode (dot at the owners, only [B, C] moves) computes the same update, in all three flavours:
+    #     v2 over NVLS multimem, v2 over unicast peer loads / stores, v1 (device barriers)
     all_batches = [synthetic_batch(200, cap, classes, 11, seed=300 + r) for r in range(world)]
     rb = route_batches(table, all_batches, rank).to(dev)
-    ship = MLRShipModel(table, arena, group, clock, classes, 0.01, 200)
-    W2 = table.to_dense().clone()
-    clock.barrier(); torch.cuda.synchronize()
-    ship.step(rb)
-    clock.barrier(); torch.cuda.synchronize(); clock.check()
-    delta = torch.zeros_like(W2)
-    loss_ref = 0.0
-    for r in range(world):
-        Wn, l, _ = mlr_reference_step(W2, all_batches[r].to(dev), classes, 0.01)
-        delta += Wn - W2
-        if r == rank:
-            loss_ref = l
-    err = float((table.to_dense() - (W2 + delta)).abs().max())
-    assert err < 1e-4, f"ship-mode mismatch {err}"
-    assert abs(float(ship.stats[0]) - loss_ref) / max(1.0, loss_ref) < 2e-3, (float(ship.stats[0]), loss_ref)
-    ship.step(rb); clock.barrier(); torch.cuda.synchronize(); clock.check()      # buffers are reusable
+    flavours = [("v2_nvls", lambda: MLRShipModel(table, arena, group, None, classes, 0.01, 200)),
+                ("v2_unicast", lambda: MLRShipModel(table, arena, group, None, classes, 0.01, 200, multicast=False)),
+                ("v1", lambda: MLRShipModelV1(table, arena, group, clock, classes, 0.01, 200))]
+    for name, make in flavours:
+        ship = make()
+        if name == "v2_nvls":
+            report["nvls_multicast"] = bool(ship.nvls)
+            report["mc_error"] = getattr(ship.region, "mc_error", None)
+        for it in range(3):                        # buffers / epochs / flags are reusable step after step
+            W2 = table.to_dense().clone()
+            ship.stats.zero_()
+            sync()
+            ship.step(rb)
+            sync()
+            if hasattr(ship, "check"):
+                ship.check()
+            delta = torch.zeros_like(W2)
+            loss_ref = 0.0
+            for r in range(world):
+                Wn, l, _ = mlr_reference_step(W2, all_batches[r].to(dev), classes, 0.01)
+                delta += Wn - W2
+                if r == rank:
+                    loss_ref = l
+            err = float((table.to_dense() - (W2 + delta)).abs().max())
+            assert err < 1e-4, f"ship-mode {name} step {it} mismatch {err}"
+            assert abs(float(ship.stats[0]) - loss_ref) / max(1.0, loss_ref) < 2e-3, (name, float(ship.stats[0]), loss_ref)
+        clock.barrier()
+
+    # 2c. ship == pull after 40 steps with a learning rate that moves the loss (two tables, same seeds)
+    def fresh(tid):
+        c = TableConfiguration(table_id=tid, dense=True, capacity=cap, row_dim=dim, num_total_blocks=32,
+                               is_ordered=False, backend="device",
+                               update_function={"name": "add", "params": {"init": "gaussian", "std": 0.01, "seed": 5}})
+        return DeviceTable(c, arena, group)
+    ta, tb = fresh("ta"), fresh("tb")
+    pull_m = MLRDeviceModel(ta, classes, step_size=0.05, lam=0.0005)         # lazy L2 on both paths
+    ship_m = MLRShipModel(tb, arena, group, None, classes, 0.05, 200, lam=0.0005)
+    mine = all_batches[rank].to(dev)
+    rb2 = route_batches(tb, all_batches, rank).to(dev)
+    losses = []
+    for it in range(40):
+        pull_m.stats.zero_(); ship_m.stats.zero_()
+        sync()
+        pull_m.step(mine, 200 * world)
+        ship_m.step(rb2)
+        sync()
+        losses.append((float(pull_m.stats[0]), float(ship_m.stats[0])))
+    ship_m.check()
+    pull_m.fold_scale(); ship_m.renormalize()
+    sync()
+    da, db = ta.to_dense(), tb.to_dense()
+    rel = float((da - db).abs().max() / da.abs().max())
+    assert rel < 2e-3, f"ship vs pull diverged after 40 steps: {rel}"
+    assert losses[-1][0] < 0.9 * losses[0][0], f"the loss did not move: {losses[0]} -> {losses[-1]}"
+    assert abs(losses[-1][0] - losses[-1][1]) / losses[-1][0] < 5e-3, losses[-1]
+    report["ship_vs_pull_rel_err_40_steps"] = rel
+    report["loss_first_last"] = [round(losses[0][0], 3), round(losses[-1][0], 3)]
     clock.barrier()
 
-    # 3. migration: move block 3 to the next rank; content and subsequent pushes stay correct
-    before = table.to_dense().clone()
-    src = table.owners[3]; dst = (src + 1) % world
-    table.migrate_block(3, dst)
-    assert table.owners[3] == dst
-    after = table.to_dense()
-    assert torch.equal(before, after), "migration changed the table content"
-    table.push(keys, torch.ones((cap, dim), device=dev))
-    clock.barrier(); torch.cuda.synchronize(); clock.check()
-    assert torch.allclose(table.to_dense(), before + world, atol=1e-5)
+    # 3. LIVE migration: move 5 blocks of rank 0 to the last rank while EVERY rank keeps pushing ones on a side
+    #    stream; nothing is stopped, nothing is lost (late pushes are forwarded by the drain)
+    tm = DeviceTable(TableConfiguration(table_id="tm", dense=True, capacity=cap, row_dim=dim, num_total_blocks=32,
+                                        is_ordered=False, backend="device",
+                                        update_function={"name": "add", "params": {"init": "const", "value": 0.0}}),
+                     arena, group)                 # integer-valued sums: exact in fp32
+    sync()
+    src, dst = 0, world - 1
+    moving = [b for b in range(tm.num_blocks) if tm.owners[b] == src][:5]
+    pusher = torch.cuda.Stream(device=dev)
+    ones = torch.ones((cap, dim), device=dev)
+    pusher.wait_stream(torch.cuda.current_stream(dev))
+    n_push = 1500
+    with torch.cuda.stream(pusher):
+        for _ in range(n_push):
+            tm.push(keys, ones)
+    stats = tm.migrate_blocks(moving, dst)             # races with the queued push kernels of every rank
+    with torch.cuda.stream(pusher):
+        for _ in range(5):
+            tm.push(keys, ones)                        # ... and pushes issued after the flip go to the new owner
+    pusher.synchronize()
+    sync()
+    after = tm.to_dense()
+    want = float(world * (n_push + 5))
+    err = float((after - want).abs().max())
+    assert err == 0.0, f"live migration lost updates: max err {err} (forwarded {stats.get('forwarded_elements')})"
+    assert all(tm.owners[b] == dst for b in moving)
     if rank == dst:
-        assert 3 in table.local_block_ids()
+        assert set(moving) <= set(tm.local_block_ids())
     if rank == src:
-        assert 3 not in table.local_block_ids()
-    clock.barrier(); torch.cuda.synchronize()
+        assert not (set(moving) & set(tm.local_block_ids()))
+        report["live_migration"] = {k: stats[k] for k in ("blocks", "bytes", "copy_ms", "forwarded_elements")}
+    clock.barrier()
+
+    # 3b. migration bandwidth: a 1 GiB move (64 blocks x 16 MiB) between two GPUs, bulk-TMA copy timed on the device
+    big_c = TableConfiguration(table_id="big", dense=True, capacity=world * 64 * 4096, row_dim=1024,
+                               num_total_blocks=world * 64, is_ordered=True, backend="device",
+                               update_function={"name": "add", "params": {"init": "const", "value": 1.0}})
+    big = DeviceTable(big_c, PeerArena(lr, group, segment_bytes=2 << 30), group)
+    sync()
+    mv = [b for b in range(big.num_blocks) if big.owners[b] == src][:64]
+    t0 = time.perf_counter()
+    st = big.migrate_blocks(mv, dst)
+    wall = time.perf_counter() - t0
+    if rank == src:
+        report["migration_1GiB"] = {"bytes": st["bytes"], "copy_ms": round(st["copy_ms"], 3),
+                                    "copy_GBps": round(st["bytes"] / (st["copy_ms"] / 1e3) / 1e9, 1),
+                                    "frac_of_770": round(st["bytes"] / (st["copy_ms"] / 1e3) / 1e9 / 770.0, 3),
+                                    "wall_ms_alloc_copy_flip_drain": round(wall * 1e3, 1)}
+    chk = big.pull(torch.tensor([mv[0] * big.rows_per_block + 7], device=dev))
+    assert torch.all(chk == 1.0), "moved block content is wrong"
+    clock.barrier()
+
+    # 4. the key guard: an out-of-range key is clamped + reported, never a wild (peer) write
     if rank == 0:
+        table.push(torch.tensor([cap * 1000], device=dev), torch.zeros((1, dim), device=dev))
+        torch.cuda.synchronize()
+        try:
+            table.check()
+            raise AssertionError("bad key was not reported")
+        except IndexError:
+            pass
+    table.check()
+    sync()
+    reports = [None] * world
+    dist.all_gather_object(reports, report)
+    if rank == 0:
+        merged = {}
+        for r in reports:
+            merged.update(r)
+        print("MULTIGPU_REPORT " + json.dumps(merged))
         print("MULTIGPU_OK")
     dist.barrier()
     dist.destroy_process_group()

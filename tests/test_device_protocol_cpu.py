@@ -65,7 +65,7 @@ def test_device_protocol_init_move_and_late_subscriber(cluster):
 
 
 def test_device_move_excludes_accessors_and_keeps_sums_exact(cluster):
-    """Updates racing with a device migration: the quiesce gate makes the copy atomic, nothing is lost."""
+    """Updates racing with a LIVE device migration (nobody is stopped): late updates are forwarded, nothing is lost."""
     master, execs, launcher = cluster
     master.create_table(_conf("race"), execs[:2]).get(30)
     table = master.get_table("race")
@@ -98,7 +98,7 @@ def test_device_move_aborts_cleanly_when_the_receiver_fails(cluster):
     before = table.get_partition_info()
     EmuDeviceExecutor.fail_recv_on = {execs[1].id}
     fut = table.move_blocks(execs[0].id, execs[1].id, 4)
-    with pytest.raises(RuntimeError, match="DeviceMoveRecv failed"):
+    with pytest.raises(RuntimeError, match="DeviceMoveAlloc failed"):
         fut.get(30)
     # nothing moved, the gate is open again (accessors work), and a later move succeeds
     assert table.get_partition_info() == before

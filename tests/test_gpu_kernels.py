@@ -135,13 +135,114 @@ def test_mlr_ship_mode_single_gpu_matches_reference(arena):
     clock = DeviceClock(arena, g)
     b = synthetic_batch(300, features, classes, 17, seed=8)
     rb = route_batches(t, [b], 0).to("cuda")
-    m = MLRShipModel(t, arena, g, clock, classes, 0.02, 300)
+    from harmony_b200.models.mlr_ship import MLRShipModelV1
+    for cls in (MLRShipModel, MLRShipModelV1):          # v2: 3 launches + flags; v1: device barriers
+        m = cls(t, arena, g, clock, classes, 0.02, 300)
+        for _ in range(2):
+            W0 = t.to_dense().clone()
+            m.stats.zero_()
+            m.step(rb)
+            torch.cuda.synchronize()
+            Wref, loss_ref, _ = mlr_reference_step(W0, b.to("cuda"), classes, 0.02)
+            torch.testing.assert_close(t.to_dense(), Wref, rtol=2e-3, atol=2e-5)
+            assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 2e-3
+        if hasattr(m, "check"):
+            m.check()
+    t.close()
+
+
+@pytest.mark.parametrize("mode", ["pull", "ship"])
+def test_mlr_lazy_l2_matches_reference_with_lambda(arena, mode):
+    """W' = (1 - step lam B) W + delta (MLRTrainer.java:387-397) through the lazy scale: no dense pass per step."""
+    from harmony_b200.models.mlr import MLRDeviceModel, mlr_reference_step, synthetic_batch
+    from harmony_b200.models.mlr_ship import MLRShipModel, route_batches
+    from harmony_b200.parallel.peer import PeerGroup
+    classes, features, lam, step = 100, 5000, 0.05, 0.02
+    t = _table(arena, features, classes, 16, False, {"name": "add", "params": {"init": "gaussian", "std": 0.05, "seed": 7}})
+    hb = synthetic_batch(128, features, classes, 9, seed=3)
+    W = t.to_dense().clone()
+    if mode == "pull":
+        m = MLRDeviceModel(t, classes, step, lam=lam)
+        stepf = lambda: m.step(hb.to("cuda"))              # noqa: E731
+        fold = m.fold_scale
+    else:
+        m = MLRShipModel(t, arena, PeerGroup(), None, classes, step, 128, lam=lam)
+        rb = route_batches(t, [hb], 0).to("cuda")
+        stepf = lambda: m.step(rb)                         # noqa: E731
+        fold = m.renormalize
+    for _ in range(5):
+        stepf()
+        W, _, _ = mlr_reference_step(W, hb.to("cuda"), classes, step, lam)
+    torch.cuda.synchronize()
+    assert m.scale < 1.0                                   # nothing was folded yet: the table holds v = w / s
+    fold()
+    torch.testing.assert_close(t.to_dense(), W, rtol=2e-3, atol=2e-5)
+    t.close()
+
+
+def test_bulk_migration_copy_snapshot_and_drain(arena):
+    """K10: one bulk-TMA launch copies a LIST of slabs to their new place + a snapshot; the drain forwards what
+    landed in the old slabs afterwards (new += old - snapshot)."""
+    from harmony_b200.ops import native
+    n = native()
+    nb, elems = 5, (3 << 20) // 4 + 4096                   # not a multiple of the 48 KB chunk: exercises the tail
+    old = [torch.randn(elems, device="cuda") for _ in range(nb)]
+    new = [torch.zeros(elems, device="cuda") for _ in range(nb)]
+    snap = [torch.zeros(elems, device="cuda") for _ in range(nb)]
+    i64 = lambda ts: torch.tensor([t.data_ptr() for t in ts], dtype=torch.int64, device="cuda")   # noqa: E731
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    n.migrate_bulk(i64(old), i64(new), i64(snap), elems * 4, err)
+    torch.cuda.synchronize()
+    assert int(err) == 0
+    for o, a, b in zip(old, new, snap):
+        assert torch.equal(o, a) and torch.equal(o, b)
+    ref = [a.clone() for a in new]
+    for k, o in enumerate(old):                            # late updates on the old slabs + fresh ones on the new
+        o[k::97] += 1.0
+        new[k][5::101] += 2.0
+        ref[k][k::97] += 1.0
+        ref[k][5::101] += 2.0
+    fw = torch.zeros(1, dtype=torch.int64, device="cuda")
+    n.migrate_drain(i64(old), i64(snap), i64(new), elems * 4, False, fw)
+    torch.cuda.synchronize()
+    for a, r in zip(new, ref):
+        torch.testing.assert_close(a, r, rtol=0, atol=1e-6)
+    assert int(fw) == sum(len(range(k, elems, 97)) for k in range(nb))
+
+
+def test_key_guard_clamps_and_reports(arena):
+    t = _table(arena, 1000, 32, 8, True, {"name": "add", "params": {}})
+    t.push(torch.tensor([5, 10 ** 9, -3], device="cuda"), torch.ones((3, 32), device="cuda"))
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="out-of-range"):
+        t.check()
+    t.check()                                              # the guard words were reset
+    d = t.to_dense()
+    assert float(d[5].sum()) == 32.0 and float(d[0].sum()) == 64.0     # bad keys were clamped to key 0
+    t.close()
+
+
+def test_int32_table_put_rows_is_bit_exact(arena):
+    """Checkpoint restore of the LDA count table: ASSIGN must not convert counts to float bits."""
+    t = _table(arena, 500, 17, 8, False, {"name": "add", "params": {}}, dtype="int32")
+    keys = torch.arange(0, 500, 3, device="cuda")
+    vals = torch.randint(0, 1000, (keys.numel(), 17), device="cuda", dtype=torch.int32)
+    t.put_rows(keys, vals)
+    got = t.pull(keys)
+    assert got.dtype == torch.int32 and torch.equal(got, vals)
+    t.put_rows(keys, vals.float())                         # float input is rounded, not reinterpreted
+    assert torch.equal(t.pull(keys), vals)
+    t.close()
+
+
+def test_scale_local_is_one_launch(arena):
+    from harmony_b200 import ops
+    t = _table(arena, 4000, 64, 16, True, {"name": "add", "params": {"init": "gaussian", "std": 1.0, "seed": 1}})
     W0 = t.to_dense().clone()
-    m.step(rb)
-    Wref, loss_ref, _ = mlr_reference_step(W0, b.to("cuda"), classes, 0.02)
-    torch.testing.assert_close(t.to_dense(), Wref, rtol=2e-3, atol=2e-5)
-    assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 2e-3
-    assert float(m.L.abs().max()) == 0.0          # logits buffer re-zeroed for the next step
+    ops.reset_launches()
+    t.scale_local(0.5)
+    assert ops.launches() == 1
+    torch.testing.assert_close(t.to_dense(), W0 * 0.5)
     t.close()
 
 
