@@ -318,6 +318,13 @@ def main():
             for k, v in ship.step_timed(dev_ship[i % len(dev_ship)]).items():
                 acc[k] = acc.get(k, 0.0) + v
         m["phases_serialised_ms"] = {k: round(max_over_ranks(v / reps), 4) for k, v in sorted(acc.items())}
+        if hasattr(ship, "step_profiled"):
+            acc = {}
+            for i in range(reps):
+                barrier_sync()
+                for k, v in ship.step_profiled(dev_ship[i % len(dev_ship)]).items():
+                    acc[k] = acc.get(k, 0.0) + v
+            m["phases_overlapped_ms"] = {k: round(max_over_ranks(v / reps), 4) for k, v in sorted(acc.items())}
         modes["ship"], runners["ship"] = m, (ship.step, host_ship, ship.stats)
 
     # ---------------- pull mode ----------------

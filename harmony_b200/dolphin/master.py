@@ -325,6 +325,28 @@ class ModelChkpManager:
         self.local_chkps: List[str] = []
         self.input_chkp: Optional[str] = None
         self._lock = threading.Lock()
+        # ONE thread takes the per-epoch checkpoints: they complete -- and are recorded -- in issue order, i.e.
+        # chronologically (ModelChkpManager.checkpointIdFutures keeps the futures in issue order for the same
+        # reason), and a slow checkpoint never parks a thread of the driver pool that SyncMsg & co. need.
+        from concurrent.futures import ThreadPoolExecutor
+        self._exec = ThreadPoolExecutor(max_workers=1, thread_name_prefix="model-chkp")
+        self._pending: List[Any] = []
+
+    def create_checkpoint_async(self):
+        """Queue the checkpoint of the current epoch (returns a concurrent.futures.Future)."""
+        f = self._exec.submit(self.create_checkpoint)
+        with self._lock:
+            self._pending.append(f)
+        return f
+
+    def wait_pending(self, timeout: float = 600.0) -> None:
+        with self._lock:
+            pending, self._pending = self._pending, []
+        for f in pending:
+            try:
+                f.result(timeout=timeout)
+            except Exception as e:  # noqa: BLE001
+                LOG.warning("a per-epoch model checkpoint failed: %s", e)
 
     def create_checkpoint(self) -> None:
         mid = self._m.get_table(self.model_table_id).checkpoint().get(timeout=600)
@@ -562,9 +584,7 @@ class DolphinMaster:
         self.mini_batch_controller = MiniBatchController(epochs, nmb, int(p.get("clock_slack", 0)), self.sender)
         on_epoch = None
         if p.get("offline_model_eval"):
-            self._chkp_futs: List[Any] = []
-            on_epoch = lambda e: self._chkp_futs.append(  # noqa: E731
-                self._m.pool.submit(self.chkp_manager.create_checkpoint))
+            on_epoch = lambda e: self.chkp_manager.create_checkpoint_async()  # noqa: E731  (issue order == epoch order)
         self.progress_tracker = BatchProgressTracker(self.job_id, epochs, nmb, self.report, on_epoch)
         self.metric_manager.start_metric_collection()
         for ex in workers:
@@ -596,11 +616,7 @@ class DolphinMaster:
         if p.get("offline_model_eval"):
             # the per-epoch checkpoints run on the driver pool: let the last ones finish before anybody evaluates
             # (or drops the tables they are reading)
-            for f in getattr(self, "_chkp_futs", []):
-                try:
-                    f.result(timeout=600)
-                except Exception as e:  # noqa: BLE001
-                    LOG.warning("[%s] a per-epoch checkpoint failed: %s", self.job_id, e)
+            self.chkp_manager.wait_pending()
             self.chkp_manager.checkpoint_input()
         return [r.result for r in results]
 

@@ -53,10 +53,11 @@ DOLPHIN = [
     P("test_data_path", str, "", "", "worker"), P("input_chkp_path", str, "", "", "worker"),
     P("model_cache_enabled", bool, False, "", "worker"),
     P("job_priority", str, "normal", "normal | high: CUDA stream priority of the job's tasklets on shared GPUs", "worker"),
-    P("mini_batch_grant_size", int, 1, "mini-batches leased per SSP sync (1 = one driver round trip per mini-batch, "
+    P("mini_batch_grant_size", int, 0, "mini-batches leased per SSP sync (1 = one driver round trip per mini-batch, "
                                        "as the reference; k > 1 saves k - 1 of them and widens the staleness bound by "
                                        "k - 1; leases taper to 1 as the budget runs out; ignored while the job's task-unit "
-                                       "barriers are on)", "worker"),
+                                       "barriers are on; 0 = auto: 4 for the fused device trainers -- their kernels queue "
+                                       "on the stream and the host only syncs at the end of a lease -- else 1)", "worker"),
     P("task_unit_scheduling", str, "auto", "on | off | auto: per-phase global barriers that interleave the phases of "
                                            "co-located jobs (one driver round trip per phase); auto = on unless the "
                                            "job server's scheduler runs jobs exclusively", "worker"),

@@ -426,7 +426,10 @@ class WorkerTasklet(Tasklet):
         pending_n = 0              # mini-batches finished since the last sync (> 1 only inside a lease)
         # -mini_batch_grant_size k: one sync leases up to k mini-batches (k - 1 driver round trips less; the SSP
         # staleness bound widens by k - 1); 1 = the reference's sync per mini-batch
-        grant_size = max(1, int(self.context.params.get("mini_batch_grant_size", 1)))
+        grant_size = int(self.context.params.get("mini_batch_grant_size", 0) or 0)
+        if grant_size <= 0:        # auto: device trainers keep the stream busy across a lease, host trainers sync per batch
+            grant_size = 4 if (getattr(self.trainer, "fused_step", False) and hasattr(self.trainer, "flush")
+                               and not self.use_task_units) else 1
         if grant_size > 1 and self.use_task_units:
             # the unit barriers need the job's workers in lock-step (same unit, same sequence number); a lease lets
             # one worker run ahead while a peer is SSP-blocked at its sync -- the two waits would deadlock
@@ -437,6 +440,7 @@ class WorkerTasklet(Tasklet):
         idle_left = False          # True while this worker has left the unit barriers because it holds no data
         flush_every = float(self.context.params.get("batch_metric_flush_interval_ms", 50)) / 1000.0
         last_flush = 0.0
+        flush = getattr(self.trainer, "flush", None)       # device trainers: stream sync, once per lease (not per batch)
         while not stop and not self._abort.is_set():
             if self.input_table.get_local_tablet().get_num_data_items() == 0:
                 # no input data here (all blocks migrated away, or none was loaded): ask the master whether to stop,
@@ -475,6 +479,8 @@ class WorkerTasklet(Tasklet):
                         stop = True
                         break
                     # SYNC (void unit): SSP clock + stop flag; carries the progress of the previous mini-batch(es)
+                    if flush is not None:
+                        flush()        # device trainers: the lease's kernels have finished before progress is reported
                     done, n_done, pending_progress, pending_n = pending_progress, pending_n, None, 0
                     if self.mini_batch_barrier.await_(done, want=grant_size, progress_count=max(1, n_done)):
                         stop = True
@@ -517,6 +523,8 @@ class WorkerTasklet(Tasklet):
                     last_flush = now
             if n_batches == 0 and not stop:
                 time.sleep(0.01)                 # its blocks left in the middle of the epoch: idle from the next pass
+            if flush is not None:
+                flush()
             if not stop:
                 self.trainer.on_epoch_finished(epoch)
             em = EpochMetrics(self.job_id, ex_id, epoch, n_batches, n_inst, time.perf_counter() - epoch_t0,

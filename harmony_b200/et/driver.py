@@ -384,12 +384,30 @@ class ChkpManagerMaster:
 
     def on_chkp_done(self, chkp_id: str, executor_id: str, block_ids: List[int]) -> None:
         with self._lock:
-            c = self._chkps[chkp_id]
+            c = self._chkps.get(chkp_id)
+            if c is None:             # the checkpoint already failed on another executor
+                return
             c["temp_blocks"][executor_id] = list(block_ids)
             c["remaining"].discard(executor_id)
             done = not c["remaining"]
         if done:
             c["future"].on_completed(chkp_id)
+
+    def on_chkp_failed(self, m: Dict[str, Any]) -> None:
+        """An executor could not write (ChkpStart) or restore (ChkpLoad, has an op_id) its part: fail the waiting
+        future instead of letting `checkpoint().get()` / `create_table_from_chkp().get()` run into their timeouts."""
+        err = RuntimeError(f"checkpoint {m['chkp_id']} failed on {m.get('executor_id')}: {m.get('error')}")
+        LOG.error("%s", err)
+        if "op_id" in m:
+            with self._lock:
+                fut = self._load_futs.pop(m["op_id"], None)
+            if fut is not None and not fut.done():
+                fut.on_failed(err)
+            return
+        with self._lock:
+            c = self._chkps.pop(m["chkp_id"], None)
+        if c is not None and not c["future"].done():
+            c["future"].on_failed(err)
 
     def on_commit_ack(self, chkp_id: str, executor_id: str) -> None:
         with self._lock:
@@ -1132,6 +1150,8 @@ class ETMaster:
             self.pool.submit(self.fallback.on_table_access_req, m)
         elif t == "OwnershipReq":
             self.pool.submit(self._on_ownership_req, m)
+        elif t == "ChkpFailed":
+            self.chkp_master.on_chkp_failed(m)
         elif t == "ChkpDone":
             self.chkp_master.on_chkp_done(m["chkp_id"], m["executor_id"], m["block_ids"])
         elif t == "ChkpCommitAck":

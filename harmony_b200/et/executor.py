@@ -151,7 +151,13 @@ class Executor:
 
     # -- checkpoint --
     def _on_ChkpStart(self, m):
-        blocks = self.chkp.checkpoint(m["chkp_id"], m["table_id"], m.get("sampling_ratio", 1.0))
+        try:
+            blocks = self.chkp.checkpoint(m["chkp_id"], m["table_id"], m.get("sampling_ratio", 1.0))
+        except Exception as e:  # noqa: BLE001  (full disk, dropped table ...): fail the driver-side future, loudly
+            LOG.exception("[%s] checkpoint %s failed", self.executor_id, m["chkp_id"])
+            self.send_to_driver({"type": "ChkpFailed", "chkp_id": m["chkp_id"], "executor_id": self.executor_id,
+                                 "error": f"{type(e).__name__}: {e}"})
+            return
         self.send_to_driver({"type": "ChkpDone", "chkp_id": m["chkp_id"], "executor_id": self.executor_id,
                              "block_ids": blocks})
 
@@ -160,7 +166,13 @@ class Executor:
         self.send_to_driver({"type": "ChkpCommitAck", "chkp_id": m["chkp_id"], "executor_id": self.executor_id})
 
     def _on_ChkpLoad(self, m):
-        n = self.chkp.load(m["chkp_id"], m["table_id"], m["block_ids"], m.get("committed", False))
+        try:
+            n = self.chkp.load(m["chkp_id"], m["table_id"], m["block_ids"], m.get("committed", False))
+        except Exception as e:  # noqa: BLE001  (missing block file, multi_put timeout ...)
+            LOG.exception("[%s] restore of %s failed", self.executor_id, m["chkp_id"])
+            self.send_to_driver({"type": "ChkpFailed", "chkp_id": m["chkp_id"], "op_id": m["op_id"],
+                                 "executor_id": self.executor_id, "error": f"{type(e).__name__}: {e}"})
+            return
         self.send_to_driver({"type": "ChkpLoadDone", "chkp_id": m["chkp_id"], "op_id": m["op_id"],
                              "executor_id": self.executor_id, "num_items": n})
 

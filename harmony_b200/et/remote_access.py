@@ -247,6 +247,13 @@ class RemoteAccessOpSender:
             self.stat.inc_count_sent_get_req()
         self._send_with_retry(op, target_id)
 
+    def register_redirected_local(self, op: RemoteDataOp) -> None:
+        """A LOCAL op that bounced to the driver fallback (its table is being dropped / flushed here) comes back as a
+        TableAccessRes from the real owner: it must be findable in `_ongoing`, or its caller waits for ever."""
+        if op.reply_required:
+            with self._lock:
+                self._ongoing[op.op_id] = op
+
     def send_ops(self, ops: List[RemoteDataOp], target_id: str) -> None:
         """All block ops of one multi-key request that live on `target_id`, in one message (the reference sends one
         message per block: TableImpl.java:460-501; a GPU-era host has far fewer, fatter peers)."""
@@ -483,10 +490,13 @@ class RemoteAccessOpHandler:
         msg["fallback"] = True
         if op.is_local:
             msg["orig_id"] = self._ex.executor_id
+            self._ex.sender.register_redirected_local(op)
         try:
             self._ex.transport.send(self._ex.driver_id, msg)
         except NetworkError:
             LOG.error("cannot reach the driver for fallback of op %s", op.op_id)
+            if op.is_local:
+                self._ex.sender._fail(op)       # fail the caller now instead of hanging it
 
     def wait_ops_to_be_flushed(self, table_id: str, timeout: float = 60.0) -> None:
         tr = self._tracker(table_id)

@@ -131,7 +131,7 @@ class MLRDeviceTrainer(Trainer):
         self._batch = self._to_device_batch(mini_batch)
 
     def pull_model(self) -> None:
-        self.comps.gate.acquire_read()          # held from PULL to PUSH: migration waits for a batch boundary
+        self.comps.gate.acquire_read()          # (uncontended: live migration does not stop accessors any more)
         self.model.stats.zero_()
         if self.dense is None and self.ship is None:
             self.model.forward(self._batch, True)
@@ -154,9 +154,16 @@ class MLRDeviceTrainer(Trainer):
             bsz = self.ship.B if self.ship is not None else (
                 self._batch[0].shape[0] if self.dense is not None else self._batch.batch_size)
             self.model.apply_l2(bsz * self.num_workers)
-            self._torch.cuda.current_stream(self.dtable.device).synchronize()
+            # no stream sync here: the next mini-batches of the lease queue behind this one on the stream; the
+            # worker loop calls flush() before it reports progress (WorkerTasklet.java:122-149 blocks 4x per batch)
         finally:
             self.comps.gate.release_read()
+
+    def flush(self) -> None:
+        """Wait for the kernels of the mini-batches issued so far (end of a lease / epoch)."""
+        self._torch.cuda.current_stream(self.dtable.device).synchronize()
+        if self.ship is not None:
+            self.ship.check()
 
     def summary(self) -> Dict[str, float]:
         return {"last_batch_loss": float(self.model.stats[0])}

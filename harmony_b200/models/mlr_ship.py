@@ -265,6 +265,28 @@ class MLRShipModel:
         self.table.scale_local(self.scale)
         self.scale = 1.0
 
+    def step_profiled(self, rb: RoutedBatch) -> dict:
+        """`step()` with its real schedule (K2 resident on the side stream next to K1) and CUDA events at the kernel
+        boundaries: how long K1 runs with K2 next to it, how long K2 outlives K1, what K3 costs after its wait."""
+        self.epoch += 1
+        ls, ds = self._scales()
+        cur = torch.cuda.current_stream(self.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev[0].record(cur)
+        self.side.wait_event(ev[0])
+        with torch.cuda.stream(self.side):
+            self._k2(rb, ls, ds)
+            ev[3].record(self.side)
+        self._k1(rb)
+        ev[1].record(cur)
+        self._k3(rb)
+        ev[2].record(cur)
+        cur.wait_event(ev[3])
+        ev[4].record(cur)
+        torch.cuda.synchronize(self.device)
+        return {"k1_with_k2_resident_ms": ev[0].elapsed_time(ev[1]), "k2_end_ms": ev[0].elapsed_time(ev[3]),
+                "k3_incl_wait_ms": ev[1].elapsed_time(ev[2]), "step_ms": ev[0].elapsed_time(ev[4])}
+
     def step_timed(self, rb: RoutedBatch) -> dict:
         """One step with the three kernels serialised on the current stream and CUDA events around each
         (bench.py --ship_phases).  No overlap here by construction: it shows what each part costs alone."""

@@ -24,6 +24,8 @@
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <map>
+#include <mutex>
 
 namespace hb {
 
@@ -118,14 +120,99 @@ __global__ void __launch_bounds__(NV_THREADS) ship_fwd_kernel(
   }
 }
 
+// Warp-per-instance K1 (row_stride <= 1024 floats).  With the model sharded over N GPUs an instance has only
+// nnz / N of its features at this owner (12 at N = 8): a CTA per instance would spend its time in barriers and in a
+// serial tail.  Here every warp owns one instance: lane j fetches non-zero j (column, value), the pair is broadcast
+// with shuffles, and each lane keeps 2 rows x NV 128-bit loads in flight -- no shared memory, no block barrier.
+static constexpr int FW_THREADS = 128;
+template <int NV>
+__global__ void __launch_bounds__(FW_THREADS) ship_fwd_warp_kernel(
+    TableView W, const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
+    const float* __restrict__ csr_val, int world, int B, int tile_rows, int n_tiles,
+    float* __restrict__ P, int p_stride, unsigned* __restrict__ tile_done,
+    const long long* __restrict__ pflag_ptrs, unsigned epoch) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int rows_per_round = world * tile_rows;
+  const int n_virtual = n_tiles * rows_per_round;
+  for (int v = wglobal; v < n_virtual; v += nwarps) {
+    const int t = v / rows_per_round;
+    const int rem = v - t * rows_per_round;
+    const int w_id = rem / tile_rows;
+    const int b = t * tile_rows + (rem - w_id * tile_rows);
+    if (b >= B) continue;
+    const int r = w_id * B + b;
+    const int beg = csr_ptr[r], end = csr_ptr[r + 1];
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = beg; base < end; base += 32) {
+      const int cnt = min(32, end - base);
+      const int my_c = (lane < cnt) ? csr_col[base + lane] : 0;
+      const float my_x = (lane < cnt) ? csr_val[base + lane] : 0.f;
+      int j = 0;
+      for (; j + 2 <= cnt; j += 2) {
+        const float* r0 = row_ptr<float>(W, (long long)__shfl_sync(0xffffffffu, my_c, j));
+        const float* r1 = row_ptr<float>(W, (long long)__shfl_sync(0xffffffffu, my_c, j + 1));
+        const float x0 = __shfl_sync(0xffffffffu, my_x, j), x1 = __shfl_sync(0xffffffffu, my_x, j + 1);
+        float4 a[NV], c[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int c0 = 4 * (lane + 32 * k);
+          a[k] = (c0 < W.row_stride) ? ld_stream_f4(r0 + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          c[k] = (c0 < W.row_stride) ? ld_stream_f4(r1 + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          acc[k].x = fmaf(x0, a[k].x, fmaf(x1, c[k].x, acc[k].x)); acc[k].y = fmaf(x0, a[k].y, fmaf(x1, c[k].y, acc[k].y));
+          acc[k].z = fmaf(x0, a[k].z, fmaf(x1, c[k].z, acc[k].z)); acc[k].w = fmaf(x0, a[k].w, fmaf(x1, c[k].w, acc[k].w));
+        }
+      }
+      if (j < cnt) {
+        const float* r0 = row_ptr<float>(W, (long long)__shfl_sync(0xffffffffu, my_c, j));
+        const float x0 = __shfl_sync(0xffffffffu, my_x, j);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int c0 = 4 * (lane + 32 * k);
+          if (c0 < W.row_stride) {
+            const float4 a = ld_stream_f4(r0 + c0);
+            acc[k].x = fmaf(x0, a.x, acc[k].x); acc[k].y = fmaf(x0, a.y, acc[k].y);
+            acc[k].z = fmaf(x0, a.z, acc[k].z); acc[k].w = fmaf(x0, a.w, acc[k].w);
+          }
+        }
+      }
+    }
+    float* dst = P + (size_t)r * p_stride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane + 32 * k);
+      if (c0 < p_stride) *reinterpret_cast<float4*>(dst + c0) = acc[k];
+    }
+    if (tile_done != nullptr) {
+      __syncwarp();                                       // every lane's stores precede the fence below
+      if (lane == 0) {
+        __threadfence();
+        const int cnt_rows = min(tile_rows, B - t * tile_rows);
+        const unsigned old = atomicAdd(tile_done + w_id * n_tiles + t, 1u);
+        if (old + 1u == epoch * (unsigned)cnt_rows) {     // last row of tile (w, t) on this owner
+          __threadfence_system();
+          red_release_sys_add_u32(reinterpret_cast<unsigned*>(pflag_ptrs[w_id]) + t, 1u);
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K2: one CTA per tile, one warp per instance (row_stride <= 1024 floats: NV float4 chunks per lane).
 //   USE_MC : src_mc / dst_mc are multicast addresses of P / D.
 //   !USE_MC: src_ptrs[n_src] are unicast buffers to sum, dst_ptrs[n_dst] are unicast destinations.
 // Source row = src_row0 + b, destination row = dst_row0 + b.
 // ---------------------------------------------------------------------------------------------------------
+static constexpr int SM_THREADS = 128;      // small CTAs: K2 must fit next to the resident K1 CTAs on every SM
 template <int NV, bool USE_MC>
-__global__ void __launch_bounds__(NV_THREADS) ship_softmax_kernel(
+__global__ void __launch_bounds__(SM_THREADS) ship_softmax_kernel(
     const float* __restrict__ src_mc, const long long* __restrict__ src_ptrs, int n_src, int src_row0,
     float* __restrict__ dst_mc, const long long* __restrict__ dst_ptrs, int n_dst, int dst_row0,
     int stride, const int* __restrict__ labels, int B, int C, float step, float lscale, int tile_rows, int n_tiles,
@@ -140,7 +227,7 @@ __global__ void __launch_bounds__(NV_THREADS) ship_softmax_kernel(
       __syncthreads();
     }
     const int b_end = min(B, (t + 1) * tile_rows);
-    for (int b = t * tile_rows + wid; b < b_end; b += NV_THREADS / 32) {
+    for (int b = t * tile_rows + wid; b < b_end; b += SM_THREADS / 32) {
       float4 v[NV];
       float tmax = -INFINITY;
 #pragma unroll
@@ -234,17 +321,19 @@ static TableView nv_view(const at::Tensor& block_ptrs, int64_t rows_per_block, i
 
 // Leaves room for the resident K2 CTAs: K1 takes (occupancy - 1) CTAs per SM.
 template <typename K>
-static int fwd_grid(K kernel) {
-  static int cached = 0;
-  if (!cached) {
-    int occ = 0, sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, NV_THREADS, 0);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cached = sms * std::max(1, occ - 1);
-  }
-  return cached;
+static int fwd_grid(K kernel, int threads = NV_THREADS) {
+  static std::mutex mu;
+  static std::map<const void*, int> cache;              // keyed by the kernel (instantiations share one K type)
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(reinterpret_cast<const void*>(kernel));
+  if (it != cache.end()) return it->second;
+  int occ = 0, sms = 148, dev = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0);
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * std::max(1, occ - 1);
+  cache[reinterpret_cast<const void*>(kernel)] = grid;
+  return grid;
 }
 
 // CUDA loads a kernel lazily at its FIRST launch, and that load can synchronise with running kernels: K2 spinning
@@ -256,6 +345,8 @@ void ship_preload(int64_t device) {
   cudaFuncAttributes a;
 #define HB_TOUCH(K) C10_CUDA_CHECK(cudaFuncGetAttributes(&a, K))
   HB_TOUCH(ship_fwd_kernel<1>); HB_TOUCH(ship_fwd_kernel<2>); HB_TOUCH(ship_fwd_kernel<4>);
+  HB_TOUCH(ship_fwd_warp_kernel<1>); HB_TOUCH(ship_fwd_warp_kernel<2>); HB_TOUCH(ship_fwd_warp_kernel<4>);
+  HB_TOUCH(ship_fwd_warp_kernel<8>);
   HB_TOUCH((ship_softmax_kernel<1, true>)); HB_TOUCH((ship_softmax_kernel<2, true>));
   HB_TOUCH((ship_softmax_kernel<4, true>)); HB_TOUCH((ship_softmax_kernel<8, true>));
   HB_TOUCH((ship_softmax_kernel<1, false>)); HB_TOUCH((ship_softmax_kernel<2, false>));
@@ -290,7 +381,26 @@ void ship_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_str
         (int)B, (int)tile_rows, n_tiles, reinterpret_cast<float*>(p_ptr), (int)row_stride, td, pf,      \
         (unsigned)epoch);                                                                               \
   }
-  if (vec <= 1) LAUNCH_F(1) else if (vec == 2) LAUNCH_F(2) else LAUNCH_F(4)
+#define LAUNCH_FW(NVv)                                                                                  \
+  {                                                                                                     \
+    const int want = (int)((n_tiles * world * tile_rows + FW_THREADS / 32 - 1) / (FW_THREADS / 32));    \
+    const int grid = std::min(want, fwd_grid(ship_fwd_warp_kernel<NVv>, FW_THREADS));                   \
+    ship_fwd_warp_kernel<NVv><<<grid, FW_THREADS, 0, stream>>>(                                         \
+        W, csr_ptr.data_ptr<int>(), csr_col.data_ptr<int>(), csr_val.data_ptr<float>(), (int)world,     \
+        (int)B, (int)tile_rows, n_tiles, reinterpret_cast<float*>(p_ptr), (int)row_stride, td, pf,      \
+        (unsigned)epoch);                                                                               \
+  }
+  // warp per instance pays off for SHORT rows (model sharded over many owners); long rows keep the CTA-per-instance
+  // kernel with 8 rows in flight per thread.  HB_SHIP_K1=cta|warp overrides (A/B runs).
+  const double avg_nnz = (double)csr_col.numel() / (double)std::max<int64_t>(1, world * B);
+  static const char* k1_env = getenv("HB_SHIP_K1");
+  const bool use_warp = row_stride <= 1024 &&
+      (k1_env && k1_env[0] == 'w' ? true : (k1_env && k1_env[0] == 'c' ? false : avg_nnz < 32.0));
+  if (use_warp) {
+    const int nv = (int)((row_stride / 4 + 31) / 32);
+    if (nv <= 1) LAUNCH_FW(1) else if (nv <= 2) LAUNCH_FW(2) else if (nv <= 4) LAUNCH_FW(4) else LAUNCH_FW(8)
+  } else if (vec <= 1) LAUNCH_F(1) else if (vec == 2) LAUNCH_F(2) else LAUNCH_F(4)
+#undef LAUNCH_FW
 #undef LAUNCH_F
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
@@ -318,7 +428,7 @@ void ship_softmax(int64_t src_mc, c10::optional<at::Tensor> src_ptrs, int64_t sr
   const long long* dc = dcount_ptrs.has_value() ? reinterpret_cast<const long long*>(dcount_ptrs->data_ptr<int64_t>()) : nullptr;
   const int grid = std::min(n_tiles, 148);
 #define LAUNCH_S(NVv, MC)                                                                                \
-  ship_softmax_kernel<NVv, MC><<<grid, NV_THREADS, 0, stream>>>(                                         \
+  ship_softmax_kernel<NVv, MC><<<grid, SM_THREADS, 0, stream>>>(                                         \
       reinterpret_cast<const float*>(src_mc), sp, n_src, (int)src_row0, reinterpret_cast<float*>(dst_mc), \
       dp, dp ? (int)dst_ptrs->numel() : n_dst, (int)dst_row0, (int)stride, labels.data_ptr<int>(), B,    \
       (int)num_classes, (float)step, (float)logit_scale, (int)tile_rows, n_tiles,                       \
