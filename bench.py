@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--ship_impl", default="v2", choices=["v1", "v2"],
                     help="v2: NVLS multimem + tile flags (3 launches); v1: round-1 peer stores + device barriers")
     ap.add_argument("--no_nvls", action="store_true", help="ship v2 over unicast peer loads/stores")
+    ap.add_argument("--ship_rs", default="push", choices=["push", "nvls"],
+                    help="reduce-scatter of the logits: push = red.add from K1's epilogue into the worker's buffer "
+                         "(default), nvls = multimem.ld_reduce by the worker's K2")
     ap.add_argument("--mode", default="both", choices=["both", "auto", "pull", "ship"])
     args, rest = ap.parse_known_args()
     args.rest = rest
@@ -293,7 +296,7 @@ def main():
         clock_s = DeviceClock(arena, group, slack=0)
         if args.ship_impl == "v2" and stride <= 1024:
             ship = MLRShipModel(table, arena, group, None, C, args.step_size, B, multicast=not args.no_nvls,
-                                lam=args.lam)
+                                lam=args.lam, reduce_scatter=args.ship_rs)
         else:
             ship = MLRShipModelV1(table, arena, group, clock_s, C, args.step_size, B)
         regions, clocks, launches = measure(ship.step, dev_ship, args.warmup, K, R, ship.stats)
@@ -304,13 +307,15 @@ def main():
         uniq_o = int(np.mean([hb.routed.uniq_feat.numel() for hb in host_ship]))
         nnz_o = int(np.mean([hb.routed.csr_col.numel() for hb in host_ship]))
         # K1: row gathers + P store; K2: P read by the switch + D landing; K3: row read-modify-write (D re-reads hit L2)
-        hbm = (nnz_o + 2 * uniq_o + 3 * world * B) * row_bytes
+        hbm = (nnz_o + 2 * uniq_o + world * B + (2 * world * B if getattr(ship, "rs", "") == "nvls" else 2 * B)) * row_bytes
         egress = (world - 1) * B * row_bytes + (B * row_bytes if world > 1 else 0)
         m.update({"clocks": clocks, "gpu_launches": launches, "loss_per_instance": round(float(ship.stats[0]) / (K * B), 5),
                   "impl": args.ship_impl if stride <= 1024 else "v1", "nvls_multicast": bool(getattr(ship, "nvls", False)),
+                  "reduce_scatter": getattr(ship, "rs", "v1 red.add + device barriers"),
                   "hbm_bytes_per_step_per_gpu": int(hbm), "nvlink_egress_bytes_per_step_per_gpu": int(egress),
                   "parallelism": (f"ps-sharded-model x{world} (co-located), owner-side sparse dot; [B,C] activations "
-                                  f"reduce-scattered (multimem.ld_reduce) / all-gathered (multimem.st) in the kernels")})
+                                  f"reduce-scattered (red.add over NVLink from the dot kernel's epilogue) / all-gathered "
+                                  f"(multimem.st, NVLS) in the kernels, tile flags instead of barriers")})
         reps = min(K, 5)                    # serialised per-kernel timing, outside the headline regions
         acc = {}
         for i in range(reps):

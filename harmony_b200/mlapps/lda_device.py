@@ -33,8 +33,72 @@ class LDADeviceTrainer(Trainer):
             base += len(d)
         self.model = LDADeviceModel(self.dtable, self.K, self.V, base, self.alpha, self.beta,
                                     seed=hash(str(params.get("job_id"))) % 100000)
+        self.model._used = base
+        self._doc_len = {k: len(d) for k, d in self._docs}
         self._cache: Dict[Any, Any] = {}
         self._batch = None
+        self._restored = False
+        if local_model_table is not None and self._docs and \
+                local_model_table.get_local_tablet().get_num_data_items() > 0:
+            # started by a plan on blocks that migrated in: the assignments published by the previous owner are in the
+            # local-model table -- adopt them instead of drawing (and pushing the counts of) a fresh random assignment
+            self._load_assignments([k for k, _ in self._docs])
+            self._restored = True
+
+    # ---- worker-side elasticity: assignments travel in the local-model table with the input blocks ----
+    def _load_assignments(self, keys) -> list:
+        """Copy the (assignments, doc-topic counts) entries of `keys` from the local-model table into HBM.  Returns
+        the keys that have no entry yet (new documents: they need an initial assignment)."""
+        vals = self.local_table.multi_get(keys).get(timeout=600)
+        missing = []
+        for k, v in zip(keys, vals):
+            if v is None:
+                missing.append(k)
+                continue
+            zz = np.asarray(v[0], dtype=np.int32)
+            lo = self._tok_base[k]
+            self.model.z[lo: lo + len(zz)] = self._torch.from_numpy(zz).to(self.model.z.device)
+        return missing
+
+    def _adopt(self, mini_batch) -> None:
+        """Documents without a token range here migrated in with their input block: give them one, fetch their
+        assignments from the local-model table (or initialise them if the previous owner never published any)."""
+        new = [(k, d) for k, d in mini_batch if k not in self._tok_base]
+        if not new:
+            return
+        new.sort(key=lambda kv: kv[0])
+        first = self.model.grow_tokens(sum(len(d) for _, d in new))
+        for k, d in new:
+            self._tok_base[k] = first
+            self._doc_len[k] = len(d)
+            first += len(d)
+        self._docs.extend(new)
+        missing = self._load_assignments([k for k, _ in new]) if self.local_table is not None else [k for k, _ in new]
+        if missing:
+            miss = set(missing)
+            self.model.step_batch(self._to_batch([(k, d) for k, d in new if k in miss]), init_mode=True)
+
+    def _write_back(self) -> None:
+        if self.local_table is None or not self._docs:
+            return
+        here = {k for k, _ in self.input.get_local_tablet().get_data_iterator()}
+        docs = [(k, d) for k, d in self._docs if k in here]
+        if not docs:
+            return
+        z = self.model.z.cpu().numpy()
+        keys, models = [], []
+        for k, d in docs:
+            zz = z[self._tok_base[k]: self._tok_base[k] + len(d)].astype(np.int32)
+            keys.append(k)
+            models.append((zz, np.bincount(zz, minlength=self.K).astype(np.int32)))
+        self.local_table.multi_put(keys, models).get(timeout=600)
+
+    def on_epoch_finished(self, epoch_idx: int) -> None:
+        super().on_epoch_finished(epoch_idx)
+        self._write_back()
+
+    def flush(self) -> None:
+        self._torch.cuda.current_stream(self.dtable.device).synchronize()
 
     def _to_batch(self, mini_batch):
         from ..models.lda import build_lda_batch
@@ -42,14 +106,16 @@ class LDADeviceTrainer(Trainer):
         key = (mb[0][0], len(mb))
         b = self._cache.get(key)
         if b is None:
-            # documents of one input block are contiguous in key order => contiguous token range
+            self._adopt(mb)
+            # documents of one input block are contiguous in key order => contiguous token range (also for blocks
+            # that migrated in: `_adopt` lays a block's documents out back to back)
             b = build_lda_batch([d for _, d in mb], self._tok_base[mb[0][0]], self.V).to(self.dtable.device)
             self._cache[key] = b
         return b
 
     def init_global_settings(self) -> None:
         """Random initial assignment of every local token; the counts are pushed to the owners."""
-        if not self._docs:
+        if not self._docs or self._restored:
             return
         self.comps.gate.acquire_read()
         try:
@@ -70,7 +136,6 @@ class LDADeviceTrainer(Trainer):
     def push_update(self) -> None:
         try:
             self.model.step_batch(self._batch)
-            self._torch.cuda.current_stream(self.dtable.device).synchronize()
         finally:
             self.comps.gate.release_read()
 
@@ -98,11 +163,4 @@ class LDADeviceTrainer(Trainer):
         self.cleanup()          # publish the HBM-resident local model before its table blocks migrate
 
     def cleanup(self) -> None:
-        if self.local_table is not None and self._docs:
-            z = self.model.z.cpu().numpy()
-            keys, models = [], []
-            for k, d in self._docs:
-                zz = z[self._tok_base[k]: self._tok_base[k] + len(d)].astype(np.int32)
-                keys.append(k)
-                models.append((zz, np.bincount(zz, minlength=self.K).astype(np.int32)))
-            self.local_table.multi_put(keys, models).get(timeout=600)
+        self._write_back()

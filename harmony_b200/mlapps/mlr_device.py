@@ -90,13 +90,38 @@ class MLRDeviceTrainer(Trainer):
         clock = DeviceClock(ctx.arena, group)
         self.ship = MLRShipModel(self.dtable, ctx.arena, group, clock, self.num_classes, self.model.step_size, B)
         self.ship.stats = self.model.stats
-        self._ship_owner_ranks = list(self.dtable.owners)
-        self._ship_steps = []
-        for s_idx in range(n_steps):
-            allw = [build_batch(*everyone[w][s_idx]) for w in range(group.world)]
-            self._ship_steps.append(route_batches(self.dtable, allw, group.rank, owner_ranks).to(self.dtable.device))
+        self._ship_group, self._ship_everyone, self._ship_ex_ids = group, everyone, ex_ids
+        self._ship_route(owner_ranks)
         self._ship_first_key = first_key
         self.wants_sorted_batches = True
+
+    def _ship_route(self, owner_ranks) -> None:
+        """(Re)build this owner's slices of every worker's mini-batches for the given block -> owner map."""
+        from ..models.mlr import build_batch
+        from ..models.mlr_ship import route_batches
+        group = self._ship_group
+        self._ship_owner_ranks = list(self.dtable.owners)
+        self._ship_steps = []
+        for s_idx in range(len(self._ship_everyone[0])):
+            allw = [build_batch(*self._ship_everyone[w][s_idx]) for w in range(group.world)]
+            self._ship_steps.append(route_batches(self.dtable, allw, group.rank, owner_ranks).to(self.dtable.device))
+
+    def _ship_reroute_if_moved(self) -> None:
+        """After a live re-partition the kernels stay CORRECT with the old routing -- every row access resolves
+        through the pointer table, a moved row is simply reached over NVLink -- but the dot should run where the rows
+        now live.  At an epoch boundary (all workers are in lock-step there) the workers compare their ownership
+        views and, once they agree on a new map, re-route their input slices."""
+        try:
+            views = self._ship_group.all_gather_object(list(self.dtable.owners), tag="ship-owners", timeout=30.0)
+        except TimeoutError:
+            return                                    # a peer left the lock-step (job is ending): keep the routing
+        mine = list(self.dtable.owners)
+        if any(v != mine for v in views) or mine == self._ship_owner_ranks:
+            return                                    # a flip is still travelling, or nothing moved
+        owner_ranks = [self._ship_ex_ids.index(o) if o in self._ship_ex_ids else -1 for o in mine]
+        if any(r < 0 for r in owner_ranks):
+            return                                    # a block left the job's executors: keep resolving over NVLink
+        self._ship_route(owner_ranks)
 
     def _to_dense_batch(self, mini_batch):
         key = ("dense", mini_batch[0][0], len(mini_batch))
@@ -142,8 +167,6 @@ class MLRDeviceTrainer(Trainer):
     def push_update(self) -> None:
         try:
             if self.ship is not None:
-                if list(self.dtable.owners) != self._ship_owner_ranks:
-                    raise RuntimeError("ship mode does not support re-partitioning the model table mid-job")
                 self.ship.step_size = self.model.step_size
                 self.ship.step(self._batch)               # BSP lockstep over the job's workers (device clocks)
             elif self.dense is not None:
@@ -171,6 +194,8 @@ class MLRDeviceTrainer(Trainer):
     def on_epoch_finished(self, epoch_idx: int) -> None:
         if self.decay_rate != 1 and (epoch_idx + 1) % self.decay_period == 0:
             self.model.decay_step(self.decay_rate)
+        if self.ship is not None:
+            self._ship_reroute_if_moved()
 
     def evaluate_model(self, input_data, test_data) -> Dict[str, float]:
         out = {}

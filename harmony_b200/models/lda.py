@@ -57,6 +57,16 @@ class LDADeviceModel:
         self._rows = None
         self._out = None
 
+    def grow_tokens(self, n_tokens: int) -> int:
+        """Room for `n_tokens` more topic assignments (documents that migrated in); returns their first index."""
+        used = getattr(self, "_used", self.z.numel())
+        if used + n_tokens > self.z.numel():
+            z = torch.zeros(max(2 * self.z.numel(), used + n_tokens), dtype=torch.int32, device=self.device)
+            z[:used] = self.z[:used]
+            self.z = z
+        self._used = used + n_tokens
+        return used
+
     def _buffers(self, U1: int, ntok: int):
         if self._rows is None or self._rows.shape[0] < U1:
             self._rows = torch.empty((U1, self.table.row_stride), dtype=torch.int32, device=self.device)

@@ -17,10 +17,13 @@ class DenseMLR:
     are TMA-loaded from the owners' slabs (pull fused) and whose epilogue reduce-adds into the owners' rows
     (push fused); ops/csrc/mlr_dense_tc.cu."""
 
-    def __init__(self, table: DeviceTable, num_classes: int, use_2cta: bool = True) -> None:
+    def __init__(self, table: DeviceTable, num_classes: int, use_2cta: bool = True, stream_k: bool = True) -> None:
         # use_2cta: cta_group::2 kernels (256 x 256 tile per CTA pair, ~640 TFLOP/s tf32 measured vs ~340 for
         # the single-CTA 128 x 128 kernel, which is L2-bandwidth bound at 32 FLOP per staged byte)
+        # stream_k: the persistent variant -- one cluster per TPC, the (tile, k-step) space cut into equal ranges,
+        # double-buffered TMEM so the epilogue of one work unit overlaps the MMAs of the next
         self.use_2cta = use_2cta
+        self.stream_k = stream_k and use_2cta
         from ..ops import native
         self._n = native()
         assert table.mode == PART_ORDERED, "dense MLR needs an ordered (range partitioned) model table"
@@ -44,7 +47,7 @@ class DenseMLR:
         if out is None:
             out = torch.empty((B, self.table.row_stride), dtype=torch.float32, device=self.device)
         self._n.dense_logits_tf32(X, self._maps(), self.table.rows_per_block, self.table.row_stride, out,
-                                  use_2cta=self.use_2cta)
+                                  use_2cta=self.use_2cta, stream_k=self.stream_k)
         count_launch()
         return out
 
@@ -75,5 +78,5 @@ class DenseMLR:
         self._n.mlr_softmax_bcast(L[:B], labels, self.num_classes, float(step_size), self._dptr, 0, stats)
         count_launch()
         bp, rpb, st, _dim, mode = self.table.view()
-        self._n.dense_grad_push_tf32(Xp, D, bp, rpb, st, self.num_classes, mode, use_2cta=self.use_2cta)
+        self._n.dense_grad_push_tf32(Xp, D, bp, rpb, st, self.num_classes, mode, use_2cta=self.use_2cta, stream_k=self.stream_k)
         count_launch()

@@ -162,13 +162,21 @@ class MLRShipModel:
     Same arithmetic as MLRTrainer.java:374-398,475-505.  `lam` != 0 uses the lazy L2 scale of the table
     (w = s * v, see `LazyScale`): logits are multiplied by s, deltas divided by the next s, no dense pass."""
 
-    TILE_ROWS = 32
+    TILE_ROWS = 8           # instances per flag: one K1 CTA owns a tile (one system fence per tile), K2 runs it as
+                            # 8 warps x 1 instance -> short tail after the last K1 tiles
 
     def __init__(self, table: DeviceTable, arena: PeerArena, group: PeerGroup, clock: Optional[DeviceClock],
                  num_classes: int, step_size: float, batch_size: int, multicast: bool = True,
-                 lam: float = 0.0) -> None:
+                 lam: float = 0.0, reduce_scatter: Optional[str] = None) -> None:
+        """reduce_scatter: "push" (default) -- K1's epilogue red.adds the partial logits into the worker's buffer over
+        NVLink (fire-and-forget, hidden behind the gathers; measured faster at 8 GPUs); "nvls" -- the owners keep their
+        partials and the worker's K2 sums them in the switch with multimem.ld_reduce (pull-based: latency-bound).
+        The all-gather of the error rows is multimem.st in both."""
+        import os
         from ..ops import native
         from ..parallel.peer import SymmetricRegion
+        self.rs = reduce_scatter or os.environ.get("HB_SHIP_RS", "push")
+        assert self.rs in ("push", "nvls"), self.rs
         self._n = native()
         self.table, self.arena, self.group, self.clock = table, arena, group, clock
         self.rank, self.world = group.rank, group.world
@@ -183,8 +191,11 @@ class MLRShipModel:
         self.n_tiles = -(-self.B // self.TILE_ROWS)
         rows = self.world * self.B
         buf = rows * stride * 4
-        self._off_p, self._off_d = 0, buf
-        self._off_pflag = 2 * buf
+        lbuf = self.B * stride * 4
+        self._off_d = 0
+        self._off_p = buf                               # "nvls" only: this owner's partial logits of every worker
+        self._off_l = buf + (buf if self.rs == "nvls" else 0)      # "push": the logits buffer the owners add into
+        self._off_pflag = self._off_l + lbuf
         self._off_dcount = self._off_pflag + ((self.n_tiles * 4 + 255) // 256) * 256
         total = self._off_dcount + 256
         self.region = SymmetricRegion(arena, group, total, multicast=multicast)
@@ -193,16 +204,18 @@ class MLRShipModel:
         torch.cuda.synchronize(self.device)
         group.barrier()
         self.D = reg.tensor(self._off_d, [rows, stride], torch.float32)
-        self.P = reg.tensor(self._off_p, [rows, stride], torch.float32)
+        self.L = reg.tensor(self._off_l, [self.B, stride], torch.float32)
         i64 = lambda xs: torch.tensor(xs, dtype=torch.int64, device=self.device)  # noqa: E731
         self.src_ptrs = i64([p + self._off_p for p in reg.peer_ptrs])
+        self.logit_ptrs = i64([p + self._off_l for p in reg.peer_ptrs])
+        self.l_local = i64([reg.local_ptr + self._off_l])
         self.dst_ptrs = i64([p + self._off_d for p in reg.peer_ptrs])
         self.pflag_ptrs = i64([p + self._off_pflag for p in reg.peer_ptrs])
         self.dcount_ptrs = i64([p + self._off_dcount for p in reg.peer_ptrs])
         self.nvls = reg.mc_ptr != 0
-        self.mc_p = reg.mc_ptr + self._off_p if self.nvls else 0
+        self.mc_p = reg.mc_ptr + self._off_p if (self.nvls and self.rs == "nvls") else 0
         self.mc_d = reg.mc_ptr + self._off_d if self.nvls else 0
-        self.tile_done = torch.zeros(self.world * self.n_tiles, dtype=torch.int32, device=self.device)
+        self.tile_done = torch.zeros(max(2, self.world * self.n_tiles), dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.stats = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.epoch = 0
@@ -217,11 +230,22 @@ class MLRShipModel:
     def _k1(self, rb: RoutedBatch) -> None:
         bp, rpb, stride, _dim, mode = self.table.view()
         r = rb.routed
+        if self.rs == "push":
+            self._n.ship3_forward(bp, rpb, stride, self.num_classes, mode, r.csr_ptr, r.csr_col, r.csr_val, self.world,
+                                  self.B, self.TILE_ROWS, self.logit_ptrs, self.tile_done.data_ptr(), self.pflag_ptrs,
+                                  self.epoch)
+            return
         self._n.ship_forward(bp, rpb, stride, self.num_classes, mode, r.csr_ptr, r.csr_col, r.csr_val, self.world,
                              self.B, self.TILE_ROWS, self.region.local_ptr + self._off_p, self.tile_done.data_ptr(),
                              self.pflag_ptrs, self.epoch)
 
     def _k2(self, rb: RoutedBatch, logit_scale: float, delta_step: float) -> None:
+        if self.rs == "push":       # the reduced logits are local; re-arm (zero) them; broadcast D with multimem.st
+            self._n.ship_softmax(0, self.l_local, 0, self.mc_d, self.dst_ptrs, self.rank * self.B, self.stride,
+                                 rb.labels, self.num_classes, delta_step, logit_scale, self.TILE_ROWS,
+                                 self.region.local_ptr + self._off_pflag, self.epoch * self.world, self.dcount_ptrs,
+                                 self.stats, self.err, True)
+            return
         self._n.ship_softmax(self.mc_p, self.src_ptrs, self.rank * self.B, self.mc_d, self.dst_ptrs,
                              self.rank * self.B, self.stride, rb.labels, self.num_classes, delta_step, logit_scale,
                              self.TILE_ROWS, self.region.local_ptr + self._off_pflag, self.epoch * self.world,

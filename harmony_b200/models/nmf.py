@@ -72,6 +72,21 @@ class NMFDeviceModel:
         self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._R = self._G = None
 
+    def append_rows(self, rows: torch.Tensor) -> int:
+        """Grow the HBM-resident local factor by `rows` ([n, rank]: the L rows of input records that migrated in with
+        their blocks); returns the index of the first new row.  Capacity doubles, so appends are amortised O(1)."""
+        n0, n = self.L.shape[0], rows.shape[0]
+        used = getattr(self, "_used", n0)
+        if used + n > self._Lbuf.shape[0]:
+            grown = torch.zeros((max(2 * self._Lbuf.shape[0], used + n), self._Lbuf.shape[1]), dtype=torch.float32,
+                                device=self.device)
+            grown[:used] = self._Lbuf[:used]
+            self._Lbuf = grown
+        self._Lbuf[used:used + n, : self.rank] = rows.to(self.device, torch.float32)
+        self._used = used + n
+        self.L = self._Lbuf[: self._used, : self.rank]
+        return used
+
     def _staging(self, U: int):
         if self._R is None or self._R.shape[0] < U:
             self._R = torch.empty((U, self.table.row_stride), dtype=torch.float32, device=self.device)

@@ -71,7 +71,12 @@ void ship_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_str
 void ship_softmax(int64_t src_mc, c10::optional<at::Tensor> src_ptrs, int64_t src_row0, int64_t dst_mc,
                   c10::optional<at::Tensor> dst_ptrs, int64_t dst_row0, int64_t stride, at::Tensor labels,
                   int64_t num_classes, double step, double logit_scale, int64_t tile_rows, int64_t pflag_ptr,
-                  int64_t pflag_target, c10::optional<at::Tensor> dcount_ptrs, at::Tensor stats, at::Tensor err);
+                  int64_t pflag_target, c10::optional<at::Tensor> dcount_ptrs, at::Tensor stats, at::Tensor err,
+                  bool zero_src);
+void ship3_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                   int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, int64_t world, int64_t B,
+                   int64_t tile_rows, at::Tensor logit_ptrs, int64_t tile_done_ptr,
+                   c10::optional<at::Tensor> pflag_ptrs, int64_t epoch);
 void wait_count(int64_t ptr, int64_t target, at::Tensor err);
 void ship_preload(int64_t device);
 // nmf_ops.cu
@@ -93,9 +98,9 @@ void mlr_softmax_bcast(at::Tensor L, at::Tensor labels, int64_t num_classes, dou
 at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_block, int64_t row_stride,
                                  int64_t device, int64_t swizzle_mode);
 void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out,
-                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout, bool use_2cta);
+                       bool use_2cta, bool stream_k);
 void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
-                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta);
+                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta, bool stream_k);
 // k12_ops.cu
 void lasso_cd(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
               at::Tensor Xt, at::Tensor y, double lambda, double step, at::Tensor w_new, at::Tensor w_old,
@@ -164,7 +169,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("samp"), py::arg("xval"), py::arg("D"), py::arg("local_rmw") = false, py::arg("wait_ptr") = 0,
         py::arg("wait_target") = 0, py::arg("err") = py::none());
   m.def("ship_forward", &hb::ship_forward);
-  m.def("ship_softmax", &hb::ship_softmax);
+  m.def("ship_softmax", &hb::ship_softmax, py::arg("src_mc"), py::arg("src_ptrs"), py::arg("src_row0"),
+        py::arg("dst_mc"), py::arg("dst_ptrs"), py::arg("dst_row0"), py::arg("stride"), py::arg("labels"),
+        py::arg("num_classes"), py::arg("step"), py::arg("logit_scale"), py::arg("tile_rows"), py::arg("pflag_ptr"),
+        py::arg("pflag_target"), py::arg("dcount_ptrs"), py::arg("stats"), py::arg("err"), py::arg("zero_src") = false);
+  m.def("ship3_forward", &hb::ship3_forward);
   m.def("wait_count", &hb::wait_count);
   m.def("ship_preload", &hb::ship_preload);
   m.def("nmf_batch", &hb::nmf_batch);
@@ -172,12 +181,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mlr_partial_forward", &hb::mlr_partial_forward);
   m.def("dense_grad_push_tf32", &hb::dense_grad_push_tf32, py::arg("X"), py::arg("D"), py::arg("block_ptrs"),
         py::arg("rows_per_block"), py::arg("row_stride"), py::arg("n_classes"), py::arg("mode"),
-        py::arg("use_2cta") = false);
+        py::arg("use_2cta") = false, py::arg("stream_k") = false);
   m.def("make_block_tensormaps", &hb::make_block_tensormaps, py::arg("block_ptrs_cpu"), py::arg("rows_per_block"),
         py::arg("row_stride"), py::arg("device"), py::arg("swizzle_mode") = 1);
   m.def("dense_logits_tf32", &hb::dense_logits_tf32, py::arg("X"), py::arg("bmaps"), py::arg("rows_per_block"),
-        py::arg("n_cols"), py::arg("out"), py::arg("dbg") = 0, py::arg("b_lbo") = 0, py::arg("b_sbo") = 0,
-        py::arg("idesc_xor") = 0, py::arg("b_layout") = 0, py::arg("use_2cta") = false);
+        py::arg("n_cols"), py::arg("out"), py::arg("use_2cta") = false, py::arg("stream_k") = false);
   m.def("mlr_softmax_bcast", &hb::mlr_softmax_bcast);
   m.def("lasso_cd", &hb::lasso_cd);
   m.def("gbt_level", &hb::gbt_level);

@@ -87,8 +87,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 template <bool A_MN, bool PUSH>
 __global__ void __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_kernel(
     const __grid_constant__ CUtensorMap tmA, const CUtensorMap* __restrict__ tmB, float* __restrict__ out,
-    int out_stride, int M, int N, int K, int rows_per_block, int dbg, int b_lbo, int b_sbo, int idesc_xor, int b_layout,
-    TableView Wtab) {
+    int out_stride, int M, int N, int K, int rows_per_block, TableView Wtab) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B needs 1024 B alignment
@@ -151,20 +150,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_kernel(
         mbar_wait(full0 + 8 * s, (kt / TC_STAGES) & 1);
         tc_fence_after();
         const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-        if (dbg && kt == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-          const float* fa = reinterpret_cast<const float*>(smem + s * TC_STAGE_BYTES);
-          const float* fb = fa + TC_A_BYTES / 4;
-          printf("[tc dbg] tmem_base=%08x base=%08x A[0..3]=%f %f %f %f  B[0..3]=%f %f %f %f idesc=%08x\n", tmem_base,
-                 base, fa[0], fa[1], fa[2], fa[3], fb[0], fb[1], fb[2], fb[3], idesc ^ (uint32_t)idesc_xor);
-        }
 #pragma unroll
         for (int i = 0; i < TC_BK / TC_UMMA_K; ++i) {
           // A: K-major SW128, 8-row groups 1024 B apart, K-step = 8 tf32 = 32 B inside the swizzle row
           const uint64_t ad = A_MN ? umma_desc(sa + i * 1024, TC_BK * 128, 512, 1)
                                    : umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
           // B: MN-major SW128, 128 B column groups (BK x 128 B = 4096 B apart), 8 K-rows = 1024 B
-          const uint64_t bd = umma_desc(sb + i * 1024, b_lbo, b_sbo, (uint32_t)b_layout);
-          tc_mma_tf32(tmem_base, ad, bd, idesc ^ (uint32_t)idesc_xor, (kt > 0 || i > 0) ? 1u : 0u);
+          const uint64_t bd = umma_desc(sb + i * 1024, TC_BK * 128, 512, 1);
+          tc_mma_tf32(tmem_base, ad, bd, idesc, (kt > 0 || i > 0) ? 1u : 0u);
         }
         tc_commit(empty0 + 8 * s);                  // smem slot is free once these MMAs retire
       }
@@ -190,9 +183,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_kernel(
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (dbg && c == 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-        printf("[tc dbg] epi warp %d q %d taddr=%08x v0..3 = %f %f %f %f\n", warp, q, taddr, __uint_as_float(v[0]),
-               __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
       if (PUSH) {
         if (row < M) {
           float* o = row_ptr<float>(Wtab, (long long)row) + n0 + c * 32;   // owner's row (local or peer)
@@ -381,6 +371,236 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) dense
   }
 }
 
+
+// ===================================================================================================
+// Persistent "data-parallel + stream-K tail" variant of the 2-CTA kernel (the default).  The grid is ONE
+// 2-CTA cluster per TPC (74 on a B200) whatever the problem.  Whole waves of 74 tiles are handed out
+// strided (cluster c computes tiles c, c + 74, ...: at any moment the machine works on 74 CONSECUTIVE
+// tiles, m fastest, which share their B panel in L2).  The last, incomplete wave of R < 74 tiles is cut
+// into 74 equal ranges of (tile, k-step) so every SM computes the same number of MMAs (plain tiling
+// leaves 10 of 74 clusters idle at 4096 x 1024 = 64 tiles).  A range that crosses a tile border is run
+// HEAD FIRST (k = 0.. of the later tile), then the tail of the earlier tile: all clusters then sit at the
+// same k (plus one common offset in the tail phase), which keeps the A / B k-slices shared in L2 -- with
+// the natural order the clusters are staggered over all k and the kernel becomes HBM bound (measured:
+// 407 instead of 640 TFLOP/s).  A partial range contributes with red.add (the output is zeroed first; the
+// PUSH epilogue is a red.add anyway).
+// TMEM is double buffered (2 x 256 columns = all 512): the epilogue of work unit u drains buffer
+// u & 1 while the MMAs of unit u + 1 fill the other; the TMA producer never stops at unit borders.
+//   barriers (per CTA): full[6] / empty[6] smem stages; tmem_full[2] (multicast commit);
+//                       tmem_empty[2] on the LEADER, 8 arrivals = 4 epilogue warps x 2 CTAs.
+// ===================================================================================================
+constexpr int SK_TMEM_COLS = 512;
+constexpr int SK_SMEM_BYTES = T2_STAGES * TC_STAGE_BYTES + 1024 + 256;
+
+struct SkPlan {            // identical in every role of the cluster (producer / MMA / epilogue)
+  int nc, cluster, KT, waves, n_units;
+  int h_tile, h_kb, h_ke;  // remainder segment run first  (head of the later tile, or the only segment)
+  int t_tile, t_kb, t_ke;  // remainder segment run second (tail of the earlier tile); t_tile < 0: none
+};
+__device__ __forceinline__ SkPlan sk_plan(int tiles, int KT, int nc, int cluster) {
+  SkPlan p;
+  p.nc = nc; p.cluster = cluster; p.KT = KT;
+  p.waves = tiles / nc;
+  const int R = tiles - p.waves * nc;
+  p.h_tile = p.t_tile = -1;
+  p.h_kb = p.h_ke = p.t_kb = p.t_ke = 0;
+  int extra = 0;
+  if (R > 0) {
+    const long long rit = (long long)R * KT;
+    const long long rb = rit * cluster / nc, re = rit * (cluster + 1) / nc;
+    if (re > rb) {
+      const int t0 = (int)(rb / KT), k0 = (int)(rb - (long long)t0 * KT);
+      const int len = (int)(re - rb);
+      if (k0 + len <= KT) {
+        p.h_tile = p.waves * nc + t0; p.h_kb = k0; p.h_ke = k0 + len; extra = 1;
+      } else {
+        p.t_tile = p.waves * nc + t0; p.t_kb = k0; p.t_ke = KT;
+        p.h_tile = p.waves * nc + t0 + 1; p.h_kb = 0; p.h_ke = k0 + len - KT; extra = 2;
+      }
+    }
+  }
+  p.n_units = p.waves + extra;
+  return p;
+}
+__device__ __forceinline__ void sk_unit(const SkPlan& p, int u, int& tile, int& kb, int& ke) {
+  if (u < p.waves) { tile = u * p.nc + p.cluster; kb = 0; ke = p.KT; }
+  else if (u == p.waves) { tile = p.h_tile; kb = p.h_kb; ke = p.h_ke; }
+  else { tile = p.t_tile; kb = p.t_kb; ke = p.t_ke; }
+}
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t target_cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(target_cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
+}
+
+template <bool A_MN, bool PUSH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) dense_gemm_tf32_sk_kernel(
+    const __grid_constant__ CUtensorMap tmA, const CUtensorMap* __restrict__ tmB, float* __restrict__ out,
+    int out_stride, int M, int N, int K, int rows_per_block, TableView Wtab) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bars = base + T2_STAGES * TC_STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * T2_STAGES;
+  const uint32_t tfull0 = bars + 16 * T2_STAGES, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T2_STAGES * TC_STAGE_BYTES + 16 * T2_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int KT = K / TC_BK;
+  const int MT = (M + 255) / 256, NT = (N + T2_BN - 1) / T2_BN;
+  const SkPlan plan = sk_plan(MT * NT, KT, (int)(gridDim.x >> 1), (int)(blockIdx.x >> 1));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(SK_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: one continuous stream of k-steps across the work units =====
+      long long g = 0;                                   // global stage counter of this CTA
+      for (int u = 0; u < plan.n_units; ++u) {
+        int tile, kb, ke;
+        sk_unit(plan, u, tile, kb, ke);
+        const int nt = tile / MT, mt = tile - nt * MT;   // m fastest: concurrent tiles share their B panel
+        const int m0 = mt * 256 + (int)cta_rank * TC_BM, nb0 = nt * T2_BN + (int)cta_rank * 128;
+        for (int kt = kb; kt < ke; ++kt, ++g) {
+          const int s = (int)(g % T2_STAGES);
+          mbar_wait(empty0 + 8 * s, (uint32_t)(((g / T2_STAGES) & 1) ^ 1));
+          const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * TC_STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < TC_BM / 32; ++j)
+              tma_load_2d_2cta(sa + j * (TC_BK * 128), &tmA, full0 + 8 * s, m0 + 32 * j, kt * TC_BK);
+          } else {
+            tma_load_2d_2cta(sa, &tmA, full0 + 8 * s, kt * TC_BK, m0);
+          }
+          const int f0 = kt * TC_BK;
+          const int blk = f0 / rows_per_block, y = f0 - blk * rows_per_block;
+          const CUtensorMap* mb = tmB + blk;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_2d_2cta(sb + j * (TC_BK * 128), mb, full0 + 8 * s, nb0 + 32 * j, y);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      // ===== MMA issuer (leader only): unit u accumulates into TMEM buffer u & 1 =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | (1u << 16) |
+                             ((uint32_t)(T2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      long long g = 0;
+      for (int u = 0; u < plan.n_units; ++u) {
+        int tile, kb, ke;
+        sk_unit(plan, u, tile, kb, ke);
+        const int a = u & 1;
+        mbar_wait(tempty0 + 8 * a, (uint32_t)(((u >> 1) & 1) ^ 1));     // both CTAs drained this buffer
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(a * T2_BN);
+        for (int kt = kb; kt < ke; ++kt, ++g) {
+          const int s = (int)(g % T2_STAGES);
+          mbar_wait(full0 + 8 * s, (uint32_t)((g / T2_STAGES) & 1));
+          tc_fence_after();
+          const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int i = 0; i < TC_BK / TC_UMMA_K; ++i) {
+            const uint64_t ad = A_MN ? umma_desc(sa + i * 1024, TC_BK * 128, 512, 1)
+                                     : umma_desc(sa + i * (TC_UMMA_K * 4), 16, 1024);
+            const uint64_t bd = umma_desc(sb + i * 1024, TC_BK * 128, 512, 1);
+            tc_mma_tf32_2cta(acc, ad, bd, idesc, (kt > kb || i > 0) ? 1u : 0u);
+          }
+          tc_commit_2cta(empty0 + 8 * s);
+        }
+        tc_commit_2cta(tfull0 + 8 * a);                    // this unit's accumulators are complete in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): drain buffer u & 1, then hand it back to the leader's MMA warp =====
+    const int q = warp & 3;
+    for (int u = 0; u < plan.n_units; ++u) {
+      int tile, kb, ke;
+      sk_unit(plan, u, tile, kb, ke);
+      const int nt = tile / MT, mt = tile - nt * MT;
+      const int m0 = mt * 256 + (int)cta_rank * TC_BM, n0 = nt * T2_BN;
+      const bool partial = PUSH || kb > 0 || ke < KT;      // another cluster owns the rest of this tile's K
+      const int a = u & 1;
+      mbar_wait(tfull0 + 8 * a, (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      const int row = m0 + 32 * q + lane;
+#pragma unroll 1
+      for (int c = 0; c < T2_BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(a * T2_BN + c * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int col0 = n0 + c * 32;
+        if (row < M) {
+          float* o = PUSH ? row_ptr<float>(Wtab, (long long)row) + col0 : out + (size_t)row * out_stride + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            if (col0 + e < N) {
+              const float4 f = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                           __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+              if (partial) red_add_f4_sys(o + e, f);
+              else *reinterpret_cast<float4*>(o + e) = f;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * a, 0);   // 8 arrivals (4 warps x 2 CTAs) free the buffer
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(SK_TMEM_COLS) : "memory");
+  }
+}
+
+// Launch helper: one cluster per TPC; `zero_me` (forward) is zeroed when some tile is split across clusters.
+template <bool A_MN, bool PUSH>
+static void launch_stream_k(const CUtensorMap& tmA, const CUtensorMap* tmB, float* out, int out_stride, int M, int N,
+                            int K, int rows_per_block, const TableView& W, at::Tensor* zero_me, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int MT = (M + 255) / 256, NT = (N + T2_BN - 1) / T2_BN, KT = K / TC_BK;
+  const long long tiles = (long long)MT * NT;
+  int n_clusters = (int)std::min<long long>(sms / 2, tiles * KT);
+  if (tiles % n_clusters != 0 && zero_me != nullptr)     // the last wave is cut by k: its writers all red.add
+    C10_CUDA_CHECK(cudaMemsetAsync(zero_me->data_ptr(), 0, (size_t)zero_me->size(0) * zero_me->stride(0) * 4, stream));
+  cudaFuncSetAttribute(dense_gemm_tf32_sk_kernel<A_MN, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES);
+  dense_gemm_tf32_sk_kernel<A_MN, PUSH><<<2 * n_clusters, TC_THREADS, SK_SMEM_BYTES, stream>>>(
+      tmA, tmB, out, out_stride, M, N, K, rows_per_block, W);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 // ---- host: tensor maps ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -430,7 +650,7 @@ at::Tensor make_block_tensormaps(at::Tensor block_ptrs_cpu, int64_t rows_per_blo
 
 // logits[M, >=N] = X[M, K] . W[K, N]   (W rows live in the table blocks described by `bmaps`)
 void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, int64_t n_cols, at::Tensor out,
-                       int64_t dbg, int64_t b_lbo, int64_t b_sbo, int64_t idesc_xor, int64_t b_layout, bool use_2cta) {
+                       bool use_2cta, bool stream_k) {
   c10::cuda::CUDAGuard guard(X.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
@@ -444,7 +664,12 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
   // per-device attribute (several executors of one process may drive different GPUs): set it every launch
   cudaFuncSetAttribute(dense_gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   TableView none{};
-  if (use_2cta && dbg == 0) {
+  if (use_2cta && stream_k) {
+    launch_stream_k<false, false>(tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(),
+                                  (int)out.stride(0), M, N, K, (int)rows_per_block, none, &out, stream);
+    return;
+  }
+  if (use_2cta) {
     cudaFuncSetAttribute(dense_gemm_tf32_2cta_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
     dim3 grid2(2 * ((M + 255) / 256), (N + T2_BN - 1) / T2_BN);
     dense_gemm_tf32_2cta_kernel<false, false><<<grid2, TC_THREADS, T2_SMEM_BYTES, stream>>>(
@@ -456,15 +681,14 @@ void dense_logits_tf32(at::Tensor X, at::Tensor bmaps, int64_t rows_per_block, i
   dim3 grid((N + TC_BN - 1) / TC_BN, (M + TC_BM - 1) / TC_BM);
   dense_gemm_tf32_kernel<false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
       tmA, reinterpret_cast<const CUtensorMap*>(bmaps.data_ptr()), out.data_ptr<float>(), (int)out.stride(0), M, N,
-      K, (int)rows_per_block, (int)dbg, (int)(b_lbo ? b_lbo : TC_BK * 128), (int)(b_sbo ? b_sbo : 512),
-      (int)idesc_xor, (int)(b_layout ? b_layout : 1), none);
+      K, (int)rows_per_block, none);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
 // W[f, :] += sum_b X[b, f] * D[b, :]   (D is pre-scaled by -step).  GEMM M = features, N = classes, K = batch;
 // the epilogue reduce-adds each 128 x 128 gradient tile into the owners' rows: no gradient buffer exists.
 void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int64_t rows_per_block,
-                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta) {
+                          int64_t row_stride, int64_t n_classes, int64_t mode, bool use_2cta, bool stream_k) {
   c10::cuda::CUDAGuard guard(X.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TORCH_CHECK(X.is_cuda() && X.scalar_type() == at::kFloat && X.dim() == 2 && X.stride(1) == 1);
@@ -489,6 +713,11 @@ void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int
   W.row_dim = (int)n_classes;
   W.mode = (int)mode;
   const int N = (int)row_stride;
+  if (use_2cta && stream_k) {
+    launch_stream_k<true, true>(tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30,
+                                W, nullptr, stream);
+    return;
+  }
   if (use_2cta) {
     cudaFuncSetAttribute(dense_gemm_tf32_2cta_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
     dim3 grid2(2 * ((F + 255) / 256), (N + T2_BN - 1) / T2_BN);
@@ -499,8 +728,7 @@ void dense_grad_push_tf32(at::Tensor X, at::Tensor D, at::Tensor block_ptrs, int
   }
   dim3 grid((N + TC_BN - 1) / TC_BN, (F + TC_BM - 1) / TC_BM);
   dense_gemm_tf32_kernel<true, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
-      tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30, 0, TC_BK * 128, 512, 0,
-      1, W);
+      tmA, reinterpret_cast<const CUtensorMap*>(dmap.data_ptr()), nullptr, 0, F, N, Bk, 1 << 30, W);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -120,6 +120,90 @@ __global__ void __launch_bounds__(NV_THREADS) ship_fwd_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K1, third generation (the default): PUSH-based reduce-scatter.  Same gather loop as above, but the partial
+// logits of instance (w, b) leave the SM as 128-bit red.add straight into worker w's logits buffer (local or
+// NVLink peer mapping): fire-and-forget, so the transfer hides behind the next rows' gathers, and no P buffer
+// exists (-256 MB of HBM traffic per step at 8 GPUs).
+// A CTA owns a whole TILE (w, t) of `tile_rows` instances: it issues the reductions of all of them, fences
+// ONCE at system scope (one NVLink round trip per tile, not per instance -- per-instance fences cost 2x on real
+// links) and raises worker w's flag itself: no tile counter.  Tiles are handed out tile-major by an atomic
+// work counter, so the SMs stay evenly loaded and the workers' tiles complete in order for K2.
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(NV_THREADS) ship3_fwd_kernel(
+    TableView W, const int* __restrict__ csr_ptr, const int* __restrict__ csr_col,
+    const float* __restrict__ csr_val, int world, int B, int tile_rows, int n_tiles,
+    const long long* __restrict__ logit_ptrs, int l_stride, unsigned* __restrict__ work_ctr,
+    const long long* __restrict__ pflag_ptrs, unsigned epoch) {
+  __shared__ const float* s_row[NV_THREADS];
+  __shared__ float s_val[NV_THREADS];
+  __shared__ int s_vt;
+  const int tid = threadIdx.x;
+  const int n_vtiles = n_tiles * world;
+  unsigned* ctr = work_ctr + (epoch & 1u);
+  if (blockIdx.x == 0 && tid == 0) work_ctr[(epoch + 1u) & 1u] = 0u;     // re-arm the NEXT launch's counter
+  while (true) {
+    __syncthreads();                                        // s_vt / s_row of the previous tile are consumed
+    if (tid == 0) s_vt = (int)atomicAdd(ctr, 1u);
+    __syncthreads();
+    const int vt = s_vt;
+    if (vt >= n_vtiles) break;
+    const int t = vt / world, w_id = vt - t * world;
+    const int b_end = min(B, (t + 1) * tile_rows);
+    for (int b = t * tile_rows; b < b_end; ++b) {
+      const int r = w_id * B + b;
+      const int beg = csr_ptr[r], end = csr_ptr[r + 1];
+      if (beg == end) continue;                             // (uniform across the CTA)
+      float4 acc[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int base = beg; base < end; base += NV_THREADS) {
+        const int cnt = min(NV_THREADS, end - base);
+        __syncthreads();
+        if (tid < cnt) {
+          s_row[tid] = row_ptr<float>(W, (long long)csr_col[base + tid]);
+          s_val[tid] = csr_val[base + tid];
+        }
+        __syncthreads();
+        constexpr int U = (VEC == 1) ? 8 : (VEC == 2 ? 4 : 2);
+        for (int j = 0; j < cnt; j += U) {                  // the tail group is padded: every load precedes the FMAs
+          float4 wv[U][VEC];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const int c0 = 4 * (tid + k * NV_THREADS);
+              wv[u][k] = (j + u < cnt && c0 < W.row_stride) ? ld_stream_f4(s_row[j + u] + c0)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float x = (j + u < cnt) ? s_val[j + u] : 0.f;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              acc[k].x = fmaf(x, wv[u][k].x, acc[k].x); acc[k].y = fmaf(x, wv[u][k].y, acc[k].y);
+              acc[k].z = fmaf(x, wv[u][k].z, acc[k].z); acc[k].w = fmaf(x, wv[u][k].w, acc[k].w);
+            }
+          }
+        }
+      }
+      // reduce-scatter epilogue: add the partial logits into the owning worker's buffer (peer memory)
+      float* dst = reinterpret_cast<float*>(logit_ptrs[w_id]) + (size_t)b * l_stride;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const int c0 = 4 * (tid + k * NV_THREADS);
+        if (c0 < l_stride) red_add_f4_sys(dst + c0, acc[k]);
+      }
+    }
+    if (pflag_ptrs != nullptr) {
+      __threadfence_system();                               // MY reductions of this tile are performed system-wide
+      __syncthreads();                                      // ... and so are those of every thread of the CTA
+      if (tid == 0) red_release_sys_add_u32(reinterpret_cast<unsigned*>(pflag_ptrs[w_id]) + t, 1u);
+    }
+  }
+}
+
 // Warp-per-instance K1 (row_stride <= 1024 floats).  With the model sharded over N GPUs an instance has only
 // nnz / N of its features at this owner (12 at N = 8): a CTA per instance would spend its time in barriers and in a
 // serial tail.  Here every warp owns one instance: lane j fetches non-zero j (column, value), the pair is broadcast
@@ -210,14 +294,14 @@ __global__ void __launch_bounds__(FW_THREADS) ship_fwd_warp_kernel(
 //   !USE_MC: src_ptrs[n_src] are unicast buffers to sum, dst_ptrs[n_dst] are unicast destinations.
 // Source row = src_row0 + b, destination row = dst_row0 + b.
 // ---------------------------------------------------------------------------------------------------------
-static constexpr int SM_THREADS = 128;      // small CTAs: K2 must fit next to the resident K1 CTAs on every SM
-template <int NV, bool USE_MC>
+static constexpr int SM_THREADS = 128;      // 4 warps x 2 instances per tile; 10 K registers: fits next to the K1 CTAs
+template <int NV, bool SRC_MC, bool DST_MC>
 __global__ void __launch_bounds__(SM_THREADS) ship_softmax_kernel(
     const float* __restrict__ src_mc, const long long* __restrict__ src_ptrs, int n_src, int src_row0,
     float* __restrict__ dst_mc, const long long* __restrict__ dst_ptrs, int n_dst, int dst_row0,
     int stride, const int* __restrict__ labels, int B, int C, float step, float lscale, int tile_rows, int n_tiles,
     const unsigned* __restrict__ pflag, unsigned pflag_target,
-    const long long* __restrict__ dcount_ptrs, float* __restrict__ stats, int* __restrict__ err) {
+    const long long* __restrict__ dcount_ptrs, float* __restrict__ stats, int* __restrict__ err, int zero_src) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   __shared__ int s_ok;
   float wloss = 0.f, whit = 0.f;
@@ -236,13 +320,16 @@ __global__ void __launch_bounds__(SM_THREADS) ship_softmax_kernel(
         v[k] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         if (c0 < stride) {
           const size_t off = (size_t)(src_row0 + b) * stride + c0;
-          if (USE_MC) {
+          if (SRC_MC) {
             v[k] = multimem_ld_reduce_add_f4(src_mc + off);
           } else {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int g = 0; g < n_src; ++g) {
-              const float4 a = ld_stream_f4(reinterpret_cast<const float*>(src_ptrs[g]) + off);
+              float* sp = reinterpret_cast<float*>(src_ptrs[g]) + off;
+              const float4 a = ld_stream_f4(sp);
               s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+              // push-based reduce-scatter (v3): the owners red.add into this buffer, the reader re-arms it
+              if (zero_src) *reinterpret_cast<float4*>(sp) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             v[k] = s;
           }
@@ -279,7 +366,7 @@ __global__ void __launch_bounds__(SM_THREADS) ship_softmax_kernel(
         }
         const float4 dv = make_float4(d[0], d[1], d[2], d[3]);
         const size_t off = (size_t)(dst_row0 + b) * stride + c0;
-        if (USE_MC) {
+        if (DST_MC) {
           multimem_st_f4(dst_mc + off, dv);
         } else {
           for (int g = 0; g < n_dst; ++g) st_stream_f4(reinterpret_cast<float*>(dst_ptrs[g]) + off, dv);
@@ -347,10 +434,13 @@ void ship_preload(int64_t device) {
   HB_TOUCH(ship_fwd_kernel<1>); HB_TOUCH(ship_fwd_kernel<2>); HB_TOUCH(ship_fwd_kernel<4>);
   HB_TOUCH(ship_fwd_warp_kernel<1>); HB_TOUCH(ship_fwd_warp_kernel<2>); HB_TOUCH(ship_fwd_warp_kernel<4>);
   HB_TOUCH(ship_fwd_warp_kernel<8>);
-  HB_TOUCH((ship_softmax_kernel<1, true>)); HB_TOUCH((ship_softmax_kernel<2, true>));
-  HB_TOUCH((ship_softmax_kernel<4, true>)); HB_TOUCH((ship_softmax_kernel<8, true>));
-  HB_TOUCH((ship_softmax_kernel<1, false>)); HB_TOUCH((ship_softmax_kernel<2, false>));
-  HB_TOUCH((ship_softmax_kernel<4, false>)); HB_TOUCH((ship_softmax_kernel<8, false>));
+  HB_TOUCH((ship_softmax_kernel<1, true, true>)); HB_TOUCH((ship_softmax_kernel<2, true, true>));
+  HB_TOUCH((ship_softmax_kernel<4, true, true>)); HB_TOUCH((ship_softmax_kernel<8, true, true>));
+  HB_TOUCH((ship_softmax_kernel<1, false, true>)); HB_TOUCH((ship_softmax_kernel<2, false, true>));
+  HB_TOUCH((ship_softmax_kernel<4, false, true>)); HB_TOUCH((ship_softmax_kernel<8, false, true>));
+  HB_TOUCH((ship_softmax_kernel<1, false, false>)); HB_TOUCH((ship_softmax_kernel<2, false, false>));
+  HB_TOUCH((ship_softmax_kernel<4, false, false>)); HB_TOUCH((ship_softmax_kernel<8, false, false>));
+  HB_TOUCH(ship3_fwd_kernel<1>); HB_TOUCH(ship3_fwd_kernel<2>); HB_TOUCH(ship3_fwd_kernel<4>);
   HB_TOUCH(wait_count_kernel);
 #undef HB_TOUCH
   mlr_preload_bwd();
@@ -405,19 +495,50 @@ void ship_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_str
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// v3 forward: logit_ptrs[w] = worker w's [B, stride] logits buffer as mapped here; tile signalling as in v2.
+void ship3_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t num_classes,
+                   int64_t mode, at::Tensor csr_ptr, at::Tensor csr_col, at::Tensor csr_val, int64_t world, int64_t B,
+                   int64_t tile_rows, at::Tensor logit_ptrs, int64_t tile_done_ptr,
+                   c10::optional<at::Tensor> pflag_ptrs, int64_t epoch) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView W = nv_view(block_ptrs, rows_per_block, row_stride, num_classes, mode);
+  TORCH_CHECK(csr_ptr.numel() - 1 == world * B, "routed CSR must have world*B rows");
+  TORCH_CHECK(row_stride % 32 == 0 && row_stride <= 4096 && logit_ptrs.numel() == world);
+  const int n_tiles = (int)((B + tile_rows - 1) / tile_rows);
+  const int vec = (int)((row_stride / 4 + NV_THREADS - 1) / NV_THREADS);
+  const long long* pf = pflag_ptrs.has_value()
+      ? reinterpret_cast<const long long*>(pflag_ptrs->data_ptr<int64_t>()) : nullptr;
+  unsigned* td = reinterpret_cast<unsigned*>(tile_done_ptr);      // uint32[2]: the per-launch work counters
+  TORCH_CHECK(td != nullptr, "ship3_forward needs the two work counters");
+  // persistent CTAs fetch tiles from the work counter; one CTA slot per SM is left to the resident K2
+  static const int spare = getenv("HB_SHIP_K1_SPARE") ? atoi(getenv("HB_SHIP_K1_SPARE")) : 1;   // CTA slots per SM left to K2
+  const int grid = (int)std::min<int64_t>((int64_t)n_tiles * world, fwd_grid(ship3_fwd_kernel<1>) + (1 - spare) * 148);
+#define LAUNCH_F3(V)                                                                                    \
+  ship3_fwd_kernel<V><<<grid, NV_THREADS, 0, stream>>>(                                                 \
+      W, csr_ptr.data_ptr<int>(), csr_col.data_ptr<int>(), csr_val.data_ptr<float>(), (int)world, (int)B, \
+      (int)tile_rows, n_tiles, reinterpret_cast<const long long*>(logit_ptrs.data_ptr<int64_t>()),      \
+      (int)row_stride, td, pf, (unsigned)epoch);
+  if (vec <= 1) { LAUNCH_F3(1) } else if (vec == 2) { LAUNCH_F3(2) } else { LAUNCH_F3(4) }
+#undef LAUNCH_F3
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
 void ship_softmax(int64_t src_mc, c10::optional<at::Tensor> src_ptrs, int64_t src_row0, int64_t dst_mc,
                   c10::optional<at::Tensor> dst_ptrs, int64_t dst_row0, int64_t stride, at::Tensor labels,
                   int64_t num_classes, double step, double logit_scale, int64_t tile_rows, int64_t pflag_ptr,
-                  int64_t pflag_target,
-                  c10::optional<at::Tensor> dcount_ptrs, at::Tensor stats, at::Tensor err) {
+                  int64_t pflag_target, c10::optional<at::Tensor> dcount_ptrs, at::Tensor stats, at::Tensor err,
+                  bool zero_src) {
   c10::cuda::CUDAGuard guard(labels.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   const int B = (int)labels.numel();
   if (B == 0) return;
   TORCH_CHECK(stride % 32 == 0 && stride <= 1024, "ship_softmax: row stride must be <= 1024 floats");
   TORCH_CHECK(labels.scalar_type() == at::kInt && err.scalar_type() == at::kInt);
-  const bool use_mc = src_mc != 0 && dst_mc != 0;
-  TORCH_CHECK(use_mc || (src_ptrs.has_value() && dst_ptrs.has_value()), "unicast mode needs pointer lists");
+  const bool src_is_mc = src_mc != 0, dst_is_mc = dst_mc != 0;
+  TORCH_CHECK(src_is_mc || src_ptrs.has_value(), "unicast source needs a pointer list");
+  TORCH_CHECK(dst_is_mc || dst_ptrs.has_value(), "unicast destination needs a pointer list");
+  TORCH_CHECK(!zero_src || (!src_is_mc && src_ptrs->numel() == 1), "zero_src re-arms ONE local source buffer");
   const int n_tiles = (int)((B + tile_rows - 1) / tile_rows);
   const int nv = (int)((stride / 4 + 31) / 32);
   const long long* sp = src_ptrs.has_value() ? reinterpret_cast<const long long*>(src_ptrs->data_ptr<int64_t>()) : nullptr;
@@ -427,16 +548,20 @@ void ship_softmax(int64_t src_mc, c10::optional<at::Tensor> src_ptrs, int64_t sr
   TORCH_CHECK(n_dst <= 32);
   const long long* dc = dcount_ptrs.has_value() ? reinterpret_cast<const long long*>(dcount_ptrs->data_ptr<int64_t>()) : nullptr;
   const int grid = std::min(n_tiles, 148);
-#define LAUNCH_S(NVv, MC)                                                                                \
-  ship_softmax_kernel<NVv, MC><<<grid, SM_THREADS, 0, stream>>>(                                         \
+#define LAUNCH_S(NVv, SMC, DMC)                                                                          \
+  ship_softmax_kernel<NVv, SMC, DMC><<<grid, SM_THREADS, 0, stream>>>(                                         \
       reinterpret_cast<const float*>(src_mc), sp, n_src, (int)src_row0, reinterpret_cast<float*>(dst_mc), \
       dp, dp ? (int)dst_ptrs->numel() : n_dst, (int)dst_row0, (int)stride, labels.data_ptr<int>(), B,    \
       (int)num_classes, (float)step, (float)logit_scale, (int)tile_rows, n_tiles,                       \
       reinterpret_cast<const unsigned*>(pflag_ptr),                                                     \
-      (unsigned)pflag_target, dc, stats.data_ptr<float>(), err.data_ptr<int>());
-#define DISPATCH_S(MC)                                                                                   \
-  if (nv <= 1) { LAUNCH_S(1, MC) } else if (nv <= 2) { LAUNCH_S(2, MC) } else if (nv <= 4) { LAUNCH_S(4, MC) } else { LAUNCH_S(8, MC) }
-  if (use_mc) { DISPATCH_S(true) } else { DISPATCH_S(false) }
+      (unsigned)pflag_target, dc, stats.data_ptr<float>(), err.data_ptr<int>(), zero_src ? 1 : 0);
+#define DISPATCH_S(SMC, DMC)                                                                             \
+  if (nv <= 1) { LAUNCH_S(1, SMC, DMC) } else if (nv <= 2) { LAUNCH_S(2, SMC, DMC) }                     \
+  else if (nv <= 4) { LAUNCH_S(4, SMC, DMC) } else { LAUNCH_S(8, SMC, DMC) }
+  if (src_is_mc && dst_is_mc) { DISPATCH_S(true, true) }
+  else if (!src_is_mc && dst_is_mc) { DISPATCH_S(false, true) }
+  else if (!src_is_mc && !dst_is_mc) { DISPATCH_S(false, false) }
+  else { TORCH_CHECK(false, "multicast source with unicast destinations is not instantiated"); }
 #undef DISPATCH_S
 #undef LAUNCH_S
   C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -70,15 +70,18 @@ def main():
     clock.barrier()
 
     # 2b. ship mode (dot at the owners, only [B, C] moves) computes the same update, in all three flavours:
-    #     v2 over NVLS multimem, v2 over unicast peer loads / stores, v1 (device barriers)
+    #     push / NVLS reduce-scatter x NVLS / unicast all-gather (flags), and v1 (device barriers)
     all_batches = [synthetic_batch(200, cap, classes, 11, seed=300 + r) for r in range(world)]
     rb = route_batches(table, all_batches, rank).to(dev)
-    flavours = [("v2_nvls", lambda: MLRShipModel(table, arena, group, None, classes, 0.01, 200)),
-                ("v2_unicast", lambda: MLRShipModel(table, arena, group, None, classes, 0.01, 200, multicast=False)),
+    mk = lambda **kw: MLRShipModel(table, arena, group, None, classes, 0.01, 200, **kw)   # noqa: E731
+    flavours = [("push_rs+nvls_ag", lambda: mk()),                       # default: red.add RS + multimem.st AG
+                ("nvls_rs+nvls_ag", lambda: mk(reduce_scatter="nvls")),  # multimem.ld_reduce RS + multimem.st AG
+                ("push_rs+unicast_ag", lambda: mk(multicast=False)),
+                ("nvls_rs_unicast", lambda: mk(multicast=False, reduce_scatter="nvls")),
                 ("v1", lambda: MLRShipModelV1(table, arena, group, clock, classes, 0.01, 200))]
     for name, make in flavours:
         ship = make()
-        if name == "v2_nvls":
+        if name == "push_rs+nvls_ag":
             report["nvls_multicast"] = bool(ship.nvls)
             report["mc_error"] = getattr(ship.region, "mc_error", None)
         for it in range(3):                        # buffers / epochs / flags are reusable step after step

@@ -125,6 +125,37 @@ def test_dashboard_receives_metrics_and_cached_accessor():
     assert res.ok and any(m.startswith("Dashboard:") for m in res.messages)
 
 
+def test_dashboard_plot_endpoints():
+    """The reference dashboard's URL surface (dashboard.py:47-151): POST / stores, /selectors lists what can be
+    plotted, /plot returns {time: value}; the page is a self-contained SVG plotter (no plotly / CDN here)."""
+    import json
+    import urllib.parse
+    import urllib.request
+    from harmony_b200.dolphin.dashboard import DashboardConnector, DashboardServer
+    srv = DashboardServer(port=0)
+    try:
+        c = DashboardConnector(srv.port)
+        for i in range(6):
+            c.post_metric("Worker-1" if i % 2 else "Server-0",
+                          {"epoch": i, "loss": 2.0 / (i + 1), "metrics": {"data": {"acc": 0.1 * i}}, "name": "x"})
+            time.sleep(0.02)
+        deadline = time.time() + 5
+        while time.time() < deadline and len(srv.rows()) < 6:
+            time.sleep(0.05)
+        base = f"http://127.0.0.1:{srv.port}"
+        sel = json.loads(urllib.request.urlopen(base + "/selectors").read())
+        assert sel["ids"] == ["Server-0", "Worker-1"] and "metrics.data.acc" in sel["y_axis"]["Worker-1"]
+        assert "name" not in sel["y_axis"]["Worker-1"]                          # only numeric leaves are plottable
+        series = json.loads(urllib.request.urlopen(base + "/plot?id=Worker-1&y=loss").read())
+        assert sorted(series.values(), reverse=True) == [2.0 / 2, 2.0 / 4, 2.0 / 6]
+        req = urllib.request.Request(base + "/plot", data=urllib.parse.urlencode({"id": "Server-0", "y": "epoch"}).encode())
+        assert sorted(json.loads(urllib.request.urlopen(req).read()).values()) == [0.0, 2.0, 4.0]
+        page = urllib.request.urlopen(base + "/").read().decode()
+        assert "<svg" in page and "/selectors" in page and "/plot" in page
+    finally:
+        srv.close()
+
+
 def test_metric_manager_validation_rules():
     mm = DolphinMetricManager(num_initial_to_skip=2)
     m = {"kind": "batch", "batch_time_sec": 1.0}

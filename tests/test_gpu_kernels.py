@@ -136,8 +136,9 @@ def test_mlr_ship_mode_single_gpu_matches_reference(arena):
     b = synthetic_batch(300, features, classes, 17, seed=8)
     rb = route_batches(t, [b], 0).to("cuda")
     from harmony_b200.models.mlr_ship import MLRShipModelV1
-    for cls in (MLRShipModel, MLRShipModelV1):          # v2: 3 launches + flags; v1: device barriers
-        m = cls(t, arena, g, clock, classes, 0.02, 300)
+    import functools
+    for cls in (MLRShipModel, functools.partial(MLRShipModel, reduce_scatter="nvls"), MLRShipModelV1):
+        m = cls(t, arena, g, clock, classes, 0.02, 300)     # push RS / pull RS (3 launches + flags) / v1 (barriers)
         for _ in range(2):
             W0 = t.to_dense().clone()
             m.stats.zero_()
@@ -246,7 +247,7 @@ def test_scale_local_is_one_launch(arena):
     t.close()
 
 
-@pytest.mark.parametrize("two_cta", [False, True])
+@pytest.mark.parametrize("two_cta", [False, True, "stream_k"])
 @pytest.mark.parametrize("B,F,C", [(128, 256, 128), (300, 1024, 1000), (4096, 4096, 1000)])
 def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C, two_cta):
     """tcgen05 (kind::tf32) GEMM whose B operand is TMA-loaded from the table's block slabs."""
@@ -255,7 +256,7 @@ def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C, two_cta):
     assert t.rows_per_block % 32 == 0
     X = torch.randn((B, F), device="cuda")
     W = t.to_dense()
-    out = DenseMLR(t, C, use_2cta=two_cta).logits(X)
+    out = DenseMLR(t, C, use_2cta=bool(two_cta), stream_k=two_cta == "stream_k").logits(X)
     torch.cuda.synchronize()
     ref = X.double() @ W.double()
     err = (out[:, :C].double() - ref).abs().max().item()
@@ -265,7 +266,7 @@ def test_dense_logits_tcgen05_matches_fp32_matmul(arena, B, F, C, two_cta):
     t.close()
 
 
-@pytest.mark.parametrize("two_cta", [False, True])
+@pytest.mark.parametrize("two_cta", [False, True, "stream_k"])
 @pytest.mark.parametrize("B,F,C", [(64, 256, 100), (500, 2048, 1000)])
 def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C, two_cta):
     """Forward GEMM + softmax + backward GEMM whose epilogue reduce-adds into the table rows."""
@@ -274,7 +275,7 @@ def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C, two_cta):
     X = torch.randn((B, F), device="cuda") * 0.5
     y = torch.randint(0, C, (B,), device="cuda", dtype=torch.int32)
     W0 = t.to_dense().clone()
-    m = DenseMLR(t, C, use_2cta=two_cta)
+    m = DenseMLR(t, C, use_2cta=bool(two_cta), stream_k=two_cta == "stream_k")
     m.step(X, y, 0.01)
     torch.cuda.synchronize()
     logits = X.double() @ W0.double()
