@@ -52,8 +52,10 @@ def main():
         W = t.to_dense()
         Wp = torch.zeros((F, t.row_stride), device="cuda"); Wp[:, :C] = W
         m = DenseMLR(t, C)
+        msk = DenseMLR(t, C, stream_k=True)
         out = torch.empty((B, t.row_stride), device="cuda")
         t_tc, t_tc_min = timed(lambda: m.logits(X, out))
+        t_sk, _ = timed(lambda: msk.logits(X, out))
         torch.backends.cuda.matmul.allow_tf32 = True
         t_cb, t_cb_min = timed(lambda: torch.matmul(X, Wp, out=out))
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -62,6 +64,7 @@ def main():
         flops = 2.0 * B * F * t.row_stride
         res.append({"B": B, "F": F, "C": C, "tcgen05_ms": round(t_tc, 4), "tcgen05_tflops": round(flops / t_tc / 1e9, 1),
                     "tcgen05_tflops_best": round(flops / t_tc_min / 1e9, 1),
+                    "tcgen05_persistent_stream_k_tflops": round(flops / t_sk / 1e9, 1),
                     "cublas_tf32_ms": round(t_cb, 4), "cublas_tf32_tflops": round(flops / t_cb / 1e9, 1),
                     "frac_of_cublas_tf32": round(t_cb / t_tc, 3), "rel_err_vs_fp64": err})
         t.close()

@@ -38,7 +38,8 @@ def main():
     arena = PeerArena(lr, group, segment_bytes=1 << 30)
     V, K = a.vocab, a.topics
     conf = TableConfiguration(table_id="model_table0", dense=True, capacity=V + 1, row_dim=K + 1, dtype="int32",
-                              num_total_blocks=1024, backend="device")
+                              num_total_blocks=1024, backend="device",
+                              update_function={"name": "lda_sparse", "params": {"num_topics": K}})
     table = DeviceTable(conf, arena, group)
     ntok_batch = a.docs_per_batch * a.doc_len
     model = LDADeviceModel(table, K, V, ntok_batch * a.distinct_batches, alpha=0.1, beta=0.01, seed=rank)

@@ -58,6 +58,9 @@ DOLPHIN = [
                                        "k - 1; leases taper to 1 as the budget runs out; ignored while the job's task-unit "
                                        "barriers are on; 0 = auto: 4 for the fused device trainers -- their kernels queue "
                                        "on the stream and the host only syncs at the end of a lease -- else 1)", "worker"),
+    P("gpu_sm_share", float, 0.0, "fraction of a GPU's SMs this job's kernels are launched for (device backend); "
+                                  "0 = auto: 1 / (jobs with an active worker on that GPU) -- the GPU twin of the "
+                                  "resource-typed task-unit slots", "worker"),
     P("task_unit_scheduling", str, "auto", "on | off | auto: per-phase global barriers that interleave the phases of "
                                            "co-located jobs (one driver round trip per phase); auto = on unless the "
                                            "job server's scheduler runs jobs exclusively", "worker"),

@@ -389,6 +389,9 @@ class WorkerTasklet(Tasklet):
         # budget counted it -- but no longer takes part in the job's unit barriers
         if self.use_task_units and not self._abort.is_set():
             sched.wait_schedule(self.context.tasklet_id, info)
+        dctx = self._device_ctx
+        if dctx is not None:            # GPU slot: this job's kernels take 1 / (jobs active on the GPU) of the SMs
+            dctx.apply_sm_share(self._sm_share)
         t0 = time.perf_counter()
         try:
             with trace.span(name, job=self.job_id):
@@ -399,9 +402,15 @@ class WorkerTasklet(Tasklet):
         return time.perf_counter() - t0
 
     def run(self) -> Any:
+        self._device_ctx = getattr(self.context.executor, "device_ctx", None)
+        self._sm_share = float(self.context.params.get("gpu_sm_share", 0.0) or 0.0)
+        if self._device_ctx is not None:
+            self._device_ctx.job_enter(self.job_id)
         try:
             return self._train()
         finally:
+            if self._device_ctx is not None:
+                self._device_ctx.job_leave(self.job_id)
             close = getattr(getattr(self, "accessor", None), "close", None)
             if close is not None:
                 close()                   # the cached accessor's refresh thread ends with its tasklet

@@ -58,7 +58,12 @@ class DeviceTable:
         self.rows_per_block = max(1, -(-conf.capacity // self.num_blocks))
         width = conf.row_dim * (2 if self.update_fn.device_fn == DEV_ADAGRAD else 1)
         self.row_dim = conf.row_dim
-        self.row_stride = _round_up(width, 32)
+        # LDA count rows carry a hidden 32-word topic BITMAP in the last 32 words of the (padded) row: the sparse pull
+        # reads it first and then only the 16 B chunks with non-zero counts (ops/csrc/table_ops.cu)
+        self.bitmap_words = 32 if (self.update_fn.name == "lda_sparse" and conf.dtype != "float32"
+                                   and 1 < conf.row_dim <= 1025) else 0
+        self.row_stride = _round_up(width + self.bitmap_words, 32)
+        self.bitmap_off = self.row_stride - 32 if self.bitmap_words else 0
         if self.update_fn.device_fn == DEV_ADAGRAD:
             self.row_stride = 2 * _round_up(conf.row_dim, 32)   # kernel expects h at stride/2
         self.mode = PART_ORDERED if conf.is_ordered else PART_HASHED
@@ -186,7 +191,23 @@ class DeviceTable:
     def push_sparse_i32(self, keys: torch.Tensor, topics: torch.Tensor, deltas: torch.Tensor) -> None:
         """K2+K5: LDA sparse (row, topic, delta) triples with clamp>=0 and nnz bookkeeping."""
         from ..ops import count_launch
-        self._n.table_push_sparse_i32(*self.view(), keys, topics, deltas, self.row_dim - 1)
+        self._n.table_push_sparse_i32(*self.view(), keys, topics, deltas, self.row_dim - 1, self.bitmap_off)
+        count_launch()
+
+    def pull_lda_sparse(self, keys: torch.Tensor, out: torch.Tensor, chunk_count: Optional[torch.Tensor] = None) -> None:
+        """Sparse PULL of count rows through their topic bitmaps into the dense staging rows `out` [n, >= K + 1]."""
+        from ..ops import count_launch
+        assert self.bitmap_off > 0
+        self._n.table_pull_lda_sparse(*self.view(), keys, out, self.row_dim - 1, self.bitmap_off, chunk_count)
+        count_launch()
+
+    def rebuild_bitmaps(self) -> None:
+        """Owner-side: recompute the bitmaps of the local rows from their counts (drops stale bits)."""
+        from ..ops import count_launch
+        if not self.bitmap_off or not self._local_ptr:
+            return
+        ptrs = torch.tensor([self._local_ptr[b] for b in sorted(self._local_ptr)], dtype=torch.int64, device=self.device)
+        self._n.lda_rebuild_bitmaps(ptrs, self.rows_per_block, self.row_stride, self.row_dim - 1, self.bitmap_off)
         count_launch()
 
     def put_rows(self, keys: torch.Tensor, values: torch.Tensor) -> None:
@@ -195,7 +216,7 @@ class DeviceTable:
         from ..ops import count_launch
         if self.torch_dtype == torch.int32:
             vals = (values.round() if values.is_floating_point() else values).to(torch.int32)
-            self._n.table_put_i32(*self.view(), keys, vals.contiguous())
+            self._n.table_put_i32(*self.view(), keys, vals.contiguous(), self.bitmap_off)
         else:
             self._n.table_push(*self.view(), keys, values.float().contiguous(), 3, 0.0, 0.0, 0.0, 0.0)
         count_launch()
@@ -276,8 +297,10 @@ class DeviceTable:
             self._mig[b] = (self._local_ptr[b], snaps[b], new_va[b])
         return e0.elapsed_time(e1)
 
-    def flip_blocks(self, locs, new_owner: Any) -> None:
-        """Every GPU: rewrite the pointer-table entries of the moved blocks (one launch, st.release), then fence."""
+    def flip_blocks(self, locs, new_owner: Any, fence=None) -> None:
+        """Every GPU: rewrite the pointer-table entries of the moved blocks (one launch, st.release), then fence:
+        `fence()` must return once every kernel queued BEFORE the call has finished (default: device synchronize;
+        the job server passes a per-stream event fence that does not wait for work queued later)."""
         from ..ops import count_launch
         new_va = self._resolve_locs(locs)
         blocks = sorted(new_va)
@@ -286,7 +309,11 @@ class DeviceTable:
                             self._i64(new_va[b] for b in blocks))
         count_launch()
         cur.synchronize()                        # the new addresses are in HBM: kernels starting from now on use them
-        torch.cuda.synchronize(self.device)      # fence: every kernel that may have read an old address has finished
+        if fence is not None:
+            fence()                              # every kernel that may have read an old address has finished
+        else:
+            torch.cuda.synchronize(self.device)
+        self.flip_count = getattr(self, "flip_count", 0) + 1
         for b in blocks:
             rr, si, off, _h = locs[b] if b in locs else locs[str(b)]
             self._loc[b] = (rr, si, off)

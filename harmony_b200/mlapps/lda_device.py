@@ -22,6 +22,8 @@ class LDADeviceTrainer(Trainer):
         self.table, self.comps = model_table, model_table.components
         self.dtable = model_table.device_table
         self.local_table, self.input = local_model_table, input_table
+        # per-epoch write-back of the HBM-resident assignments is only needed when plans can move worker blocks
+        self._elastic = "EmptyPlanOptimizer" not in str(params.get("optimizer", "EmptyPlanOptimizer"))
         self.K, self.V = int(params["num_topics"]), int(params["num_vocabs"])
         self.alpha, self.beta = float(params.get("alpha", 0.001)), float(params.get("beta", 0.01))
         # token layout of the worker-local assignment array: documents in key order
@@ -95,7 +97,8 @@ class LDADeviceTrainer(Trainer):
 
     def on_epoch_finished(self, epoch_idx: int) -> None:
         super().on_epoch_finished(epoch_idx)
-        self._write_back()
+        if self._elastic:
+            self._write_back()        # worker blocks can only move under an optimizer's plans
 
     def flush(self) -> None:
         self._torch.cuda.current_stream(self.dtable.device).synchronize()

@@ -24,6 +24,7 @@ class MLRDeviceTrainer(Trainer):
 
     fused_step = True      # pull / compute / push are back-to-back kernels on one stream
     wants_sorted_batches = False
+    REROUTE_CHECK_EPOCHS = 16      # ship mode: compare ownership views (rendezvous through the master) every 16th epoch
 
     def __init__(self, params: Dict[str, Any], model_table, input_table=None, **_: Any) -> None:
         import torch
@@ -194,8 +195,8 @@ class MLRDeviceTrainer(Trainer):
     def on_epoch_finished(self, epoch_idx: int) -> None:
         if self.decay_rate != 1 and (epoch_idx + 1) % self.decay_period == 0:
             self.model.decay_step(self.decay_rate)
-        if self.ship is not None:
-            self._ship_reroute_if_moved()
+        if self.ship is not None and (epoch_idx + 1) % self.REROUTE_CHECK_EPOCHS == 0:
+            self._ship_reroute_if_moved()       # a control-plane rendezvous: every worker, at the same epochs
 
     def evaluate_model(self, input_data, test_data) -> Dict[str, float]:
         out = {}

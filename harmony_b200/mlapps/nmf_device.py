@@ -26,6 +26,8 @@ class NMFDeviceTrainer(Trainer):
         self.rank = int(params["rank"])
         # worker-local L lives in HBM: one row per local input record, in key order
         self._input = input_table
+        # per-epoch write-back of the HBM-resident local model is only needed when plans can move worker blocks
+        self._elastic = "EmptyPlanOptimizer" not in str(params.get("optimizer", "EmptyPlanOptimizer"))
         self._input_rows = list(input_table.get_local_tablet().get_data_iterator())
         self._keys = sorted(k for k, _ in self._input_rows)
         self._row_of = {k: i for i, k in enumerate(self._keys)}
@@ -74,7 +76,8 @@ class NMFDeviceTrainer(Trainer):
 
     def on_epoch_finished(self, epoch_idx: int) -> None:
         super().on_epoch_finished(epoch_idx)
-        self._write_back()
+        if self._elastic:
+            self._write_back()        # worker blocks can only move under an optimizer's plans
 
     def _to_batch(self, mini_batch):
         from ..models.nmf import build_nmf_batch

@@ -43,6 +43,8 @@ class LDADeviceModel:
     sparse (row, topic, +-1) pushes with clamp / nnz bookkeeping at the owners.  Reference:
     dolphin/mlapps/lda/SparseLDASampler.java:141-274, LDATrainer.java:317-357."""
 
+    REBUILD_EVERY = 64        # steps between owner-side bitmap rebuilds (the push only ever sets bits)
+
     def __init__(self, table: DeviceTable, num_topics: int, num_vocabs: int, n_local_tokens: int,
                  alpha: float, beta: float, seed: int = 0) -> None:
         from ..ops import native
@@ -83,8 +85,13 @@ class LDADeviceModel:
             return
         rows, (ok, ot, od) = self._buffers(b.vocab.numel(), ntok)
         if not init_mode:
-            self._n.table_pull(*self.table.view(), b.vocab, rows)       # PULL batch vocabulary + summary row
-            count_launch()
+            if getattr(self.table, "bitmap_off", 0):                     # sparse PULL: bitmap first, then non-zero chunks
+                self.table.pull_lda_sparse(b.vocab, rows)
+                if self._iter % self.REBUILD_EVERY == self.REBUILD_EVERY - 1:
+                    self.table.rebuild_bitmaps()                         # owner-side: drop the stale bits
+            else:
+                self._n.table_pull(*self.table.view(), b.vocab, rows)   # PULL batch vocabulary + summary row
+                count_launch()
         nk = rows[b.vocab.numel() - 1]
         self.sum_delta.zero_()
         self._iter += 1

@@ -17,11 +17,12 @@ class DenseMLR:
     are TMA-loaded from the owners' slabs (pull fused) and whose epilogue reduce-adds into the owners' rows
     (push fused); ops/csrc/mlr_dense_tc.cu."""
 
-    def __init__(self, table: DeviceTable, num_classes: int, use_2cta: bool = True, stream_k: bool = True) -> None:
+    def __init__(self, table: DeviceTable, num_classes: int, use_2cta: bool = True, stream_k: bool = False) -> None:
         # use_2cta: cta_group::2 kernels (256 x 256 tile per CTA pair, ~640 TFLOP/s tf32 measured vs ~340 for
         # the single-CTA 128 x 128 kernel, which is L2-bandwidth bound at 32 FLOP per staged byte)
-        # stream_k: the persistent variant -- one cluster per TPC, the (tile, k-step) space cut into equal ranges,
-        # double-buffered TMEM so the epilogue of one work unit overlaps the MMAs of the next
+        # stream_k: the persistent variant -- one cluster per TPC, whole waves strided + a stream-K tail, double-buffered
+        # TMEM so the epilogue of one work unit overlaps the MMAs of the next.  Measured slower than the tile-parallel
+        # kernel on B200 (508 / 642 / 578 vs 639 / 644 / 599 TFLOP/s, DESIGN.md section 5), hence off by default
         self.use_2cta = use_2cta
         self.stream_k = stream_k and use_2cta
         from ..ops import native

@@ -58,6 +58,22 @@ static std::mutex g_mu;
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- per-thread SM budget (see hb_common.cuh) ----
+static thread_local double t_sm_share = 1.0;
+void set_sm_share(double share) { t_sm_share = share <= 0.0 ? 1.0 : (share > 1.0 ? 1.0 : share); }
+double get_sm_share() { return t_sm_share; }
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+      sms = n;
+    else { cudaGetLastError(); sms = 148; }
+  }
+  const int n = (int)(sms * t_sm_share + 0.5);
+  return n < 1 ? 1 : n;
+}
+
 int64_t arena_create(int64_t device, int64_t bytes, int64_t kind, int64_t align) {
   auto* a = new Arena();
   a->device = (int)device;

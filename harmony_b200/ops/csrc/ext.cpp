@@ -23,6 +23,9 @@ void mc_unmap(int64_t va, int64_t bytes);
 void mc_destroy(int64_t id, int64_t device);
 void close_fd(int64_t fd);
 int64_t arena_alloc(int64_t id, int64_t bytes);
+void set_sm_share(double share);
+double get_sm_share();
+int sm_count();
 void arena_free(int64_t id, int64_t ptr);
 std::vector<int64_t> arena_stats(int64_t id);
 void arena_destroy(int64_t id);
@@ -38,7 +41,12 @@ void table_pull(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_strid
 void table_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
                 at::Tensor keys, at::Tensor deltas, int64_t fn, double step, double lo, double hi, double eps);
 void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
-                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K);
+                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K,
+                           int64_t bitmap_off);
+void table_pull_lda_sparse(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor out, int64_t K, int64_t bitmap_off,
+                           c10::optional<at::Tensor> chunk_count);
+void lda_rebuild_bitmaps(at::Tensor slab_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t K, int64_t bitmap_off);
 void table_push_scalar_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
                            int64_t mode, at::Tensor keys, at::Tensor values, int64_t op);
 void init_slab(int64_t slab_ptr, int64_t rows, int64_t row_stride, int64_t row_dim, int64_t kind, double a,
@@ -52,7 +60,7 @@ void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptr
 void flip_blocks(at::Tensor ptr_table, at::Tensor blocks, at::Tensor new_ptrs);
 void scale_blocks(at::Tensor ptrs, int64_t block_bytes, double factor);
 void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
-                   at::Tensor keys, at::Tensor values);
+                   at::Tensor keys, at::Tensor values, int64_t bitmap_off);
 void clock_publish(at::Tensor clock_ptrs, int64_t rank, int64_t value);
 void clock_wait(at::Tensor my_clocks, int64_t min_value, int64_t timeout_cycles, at::Tensor err_flag);
 // mlr_ops.cu
@@ -139,6 +147,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mc_destroy", &hb::mc_destroy);
   m.def("close_fd", &hb::close_fd);
   m.def("arena_alloc", &hb::arena_alloc);
+  m.def("set_sm_share", &hb::set_sm_share);
+  m.def("get_sm_share", &hb::get_sm_share);
+  m.def("sm_count", &hb::sm_count);
   m.def("arena_free", &hb::arena_free);
   m.def("arena_stats", &hb::arena_stats);
   m.def("arena_destroy", &hb::arena_destroy);
@@ -149,7 +160,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("tensor_from_ptr", &hb::tensor_from_ptr);
   m.def("table_pull", &hb::table_pull);
   m.def("table_push", &hb::table_push);
-  m.def("table_push_sparse_i32", &hb::table_push_sparse_i32);
+  m.def("table_push_sparse_i32", &hb::table_push_sparse_i32, py::arg("block_ptrs"), py::arg("rows_per_block"),
+        py::arg("row_stride"), py::arg("row_dim"), py::arg("mode"), py::arg("keys"), py::arg("topics"), py::arg("deltas"),
+        py::arg("K"), py::arg("bitmap_off") = 0);
+  m.def("table_pull_lda_sparse", &hb::table_pull_lda_sparse, py::arg("block_ptrs"), py::arg("rows_per_block"),
+        py::arg("row_stride"), py::arg("row_dim"), py::arg("mode"), py::arg("keys"), py::arg("out"), py::arg("K"),
+        py::arg("bitmap_off"), py::arg("chunk_count") = py::none());
+  m.def("lda_rebuild_bitmaps", &hb::lda_rebuild_bitmaps);
   m.def("table_push_scalar_i32", &hb::table_push_scalar_i32);
   m.def("init_slab", &hb::init_slab);
   m.def("migrate_copy", &hb::migrate_copy);
@@ -158,7 +175,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("migrate_drain", &hb::migrate_drain);
   m.def("flip_blocks", &hb::flip_blocks);
   m.def("scale_blocks", &hb::scale_blocks);
-  m.def("table_put_i32", &hb::table_put_i32);
+  m.def("table_put_i32", &hb::table_put_i32, py::arg("block_ptrs"), py::arg("rows_per_block"), py::arg("row_stride"),
+        py::arg("row_dim"), py::arg("mode"), py::arg("keys"), py::arg("values"), py::arg("bitmap_off") = 0);
   m.def("clock_publish", &hb::clock_publish);
   m.def("clock_wait", &hb::clock_wait);
   m.def("mlr_forward", &hb::mlr_forward, py::arg("block_ptrs"), py::arg("rows_per_block"), py::arg("row_stride"),

@@ -15,6 +15,12 @@
 
 namespace hb {
 
+// Host side: the number of SMs a launch of the CALLING THREAD may fill (arena.cpp).  A tasklet thread whose job
+// shares the GPU with other jobs gets a fraction of the 148 SMs (`set_sm_share`): its grid-stride kernels then take
+// that share of the CTA slots and the co-located jobs' kernels run next to them instead of behind them -- the GPU
+// form of the reference's resource-typed task-unit slots (LocalTaskUnitScheduler.java:36-37: CPU x1, NET x2).
+int sm_count();
+
 enum PartitionMode : int { PART_ORDERED = 0, PART_HASHED = 1 };
 
 struct TableView {

@@ -399,7 +399,7 @@ double lgamma_sum_i32(at::Tensor x, int64_t cols, double c) {
   at::Tensor out = at::zeros({1}, x.options().dtype(at::kDouble));
   long long rows = x.size(0);
   if (rows * cols == 0) return 0.0;
-  int grid = (int)std::min<long long>((rows * cols + 255) / 256, 148 * 8);
+  int grid = (int)std::min<long long>((rows * cols + 255) / 256, hb::sm_count() * 8);
   lgamma_sum_kernel<<<grid, 256, 0, stream>>>(x.data_ptr<int>(), rows, (int)cols, (int)x.stride(0), c,
                                               out.data_ptr<double>());
   C10_CUDA_KERNEL_LAUNCH_CHECK();

@@ -179,7 +179,7 @@ void lda_sample(at::Tensor doc_ptr, at::Tensor tok_slot, at::Tensor slot_key, at
   TORCH_CHECK(smem <= 200 * 1024, "num_topics too large for the shared-memory sampler");
   // per-device attribute: set on every launch (executors of one process may drive different GPUs)
   cudaFuncSetAttribute(lda_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int grid = std::min((n_docs + LDA_WARPS - 1) / LDA_WARPS, 148 * 8);
+  const int grid = std::min((n_docs + LDA_WARPS - 1) / LDA_WARPS, hb::sm_count() * 8);
   lda_sample_kernel<<<grid, LDA_WARPS * 32, smem, stream>>>(
       doc_ptr.data_ptr<int>(), tok_slot.data_ptr<int>(),
       reinterpret_cast<const long long*>(slot_key.data_ptr<int64_t>()), z.data_ptr<int>(), n_docs,

@@ -322,7 +322,7 @@ void mlr_forward(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stri
     dptr = D->data_ptr<float>();
   }
   const int vec = (int)((row_stride / 4 + MLR_THREADS - 1) / MLR_THREADS);
-  const int grid = std::min(B, 148 * 32);
+  const int grid = std::min(B, hb::sm_count() * 32);
 #define LAUNCH_FWD(V)                                                                                      \
   if (dptr) mlr_fwd_kernel<V, true><<<grid, MLR_THREADS, 0, stream>>>(                                     \
         W, csr_ptr.data_ptr<int>(), csr_col.data_ptr<int>(), csr_val.data_ptr<float>(),                    \
@@ -354,7 +354,7 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
   TORCH_CHECK(D.scalar_type() == at::kFloat && D.stride(0) == row_stride && D.stride(1) == 1);
   if (!local_rmw && row_stride <= 1024) {     // warp-per-feature fast path
     const int nv = (int)((row_stride / 4 + 31) / 32);
-    const int gridw = std::min((U + 7) / 8, 148 * 16);
+    const int gridw = std::min((U + 7) / 8, hb::sm_count() * 16);
 #define LAUNCH_BW(NVv)                                                                             \
     mlr_bwd_push_warp_kernel<NVv><<<gridw, 256, 0, stream>>>(                                      \
         W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),               \
@@ -365,7 +365,7 @@ void mlr_backward_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t ro
     return;
   }
   const int vec = (int)((row_stride / 4 + MLR_THREADS - 1) / MLR_THREADS);
-  const int grid = std::min(U, 148 * 8);
+  const int grid = std::min(U, hb::sm_count() * 8);
 #define LAUNCH_BWD(V)                                                                               \
   if (local_rmw) mlr_bwd_push_kernel<V, true><<<grid, MLR_THREADS, 0, stream>>>(                    \
       W, uniq_feat.data_ptr<int>(), feat_ptr.data_ptr<int>(), samp.data_ptr<int>(),                 \

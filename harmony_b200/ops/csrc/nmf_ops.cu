@@ -99,7 +99,7 @@ void nmf_batch(at::Tensor csr_ptr, at::Tensor col_slot, at::Tensor val, at::Tens
   TORCH_CHECK(L.stride(0) % 4 == 0 && Rst.stride(0) % 4 == 0, "row strides must be multiples of 4 floats");
   TORCH_CHECK(L.stride(0) >= ((rank + 3) / 4) * 4, "L rows must be padded to a multiple of 4 floats");
   const int rpl = (int)((rank + 127) / 128);
-  const int grid = std::min((n_rows + 7) / 8, 148 * 8);
+  const int grid = std::min((n_rows + 7) / 8, hb::sm_count() * 8);
 #define LAUNCH_NMF(R)                                                                                   \
   nmf_batch_kernel<R><<<grid, 256, 0, stream>>>(                                                        \
       csr_ptr.data_ptr<int>(), col_slot.data_ptr<int>(), val.data_ptr<float>(), n_rows, (int)rank,      \

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) pull_rows_i32_kernel(TableView t, const l
 // a decrement below zero is compensated by adding the deficit back.
 __global__ void __launch_bounds__(256) push_sparse_i32_kernel(TableView t, const long long* __restrict__ keys,
                                                               const int* __restrict__ topics,
-                                                              const int* __restrict__ deltas, int n, int K) {
+                                                              const int* __restrict__ deltas, int n, int K,
+                                                              int bitmap_off) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int d = deltas[i];
@@ -148,8 +149,74 @@ __global__ void __launch_bounds__(256) push_sparse_i32_kernel(TableView t, const
     atom_add_s32_sys(row + topics[i], -nv);
     nv = 0;
   }
-  if (old <= 0 && nv > 0) atom_add_s32_sys(row + K, 1);
-  else if (old > 0 && nv == 0) atom_add_s32_sys(row + K, -1);
+  if (old <= 0 && nv > 0) {
+    atom_add_s32_sys(row + K, 1);
+    // topic bitmap of the sparse PULL: bits are only ever SET here (set / clear do not commute under concurrent
+    // +1 / -1 of different workers); stale bits cost a 16 B chunk read and are dropped by lda_rebuild_bitmaps
+    if (bitmap_off > 0) {
+      unsigned* w = reinterpret_cast<unsigned*>(row + bitmap_off) + (topics[i] >> 5);
+      asm volatile("red.relaxed.sys.global.or.b32 [%0], %1;" :: "l"(w), "r"(1u << (topics[i] & 31)) : "memory");
+    }
+  } else if (old > 0 && nv == 0) {
+    atom_add_s32_sys(row + K, -1);
+  }
+}
+
+// Sparse PULL of LDA count rows (SparseArrayCodec.java:58-101 sends nnz-prefixed (index, value) pairs; here the
+// row's topic BITMAP -- 128 B -- is read first and then only the 16 B chunks that hold a non-zero count, so a
+// word with 10 topics costs ~300 B of NVLink / HBM traffic instead of 4 KB).  The output row is the dense
+// staging row the sampler expects (zero-filled locally).  One warp per row; lane l owns topics [32 l, 32 l + 32).
+__global__ void __launch_bounds__(256) pull_rows_lda_sparse_kernel(TableView t, const long long* __restrict__ keys,
+                                                                   int n, int* __restrict__ out, int out_stride,
+                                                                   int K, int bitmap_off,
+                                                                   unsigned long long* __restrict__ chunk_count) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  unsigned long long mine = 0;
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    const int* src = row_ptr<int>(t, keys[i]);
+    int* dst = out + (size_t)i * out_stride;
+    const unsigned word = (unsigned)src[bitmap_off + lane];          // 128 B: the whole bitmap in one transaction
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ch = 32 * q + lane;                                  // chunk (4 topics): coalesced across the warp
+      const unsigned w = __shfl_sync(0xffffffffu, word, ch >> 3);    // bitmap word of topics [32 (ch / 8), +32)
+      const int c = 4 * ch;
+      if (c < out_stride) {
+        int4 x = make_int4(0, 0, 0, 0);
+        if ((w >> (4 * (ch & 7))) & 0xFu) { x = ld_stream_i4(src + c); ++mine; }
+        *reinterpret_cast<int4*>(dst + c) = x;                       // the staging row is dense: zeros elsewhere
+      }
+    }
+    __syncwarp();
+    if (lane == 0) dst[K] = src[K];                                  // the row's non-zero counter rides along
+  }
+  if (chunk_count != nullptr && mine) atomicAdd(chunk_count, mine);
+}
+
+// Owner-side: recompute the bitmaps of a list of LOCAL slabs from the counts (drops stale bits).
+__global__ void __launch_bounds__(256) lda_rebuild_bitmaps_kernel(const long long* __restrict__ slab_ptrs, int n_blocks,
+                                                                  int rows_per_block, int row_stride, int K,
+                                                                  int bitmap_off) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)n_blocks * rows_per_block;
+  for (long long r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < total; r += (long long)gridDim.x * warps_per_cta) {
+    int* row = reinterpret_cast<int*>(slab_ptrs[r / rows_per_block]) + (size_t)(r % rows_per_block) * row_stride;
+    unsigned word = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int c = 32 * lane + 4 * q;
+      if (c < K) {
+        const int4 x = *reinterpret_cast<const int4*>(row + c);
+        const int xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < K && xs[e] > 0) word |= 1u << (4 * q + e);
+      }
+    }
+    reinterpret_cast<unsigned*>(row + bitmap_off)[lane] = word;
+  }
 }
 
 // Integer scatter-reduce of one value per key (Pregel message combiners, K13): op 0 = add, 1 = min.
@@ -361,13 +428,22 @@ __global__ void __launch_bounds__(256) scale_blocks_kernel(const long long* __re
 
 // ASSIGN for int32 tables (checkpoint restore of the LDA model): bit-exact copy, no float conversion.
 __global__ void __launch_bounds__(256) put_rows_i32_kernel(TableView t, const long long* __restrict__ keys, int n,
-                                                           const int* __restrict__ values, int v_stride) {
+                                                           const int* __restrict__ values, int v_stride,
+                                                           int bitmap_off) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
     int* dst = row_ptr<int>(t, keys[i]);
     const int* src = values + (size_t)i * v_stride;
-    for (int e = lane; e < t.row_dim; e += 32) dst[e] = src[e];
+    for (int e0 = 0; e0 < t.row_dim; e0 += 32) {
+      const int e = e0 + lane;
+      const int v = (e < t.row_dim) ? src[e] : 0;
+      if (e < t.row_dim) dst[e] = v;
+      if (bitmap_off > 0) {                       // LDA rows: word e0 / 32 of the topic bitmap (last column = nnz counter)
+        const unsigned m = __ballot_sync(0xffffffffu, e < t.row_dim - 1 && v > 0);
+        if (lane == 0 && (e0 >> 5) < 32) reinterpret_cast<unsigned*>(dst + bitmap_off)[e0 >> 5] = m;
+      }
+    }
   }
 }
 
@@ -427,7 +503,7 @@ static TableView make_view(const at::Tensor& block_ptrs, int64_t rows_per_block,
 
 static int grid_for_rows(int64_t n, int warps_per_cta) {
   int64_t g = (n + warps_per_cta - 1) / warps_per_cta;
-  int64_t cap = 148 * 16;
+  int64_t cap = hb::sm_count() * 16;
   return (int)std::max<int64_t>(1, std::min<int64_t>(g, cap));
 }
 
@@ -474,7 +550,8 @@ void table_push(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_strid
 }
 
 void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
-                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K) {
+                           int64_t mode, at::Tensor keys, at::Tensor topics, at::Tensor deltas, int64_t K,
+                           int64_t bitmap_off) {
   c10::cuda::CUDAGuard guard(block_ptrs.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
@@ -483,7 +560,38 @@ void table_push_sparse_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_
   TORCH_CHECK(keys.scalar_type() == at::kLong && topics.scalar_type() == at::kInt && deltas.scalar_type() == at::kInt);
   push_sparse_i32_kernel<<<(int)((n + 255) / 256), 256, 0, stream>>>(
       v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), topics.data_ptr<int>(),
-      deltas.data_ptr<int>(), (int)n, (int)K);
+      deltas.data_ptr<int>(), (int)n, (int)K, (int)bitmap_off);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void table_pull_lda_sparse(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim,
+                           int64_t mode, at::Tensor keys, at::Tensor out, int64_t K, int64_t bitmap_off,
+                           c10::optional<at::Tensor> chunk_count) {
+  c10::cuda::CUDAGuard guard(block_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
+  int64_t n = keys.numel();
+  if (n == 0) return;
+  TORCH_CHECK(keys.scalar_type() == at::kLong && out.scalar_type() == at::kInt && out.dim() == 2 && out.size(0) >= n);
+  TORCH_CHECK(out.stride(1) == 1 && out.stride(0) % 4 == 0 && out.stride(0) <= row_stride && out.stride(0) > K &&
+              reinterpret_cast<uintptr_t>(out.data_ptr<int>()) % 16 == 0, "sparse pull: bad staging layout");
+  TORCH_CHECK(bitmap_off > 0 && bitmap_off + 32 <= row_stride && K <= 1024);
+  pull_rows_lda_sparse_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
+      v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, out.data_ptr<int>(), (int)out.stride(0),
+      (int)K, (int)bitmap_off,
+      chunk_count.has_value() ? reinterpret_cast<unsigned long long*>(chunk_count->data_ptr<int64_t>()) : nullptr);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+void lda_rebuild_bitmaps(at::Tensor slab_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t K, int64_t bitmap_off) {
+  c10::cuda::CUDAGuard guard(slab_ptrs.device());
+  auto stream = at::cuda::getCurrentCUDAStream();
+  const int nb = (int)slab_ptrs.numel();
+  if (nb == 0) return;
+  const long long rows = (long long)nb * rows_per_block;
+  lda_rebuild_bitmaps_kernel<<<(int)std::min<long long>((rows + 7) / 8, 148 * 16), 256, 0, stream>>>(
+      reinterpret_cast<const long long*>(slab_ptrs.data_ptr<int64_t>()), nb, (int)rows_per_block, (int)row_stride, (int)K,
+      (int)bitmap_off);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -598,7 +706,7 @@ void scale_blocks(at::Tensor ptrs, int64_t block_bytes, double factor) {
 }
 
 void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
-                   at::Tensor keys, at::Tensor values) {
+                   at::Tensor keys, at::Tensor values, int64_t bitmap_off) {
   c10::cuda::CUDAGuard guard(block_ptrs.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   TableView v = make_view(block_ptrs, rows_per_block, row_stride, row_dim, mode);
@@ -608,7 +716,7 @@ void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_st
               values.size(0) == n && values.stride(1) == 1 && values.size(1) >= row_dim);
   put_rows_i32_kernel<<<grid_for_rows(n, 8), 256, 0, stream>>>(
       v, reinterpret_cast<const long long*>(keys.data_ptr<int64_t>()), (int)n, values.data_ptr<int>(),
-      (int)values.stride(0));
+      (int)values.stride(0), (int)bitmap_off);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

@@ -338,3 +338,50 @@ def test_block_snapshot_is_shared_until_the_block_changes():
         after = b.items_snapshot()
         assert after is not before and sorted(after) == sorted(b.items())
     assert b.items_snapshot().min_key() is None               # empty block
+
+
+def test_failing_checkpoint_write_and_restore_fail_the_driver_future_fast(cluster, monkeypatch):
+    """an exception in ChkpManagerSlave.checkpoint / load must fail checkpoint().get() /
+    create_table_from_chkp().get() with its cause instead of letting them run into their 600 s timeouts."""
+    master, execs, launcher = cluster
+    conf = TableConfiguration(table_id="ckf", dense=True, capacity=100, row_dim=2, num_total_blocks=6,
+                              update_function="add")
+    master.create_table(conf, execs).get(10)
+    good = master.get_table("ckf").checkpoint().get(20)
+    victim = launcher.executors[execs[1].id]
+
+    def boom(*a, **k):
+        raise OSError("disk full (injected)")
+    monkeypatch.setattr(victim.chkp, "checkpoint", boom)
+    t0 = time.time()
+    with pytest.raises(RuntimeError, match="disk full"):
+        master.get_table("ckf").checkpoint().get(30)
+    assert time.time() - t0 < 10
+    monkeypatch.setattr(victim.chkp, "load", boom)
+    with pytest.raises(RuntimeError, match="disk full"):
+        master.create_table_from_chkp(good, execs, table_id="ckf_restored").get(30)
+
+
+def test_model_chkp_manager_records_checkpoints_in_issue_order():
+    """per-epoch model checkpoints are taken by ONE thread, so they complete -- and are replayed -- in
+    epoch order even when a later one would finish faster."""
+    from harmony_b200.dolphin.master import ModelChkpManager
+    from harmony_b200.utils.concurrent import ResultFuture
+    delays = iter([0.30, 0.01, 0.10])
+    ids = iter(["e0", "e1", "e2"])
+
+    class FakeTable:
+        def checkpoint(self):
+            f, d, i = ResultFuture(), next(delays), next(ids)
+            threading.Timer(d, lambda: f.on_completed(i)).start()
+            return f
+
+    class FakeMaster:
+        def get_table(self, _):
+            return table
+    table = FakeTable()
+    mgr = ModelChkpManager(FakeMaster(), "model", None, "input")
+    for _ in range(3):
+        mgr.create_checkpoint_async()          # epochs end faster than a checkpoint takes
+    mgr.wait_pending()
+    assert mgr.model_chkps == ["e0", "e1", "e2"]

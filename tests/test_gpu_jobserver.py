@@ -193,21 +193,21 @@ def test_apps_with_local_model_tables_reconfigure_workers_live_on_device(app_nam
     from harmony_b200.common.samples import write_lda_sample, write_nmf_sample
     from harmony_b200.dolphin.launcher import ETDolphinLauncher
     from harmony_b200.mlapps import lda, nmf
-    opt = ["-optimizer", optimizer, "-optimization_interval_ms", "300", "-delay_after_optimization_ms", "100",
+    opt = ["-optimizer", optimizer, "-optimization_interval_ms", "60", "-delay_after_optimization_ms", "30",
            "-min_num_required_batch_metrics", "1", "-num_extra_resources", "1", "-num_dolphin_workers", "2",
            "-num_servers", "2", "-num_mini_batches", "8", "-num_worker_blocks", "8", "-num_server_blocks", "4",
            "-backend", "device"]
     if app_name == "nmf":
         d = write_nmf_sample(str(tmp_path / "n"), rows=160, cols=30, rank=4)
-        res = ETDolphinLauncher.launch(nmf.APP, ["-input", d, "-max_num_epochs", "30", "-step_size", "0.01", "-rank", "4",
+        res = ETDolphinLauncher.launch(nmf.APP, ["-input", d, "-max_num_epochs", "300", "-step_size", "0.01", "-rank", "4",
                                                  "-features", "30", "-decay_rate", "1.0"] + opt,
                                        extra_conf={"job_timeout_sec": 180})
         assert res.ok, res.messages
         assert all(r["trainer"] == "NMFDeviceTrainer" for r in res.results), res.results
-        assert max(r["last_batch_loss"] for r in res.results) < 8.0, res.results       # ~4 without reconfiguration
+        assert max(r["last_batch_loss"] for r in res.results) < 8.0, res.results       # GPU jobs are fast: many short epochs so that the optimizer fires mid-run
     else:
         d = write_lda_sample(str(tmp_path / "l"), docs=80, vocab=50, topics=3, doc_len=30)
-        res = ETDolphinLauncher.launch(lda.APP, ["-input", d, "-max_num_epochs", "10", "-num_topics", "3",
+        res = ETDolphinLauncher.launch(lda.APP, ["-input", d, "-max_num_epochs", "150", "-num_topics", "3",
                                                  "-num_vocabs", "50"] + opt, extra_conf={"job_timeout_sec": 180})
         assert res.ok, res.messages
         assert all(r["trainer"] == "LDADeviceTrainer" for r in res.results), res.results

@@ -87,6 +87,39 @@ def test_lda_sparse_push(arena):
     t.close()
 
 
+@pytest.mark.parametrize("K", [20, 1000])
+def test_lda_sparse_pull_through_topic_bitmaps(arena, K):
+    """Sparse PULL (SparseArrayCodec.java:58-101 on the GPU): bitmap first, then only the non-zero 16 B chunks; the
+    staging rows must equal the dense pull, before and after the owner-side bitmap rebuild, and after a restore."""
+    V = 500
+    t = _table(arena, V + 1, K + 1, 8, False, {"name": "lda_sparse", "params": {"num_topics": K}}, dtype="int32")
+    assert t.bitmap_off > 0 and t.row_stride >= K + 1 + 32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 4000
+    keys = torch.randint(0, V + 1, (n,), device="cuda", generator=g)
+    topics = torch.randint(0, K, (n,), device="cuda", generator=g).int()
+    t.push_sparse_i32(keys, topics, torch.randint(1, 4, (n,), device="cuda", generator=g).int())
+    t.push_sparse_i32(keys[: n // 2], topics[: n // 2], torch.full((n // 2,), -9, dtype=torch.int32, device="cuda"))  # zeros
+    all_keys = torch.arange(V + 1, device="cuda")
+    dense = t.pull(all_keys)                                            # [V + 1, K + 1]
+    out = torch.full((V + 1, t.row_stride), -7, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    t.pull_lda_sparse(all_keys, out, cnt)
+    assert torch.equal(out[:, : K + 1], dense)
+    stale = int(cnt)
+    t.rebuild_bitmaps()
+    cnt.zero_()
+    t.pull_lda_sparse(all_keys, out, cnt)
+    assert torch.equal(out[:, : K + 1], dense) and int(cnt) <= stale
+    assert int(cnt) * 16 < (V + 1) * t.row_stride * 4                 # fewer bytes than the dense rows
+    # ASSIGN (checkpoint restore) maintains the bitmaps too
+    t2 = _table(arena, V + 1, K + 1, 8, False, {"name": "lda_sparse", "params": {"num_topics": K}}, dtype="int32")
+    t2.put_rows(all_keys, dense)
+    t2.pull_lda_sparse(all_keys, out)
+    assert torch.equal(out[:, : K + 1], dense)
+    t.close(); t2.close()
+
+
 @pytest.mark.parametrize("classes,features", [(10, 784), (1000, 20000), (1500, 5000)])
 def test_mlr_step_matches_reference(arena, classes, features):
     from harmony_b200.models.mlr import MLRDeviceModel, mlr_reference_step, synthetic_batch
@@ -288,3 +321,30 @@ def test_dense_mlr_step_tcgen05_matches_reference(arena, B, F, C, two_cta):
     assert err < 5e-3 * upd + 1e-6, (err, upd)
     assert abs(float(m.stats[0]) - loss_ref) / loss_ref < 5e-3
     t.close()
+
+
+def test_sm_share_budget_is_per_thread_and_kernels_stay_correct(arena):
+    """GPU twin of the resource-typed task-unit slots: a tasklet thread launches for its job's SHARE of the SMs."""
+    import threading
+    from harmony_b200.ops import native
+    n = native()
+    full = n.sm_count()
+    assert full >= 100 and n.get_sm_share() == 1.0
+    seen = {}
+
+    def other():
+        n.set_sm_share(0.25)
+        seen["other"] = n.sm_count()
+    th = threading.Thread(target=other); th.start(); th.join()
+    assert seen["other"] == round(full * 0.25) and n.sm_count() == full        # thread-local
+    try:
+        n.set_sm_share(0.25)
+        t = _table(arena, 3000, 64, 16, False, {"name": "add", "params": {"init": "gaussian", "std": 0.1, "seed": 2}})
+        W0 = t.to_dense().clone()
+        keys = torch.randint(0, 3000, (5000,), device="cuda")
+        d = torch.randn((5000, 64), device="cuda")
+        t.push(keys, d)
+        torch.testing.assert_close(t.to_dense(), W0.clone().index_add_(0, keys, d), rtol=1e-4, atol=1e-4)
+        t.close()
+    finally:
+        n.set_sm_share(1.0)

@@ -319,3 +319,38 @@ def test_parsers_resolve_in_a_fresh_executor_process():
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PYTHONPATH=root), capture_output=True,
                          text=True, timeout=120)
     assert out.returncode == 0, out.stderr
+
+
+def test_fd_server_hands_out_duplicates_of_registered_fds():
+    """VMM segments are shared between executor processes as POSIX fds over a unix socket (SCM_RIGHTS)."""
+    import os
+    from harmony_b200.parallel.peer import FdServer
+    r, w = os.pipe()
+    srv = FdServer.get()
+    srv.register("pipe-w", lambda: os.dup(w))
+    fd = FdServer.fetch(os.getpid(), "pipe-w")
+    try:
+        assert fd != w
+        os.write(fd, b"hb")
+        assert os.read(r, 2) == b"hb"
+    finally:
+        os.close(fd)
+    with pytest.raises(KeyError):
+        FdServer.fetch(os.getpid(), "no-such-allocation")
+    srv.unregister("pipe-w")
+    with pytest.raises(KeyError):
+        FdServer.fetch(os.getpid(), "pipe-w")
+    os.close(r); os.close(w)
+
+
+def test_native_sm_share_is_thread_local():
+    from harmony_b200.ops import native_or_none
+    n = native_or_none()
+    if n is None:
+        pytest.skip("extension not built")
+    import threading
+    base = n.sm_count()
+    out = {}
+    th = threading.Thread(target=lambda: (n.set_sm_share(0.5), out.update(v=n.sm_count())))
+    th.start(); th.join()
+    assert out["v"] == round(base * 0.5) and n.sm_count() == base and n.get_sm_share() == 1.0
