@@ -21,7 +21,6 @@ from __future__ import annotations
 
 import logging
 import threading
-import weakref
 from typing import Any, Iterator, List, Optional, Tuple
 
 import numpy as np
@@ -91,9 +90,13 @@ class DeviceContext:
         # scheduled ahead of co-located jobs' when both have work queued
         s = torch.cuda.Stream(device=self.device, priority=-1 if priority < 0 else 0)
         with self._jobs_lock:
-            self._streams = [w for w in getattr(self, "_streams", []) if w() is not None]
-            self._streams.append(weakref.ref(s))
+            self._streams = getattr(self, "_streams", [])
+            self._streams.append(s)              # strong reference until the tasklet releases it (release_stream)
         return s
+
+    def release_stream(self, stream) -> None:
+        with self._jobs_lock:
+            self._streams = [x for x in getattr(self, "_streams", []) if x is not stream]
 
     def fence_streams(self) -> None:
         """Wait for the work that is ALREADY queued on this GPU's tasklet streams (+ the default and side streams) --
@@ -101,15 +104,16 @@ class DeviceContext:
         enqueueing while it waits: with four busy jobs an ownership flip took 2.2 s instead of 27 ms."""
         import torch
         with self._jobs_lock:
-            streams = [w() for w in getattr(self, "_streams", [])]
-        streams = [s for s in streams if s is not None] + [torch.cuda.default_stream(self.torch_device), self.side_stream]
-        events = []
-        for s in streams:
-            ev = torch.cuda.Event()
-            ev.record(s)
-            events.append(ev)
-        for ev in events:
-            ev.synchronize()
+            streams = list(getattr(self, "_streams", []))
+        with torch.cuda.device(self.device):
+            streams += [torch.cuda.default_stream(self.torch_device), self.side_stream]
+            events = []
+            for s in streams:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                events.append(ev)
+            for ev in events:
+                ev.synchronize()
 
 
 class DeviceBlock(Block):

@@ -142,6 +142,15 @@ class TaskletRuntime:
                 return tasklet.run()
             finally:
                 stream.synchronize()
+                release = getattr(ctx, "release_stream", None)
+                if release is not None:
+                    release(stream)
+                # the trainer's cycles (trainer <-> model <-> streams / events / HBM tensors) die HERE, on the thread
+                # and device that created them, instead of inside whichever thread happens to trigger the next
+                # automatic collection (a GC run inside torch.cuda.memory_stats of another worker segfaulted once)
+                tasklet = None   # noqa: F841
+                import gc
+                gc.collect()
 
     def stop_tasklet(self, tasklet_id: str) -> None:
         with self._lock:
