@@ -22,7 +22,7 @@ class DenseMLR:
         # the single-CTA 128 x 128 kernel, which is L2-bandwidth bound at 32 FLOP per staged byte)
         # stream_k: the persistent variant -- one cluster per TPC, whole waves strided + a stream-K tail, double-buffered
         # TMEM so the epilogue of one work unit overlaps the MMAs of the next.  Measured slower than the tile-parallel
-        # kernel on B200 (508 / 642 / 578 vs 639 / 644 / 599 TFLOP/s), hence off by default
+        # kernel at 2 of 3 shapes on B200 (516 / 645 / 513 vs 512 / 610 / 582 TFLOP/s): off by default
         self.use_2cta = use_2cta
         self.stream_k = stream_k and use_2cta
         from ..ops import native
