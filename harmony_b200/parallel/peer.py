@@ -324,7 +324,16 @@ class SymmetricRegion:
         self.mc_ptr = 0
         self._mc_id = None
         if want_mc:
-            self._setup_multicast(infos)
+            try:
+                self._setup_multicast(infos)
+            finally:
+                if getattr(self, "_mc_fd", None) is not None:      # rank 0: the exported fd has served its purpose
+                    FdServer.get().unregister("mc:%x" % self.local_ptr)
+                    try:
+                        self._n.close_fd(self._mc_fd)
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._mc_fd = None
         self.group.barrier()
 
     def _stage_ok(self, ok: bool) -> bool:
@@ -371,9 +380,6 @@ class SymmetricRegion:
         if not self._stage_ok(ok):
             return
         self.mc_ptr, self._mc_id = int(va), mc_id
-        if rank == 0:
-            FdServer.get().unregister(key)
-            n.close_fd(self._mc_fd)
 
     def tensor(self, offset: int, shape, dtype=torch.float32) -> torch.Tensor:
         return self.arena.tensor(self.local_ptr + offset, shape, dtype)

@@ -137,3 +137,92 @@ def test_load_batches_splits_a_file_exactly_over_ranks(tmp_path):
     assert all(b.batch_size == 50 for b in load_batches(path, 50, drop_last=True))
     with pytest.raises(ValueError):
         load_batches(path, 50, num_features=32)                                 # feature ids reach 63
+
+
+class _ThreadGroup:
+    """PeerGroup stand-in for N threads of one process (all_gather_object through a barrier)."""
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self.pg, self._s = rank, world, None, shared
+
+    def all_gather_object(self, obj):
+        import threading
+        s = self._s
+        with s["lock"]:
+            s["slots"][self.rank] = obj
+        s["bar"].wait(timeout=20)
+        out = list(s["slots"])
+        s["bar"].wait(timeout=20)          # nobody overwrites a slot before everyone has read
+        return out
+
+    def barrier(self):
+        self.all_gather_object(None)
+
+
+@pytest.mark.parametrize("fail_stage", [None, "add_device", "bind", "map"])
+def test_symmetric_region_downgrades_all_ranks_together_when_multicast_setup_fails(fail_stage):
+    """The NVLS set-up (cuMulticastCreate -> fd -> add device -> bind -> map) votes after every stage: a failure on ONE
+    rank must leave EVERY rank on the unicast path -- nobody may be left waiting inside a bind.  (Driver calls are
+    faked; the fd really travels through the FdServer.)"""
+    import threading
+    from harmony_b200.parallel.peer import SymmetricRegion
+    world = 2
+    shared = {"lock": threading.Lock(), "slots": [None] * world, "bar": threading.Barrier(world)}
+
+    class FakeNative:
+        def __init__(self, rank):
+            self.rank = rank
+
+        def vmm_supported(self, dev): return [True, True]
+        def mc_granularity(self, w, b, rec): return 1 << 21
+
+        def mc_create(self, dev, w, nbytes):
+            return 7, os.open(os.devnull, os.O_RDONLY)
+
+        def mc_import(self, fd, dev, w, nbytes):
+            os.fstat(fd)                       # the fd that arrived over the unix socket is a live descriptor
+            return 8
+
+        def _maybe_fail(self, stage):
+            if fail_stage == stage and self.rank == 1:
+                raise RuntimeError(f"injected {stage} failure")
+
+        def mc_add_device(self, mc, dev): self._maybe_fail("add_device")
+        def mc_bind(self, mc, off, seg, moff, nbytes): self._maybe_fail("bind")
+
+        def mc_map(self, mc, dev):
+            self._maybe_fail("map")
+            return 0xABC00000 + self.rank
+
+        def close_fd(self, fd): os.close(fd)
+
+    class FakeArena:
+        kind = "vmm"
+
+        def __init__(self, rank):
+            self.device, self._n, self.rank = rank, FakeNative(rank), rank
+
+        def new_segment(self, nbytes, align): return 0
+        def segment_base(self, seg): return 0x10000000 * (self.rank + 1)
+        def alloc_in(self, seg, nbytes): return self.segment_base(seg), seg, 0
+        def segment_info(self, seg): return {"kind": "vmm", "base": self.segment_base(seg)}
+        def map_peer(self, r, si, h): pass
+        def resolve(self, r, si, off): return 0x10000000 * (r + 1) + off
+
+    regions, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            regions[rank] = SymmetricRegion(FakeArena(rank), _ThreadGroup(rank, world, shared), 1000)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ths]
+    [t.join(30) for t in ths]
+    assert not errors and all(r is not None for r in regions), errors
+    assert [r.peer_ptrs for r in regions] == [[0x10000000, 0x20000000]] * 2
+    if fail_stage is None:
+        assert [r.mc_ptr for r in regions] == [0xABC00000, 0xABC00001]
+    else:
+        assert [r.mc_ptr for r in regions] == [0, 0]             # both downgraded, nobody hung
+        assert "injected" in regions[1].mc_error
