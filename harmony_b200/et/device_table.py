@@ -282,17 +282,20 @@ class DeviceTable:
         s = stream or torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(s):
-            e0.record()
-            self._n.migrate_bulk(self._i64(self._local_ptr[b] for b in blocks), self._i64(new_va[b] for b in blocks),
-                                 self._i64(snaps[b] for b in blocks), self.block_bytes, err)
-            e1.record()
-            count_launch()
-        s.synchronize()
-        if int(err.item()) != 0:
-            for p in snaps.values():
+        try:
+            with torch.cuda.stream(s):
+                e0.record()
+                self._n.migrate_bulk(self._i64(self._local_ptr[b] for b in blocks), self._i64(new_va[b] for b in blocks),
+                                     self._i64(snaps[b] for b in blocks), self.block_bytes, err)
+                e1.record()
+                count_launch()
+            s.synchronize()
+            if int(err.item()) != 0:
+                raise RuntimeError("bulk migration copy timed out on an mbarrier")
+        except Exception:
+            for p in snaps.values():             # nothing was flipped: the old slabs stay authoritative
                 self.arena.free(p)
-            raise RuntimeError("bulk migration copy timed out on an mbarrier")
+            raise
         for b in blocks:
             self._mig[b] = (self._local_ptr[b], snaps[b], new_va[b])
         return e0.elapsed_time(e1)
@@ -333,9 +336,12 @@ class DeviceTable:
         fw = torch.zeros(1, dtype=torch.int64, device=self.device)
         s = stream or torch.cuda.current_stream(self.device)
         with torch.cuda.stream(s):
+            from .update_function import DEV_SGD_CLAMP
+            p = self.update_fn.device_params()
+            clamp = self.update_fn.device_fn == DEV_SGD_CLAMP       # bounded rows stay inside [lo, hi] after the forward
             self._n.migrate_drain(self._i64(self._mig[b][0] for b in blocks), self._i64(self._mig[b][1] for b in blocks),
                                   self._i64(self._mig[b][2] for b in blocks), self.block_bytes,
-                                  self.torch_dtype == torch.int32, fw)
+                                  self.torch_dtype == torch.int32, fw, clamp, p["lo"], p["hi"])
             count_launch()
         s.synchronize()
         for b in blocks:

@@ -56,7 +56,7 @@ void flip_owner(at::Tensor ptr_tables, int64_t block, at::Tensor new_ptrs);
 void migrate_bulk(at::Tensor src_ptrs, at::Tensor dst_ptrs, c10::optional<at::Tensor> snap_ptrs, int64_t block_bytes,
                   at::Tensor err);
 void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptrs, int64_t block_bytes, bool is_int,
-                   at::Tensor forwarded);
+                   at::Tensor forwarded, bool do_clamp, double lo, double hi);
 void flip_blocks(at::Tensor ptr_table, at::Tensor blocks, at::Tensor new_ptrs);
 void scale_blocks(at::Tensor ptrs, int64_t block_bytes, double factor);
 void table_put_i32(at::Tensor block_ptrs, int64_t rows_per_block, int64_t row_stride, int64_t row_dim, int64_t mode,
@@ -172,7 +172,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("migrate_copy", &hb::migrate_copy);
   m.def("flip_owner", &hb::flip_owner);
   m.def("migrate_bulk", &hb::migrate_bulk);
-  m.def("migrate_drain", &hb::migrate_drain);
+  m.def("migrate_drain", &hb::migrate_drain, py::arg("old_ptrs"), py::arg("snap_ptrs"), py::arg("new_ptrs"),
+        py::arg("block_bytes"), py::arg("is_int"), py::arg("forwarded"), py::arg("do_clamp") = false,
+        py::arg("lo") = 0.0, py::arg("hi") = 0.0);
   m.def("flip_blocks", &hb::flip_blocks);
   m.def("scale_blocks", &hb::scale_blocks);
   m.def("table_put_i32", &hb::table_put_i32, py::arg("block_ptrs"), py::arg("rows_per_block"), py::arg("row_stride"),

@@ -371,12 +371,15 @@ __global__ void __launch_bounds__(128) migrate_bulk_kernel(const long long* __re
 }
 
 // new += old - snapshot for every element that changed after it was copied.  IS_INT selects s32 arithmetic.
+// CLAMP (float tables with a bounded update function, e.g. NMF's SGD + clamp): the forwarded delta is applied with
+// the returning atomic and the result is projected back into [lo, hi], like the push kernel does.
 template <bool IS_INT>
 __global__ void __launch_bounds__(256) migrate_drain_kernel(const long long* __restrict__ old_ptrs,
                                                             const long long* __restrict__ snap_ptrs,
                                                             const long long* __restrict__ new_ptrs, int n_blocks,
                                                             long long vec_per_block,
-                                                            unsigned long long* __restrict__ forwarded) {
+                                                            unsigned long long* __restrict__ forwarded,
+                                                            int do_clamp, float lo, float hi) {
   const long long total = vec_per_block * n_blocks;
   unsigned long long mine = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -395,7 +398,13 @@ __global__ void __launch_bounds__(256) migrate_drain_kernel(const long long* __r
         asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" :: "l"(p), "r"(oo[e] - ss[e]) : "memory");
       } else {
         float* p = reinterpret_cast<float*>(new_ptrs[b]) + 4 * v + e;
-        red_add_f32_sys(p, __int_as_float(oo[e]) - __int_as_float(ss[e]));
+        const float d = __int_as_float(oo[e]) - __int_as_float(ss[e]);
+        if (do_clamp) {
+            const float nv = atom_add_f32_sys(p, d) + d;
+            if (nv < lo || nv > hi) clamp_fixup(p, lo, hi);
+        } else {
+            red_add_f32_sys(p, d);
+        }
       }
     }
   }
@@ -664,7 +673,7 @@ void migrate_bulk(at::Tensor src_ptrs, at::Tensor dst_ptrs, c10::optional<at::Te
 }
 
 void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptrs, int64_t block_bytes, bool is_int,
-                   at::Tensor forwarded) {
+                   at::Tensor forwarded, bool do_clamp, double lo, double hi) {
   c10::cuda::CUDAGuard guard(old_ptrs.device());
   auto stream = at::cuda::getCurrentCUDAStream();
   const int n = (int)old_ptrs.numel();
@@ -676,8 +685,8 @@ void migrate_drain(at::Tensor old_ptrs, at::Tensor snap_ptrs, at::Tensor new_ptr
   auto* o = reinterpret_cast<const long long*>(old_ptrs.data_ptr<int64_t>());
   auto* sn = reinterpret_cast<const long long*>(snap_ptrs.data_ptr<int64_t>());
   auto* nw = reinterpret_cast<const long long*>(new_ptrs.data_ptr<int64_t>());
-  if (is_int) migrate_drain_kernel<true><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw);
-  else migrate_drain_kernel<false><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw);
+  if (is_int) migrate_drain_kernel<true><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw, 0, 0.f, 0.f);
+  else migrate_drain_kernel<false><<<grid, 256, 0, stream>>>(o, sn, nw, n, vpb, fw, do_clamp ? 1 : 0, (float)lo, (float)hi);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 

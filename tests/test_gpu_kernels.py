@@ -242,6 +242,13 @@ def test_bulk_migration_copy_snapshot_and_drain(arena):
     for a, r in zip(new, ref):
         torch.testing.assert_close(a, r, rtol=0, atol=1e-6)
     assert int(fw) == sum(len(range(k, elems, 97)) for k in range(nb))
+    # bounded update functions (NMF's SGD + clamp): the forwarded delta is projected back into [lo, hi]
+    o, sn, nw = torch.full((1024,), 0.9, device="cuda"), torch.full((1024,), 0.2, device="cuda"), \
+        torch.full((1024,), 0.6, device="cuda")
+    fw.zero_()
+    n.migrate_drain(i64([o]), i64([sn]), i64([nw]), 4096, False, fw, True, 0.0, 1.0)      # 0.6 + 0.7 -> clamp at 1.0
+    torch.cuda.synchronize()
+    assert int(fw) == 1024 and torch.allclose(nw, torch.ones_like(nw))
 
 
 def test_key_guard_clamps_and_reports(arena):
