@@ -226,3 +226,22 @@ def test_symmetric_region_downgrades_all_ranks_together_when_multicast_setup_fai
     else:
         assert [r.mc_ptr for r in regions] == [0, 0]             # both downgraded, nobody hung
         assert "injected" in regions[1].mc_error
+
+
+def test_lazy_l2_scale_algebra_matches_the_dense_decay():
+    """The lazy L2 decay (models/mlr.py, models/mlr_ship.py): the table stores v with w = s v; one step is
+    s' = s (1 - c), v' = v + delta / s' and must equal the reference's W' = (1 - c) W + delta
+    (MLRTrainer.java:387-397) -- also across a fold (v <- s v, s <- 1)."""
+    rng = np.random.default_rng(0)
+    W = rng.standard_normal((50, 7))
+    v, s = W.copy(), 1.0
+    c = 1e-2 * 0.5 * 64
+    for step in range(30):
+        delta = 1e-2 * rng.standard_normal(W.shape)            # what the push of this step adds (pre-scaled by -step)
+        W = (1 - c) * W + delta
+        s_next = s * (1 - c)
+        v = v + delta / s_next
+        s = s_next
+        if s < 1e-3 or step == 11:                             # fold_scale / renormalize
+            v, s = s * v, 1.0
+        np.testing.assert_allclose(s * v, W, rtol=1e-9, atol=1e-12)
