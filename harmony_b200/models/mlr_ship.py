@@ -153,14 +153,15 @@ class MLRShipModelV1:
 
 
 class MLRShipModel:
-    """Ship mode, second generation (ops/csrc/mlr_nvls_ops.cu): three launches per BSP step and no barrier.
+    """Ship mode, round 2 (ops/csrc/mlr_nvls_ops.cu): three launches per BSP step and no barrier.
 
-    K2 (softmax) runs on a high-priority side stream NEXT TO K1 (owner-side partial logits) and consumes logit tiles
-    as the owners flag them; the reduce-scatter is `multimem.ld_reduce` and the all-gather `multimem.st` on the
-    multicast mapping of a `SymmetricRegion` (NVLS; unicast peer loads / stores when there is no multicast);
-    K3 (owner-side row update) acquires the "all error rows have landed" counter inside the kernel.
-    Same arithmetic as MLRTrainer.java:374-398,475-505.  `lam` != 0 uses the lazy L2 scale of the table
-    (w = s * v, see `LazyScale`): logits are multiplied by s, deltas divided by the next s, no dense pass."""
+    K1 (owner-side partial logits) pushes its rows into the workers' logits buffers with `red.add` over NVLink and
+    flags each 8-instance tile; K2 (softmax) runs on a high-priority side stream NEXT TO K1, consumes tiles as all
+    owners have flagged them and broadcasts the error rows with `multimem.st` on the multicast mapping of a
+    `SymmetricRegion` (NVLS; unicast peer stores when there is no multicast); K3 (owner-side row update) acquires the
+    "all error rows have landed" counter inside the kernel.  `reduce_scatter="nvls"` swaps the push for an in-switch
+    `multimem.ld_reduce` by K2.  Same arithmetic as MLRTrainer.java:374-398,475-505.  `lam` != 0 uses the lazy L2
+    scale (w = s * v, `_scales`): logits are multiplied by s, deltas divided by the next s, no dense pass."""
 
     TILE_ROWS = 8           # instances per flag: one K1 CTA owns a tile (one system fence per tile), K2 runs it as
                             # 8 warps x 1 instance -> short tail after the last K1 tiles
