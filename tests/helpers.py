@@ -52,3 +52,27 @@ class EchoTasklet(_Tasklet):
 
     def run(self):
         return self.context.params.get("value")
+
+
+class FlushCountingTrainer(FailingTrainer):
+    """Stands in for a fused device trainer on the CPU: records when the worker loop asks it to `flush()` (wait for
+    the kernels of the mini-batches issued so far) relative to the mini-batches it was handed."""
+
+    fused_step = True
+    events = []            # class-level log: ("batch",) / ("flush",) in call order, per process
+
+    def __init__(self, params, model_accessor, context=None, **kw):
+        super().__init__(params, model_accessor, context=context, **kw)
+        FlushCountingTrainer.events = []
+
+    def local_compute(self):
+        pass
+
+    def push_update(self):
+        FlushCountingTrainer.events.append("batch")
+
+    def flush(self):
+        FlushCountingTrainer.events.append("flush")
+
+    def summary(self):
+        return {"events": list(FlushCountingTrainer.events)}

@@ -652,3 +652,27 @@ def test_standalone_offline_model_evaluation_replays_every_epoch_checkpoint():
     assert [m for m in res.messages if m.startswith("Model eval progress")] == \
         [f"Model eval progress: [{i}], JobId: MLR-0" for i in (1, 2, 3)]
     assert res.eval_results is not None and len(res.eval_results) == 2
+
+
+def test_fused_device_trainers_get_leases_by_default_and_one_flush_per_lease():
+    """Job-server GPU path (round 2): device trainers queue a whole lease of mini-batches on their stream; the worker
+    loop syncs the stream (`trainer.flush()`) once before it reports progress -- not once per mini-batch -- and
+    `-mini_batch_grant_size 0` (auto) leases 4 mini-batches to a fused trainer that can flush."""
+    from harmony_b200.dolphin.conf import ETDolphinConfiguration
+    from harmony_b200.mlapps import examples
+    import helpers  # noqa: F401
+    app = ETDolphinConfiguration(app_id="Flush", trainer_class="helpers:FlushCountingTrainer", input_parser="example",
+                                 model_table_conf=examples._vec_table, parameters=examples.P.EXAMPLES)
+    data = examples.write_dummy_input(32)
+    res = ETDolphinLauncher.launch(app, ["-input", data, "-max_num_epochs", "2", "-num_mini_batches", "8",
+                                         "-num_worker_blocks", "8", "-num_server_blocks", "4", "-num_keys", "4",
+                                         "-num_dolphin_workers", "1", "-num_servers", "1",
+                                         "-task_unit_scheduling", "off"])
+    assert res.ok, res.messages
+    ev = res.results[0]["events"]
+    assert ev.count("batch") == 16
+    # leases of 4: a flush before every sync that follows a lease, and one at each epoch end -- never between the
+    # mini-batches of a lease
+    runs = [len(r) for r in "".join("b" if e == "batch" else "|" for e in ev).split("|") if r]
+    assert max(runs) == 4 and all(r in (1, 2, 3, 4) for r in runs), ev
+    assert 4 <= ev.count("flush") <= 10, ev
