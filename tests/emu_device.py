@@ -16,7 +16,9 @@ from harmony_b200.et.executor import Executor
 
 class EmuDeviceExecutor(Executor):
     registry: Dict[str, "EmuDeviceExecutor"] = {}
-    fail_recv_on: set = set()           # executor ids whose DeviceMoveRecv raises (fault injection)
+    fail_recv_on: set = set()           # executor ids whose DeviceMoveAlloc raises (fault injection)
+    fail_send_on: set = set()           # executor ids whose DeviceMoveSend raises
+    aborted: list = []                  # (executor id, block ids) of every DeviceMoveAbort received
 
     def __init__(self, executor_id, transport, conf=None, driver_id="driver", **_: Any) -> None:
         super().__init__(executor_id, transport, conf, driver_id)
@@ -65,9 +67,12 @@ class EmuDeviceExecutor(Executor):
                              "locs": locs})
 
     def _on_DeviceMoveAbort(self, m):
+        EmuDeviceExecutor.aborted.append((self.executor_id, sorted(int(b) for b in m["block_ids"])))
         self.send_to_driver({"type": "DeviceMoveAbortAck", "op_id": m["op_id"], "table_id": m["table_id"]})
 
     def _on_DeviceMoveSend(self, m):
+        if self.executor_id in EmuDeviceExecutor.fail_send_on:
+            raise RuntimeError("emulated: bulk copy timed out")
         comps = self.tables.get_components(m["table_id"])
         self._snap = getattr(self, "_snap", {})
         for b, loc in m["locs"].items():

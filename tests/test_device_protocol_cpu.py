@@ -108,6 +108,31 @@ def test_device_move_aborts_cleanly_when_the_receiver_fails(cluster):
     np.testing.assert_array_equal(np.asarray(t0.multi_get_or_init(keys).get(30)), np.full((256, 4), 2.0))
 
 
+def test_device_move_aborts_cleanly_when_the_sender_fails(cluster):
+    """The copy (DeviceMoveSend) fails after the receiver allocated its slabs: the receiver is told to free them
+    (DeviceMoveAbort), nothing was flipped, the blocks are released and a later move succeeds."""
+    master, execs, launcher = cluster
+    master.create_table(_conf("abort2"), execs[:2]).get(30)
+    table = master.get_table("abort2")
+    t0 = launcher.executors[execs[0].id].tables.get_table("abort2")
+    keys = np.arange(256, dtype=np.int64)
+    t0.multi_update(keys, np.ones((256, 4), dtype=np.float32)).get(30)
+    before = table.get_partition_info()
+    EmuDeviceExecutor.aborted = []
+    EmuDeviceExecutor.fail_send_on = {execs[0].id}
+    try:
+        with pytest.raises(RuntimeError, match="DeviceMoveSend failed"):
+            table.move_blocks(execs[0].id, execs[1].id, 4).get(30)
+    finally:
+        EmuDeviceExecutor.fail_send_on = set()
+    assert table.get_partition_info() == before
+    assert len(EmuDeviceExecutor.aborted) == 1 and EmuDeviceExecutor.aborted[0][0] == execs[1].id
+    assert len(EmuDeviceExecutor.aborted[0][1]) == 4
+    t0.multi_update(keys, np.ones((256, 4), dtype=np.float32)).get(10)          # accessors were never stopped
+    assert table.move_blocks(execs[0].id, execs[1].id, 4).get(60).is_completed
+    np.testing.assert_array_equal(np.asarray(t0.multi_get_or_init(keys).get(30)), np.full((256, 4), 2.0))
+
+
 @pytest.mark.parametrize("optimizer", ["DeleteOneServerOptimizer", "AddOneServerOptimizer", "MoveModelBlocksOptimizer",
                                        "ExchangeOneOptimizer", "DeleteOneWorkerOptimizer"])
 def test_addvector_job_reconfigures_over_the_device_protocol(optimizer, monkeypatch):
