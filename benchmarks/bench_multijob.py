@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="dataset size multiplier")
     ap.add_argument("--epochs", type=int, default=6)
     ap.add_argument("--repartition_after_s", type=float, default=0.2)
+    ap.add_argument("--solo", action="store_true",
+                    help="first run every job ALONE on the same server (sequentially) and report the concurrent makespan "
+                         "over the slowest solo job")
     ap.add_argument("--extra", default="", help="comma-separated flags added to every job, e.g. "
                                                 "--extra=-mini_batch_grant_size,4,-task_unit_scheduling,off")
     a = ap.parse_args()
@@ -60,6 +63,18 @@ def main():
         ("LDA-2", lda, ["-input", d_lda, "-num_topics", "64", "-num_vocabs", "2000"] + common),
         ("MLR-3", mlr, ["-input", d_mlr2, "-classes", str(C), "-features", str(F), "-step_size", "0.01"] + common),
     ]
+    solo = {}
+    n_prev = 0
+    if a.solo:                       # job ids are <App>-<n> with one counter per server: solo runs take the first ids
+        for name, app, args in jobs:
+            ts = time.perf_counter()
+            r = DolphinJobLauncher.submit_job(app.APP_PATH, app.APP, args, port=port)
+            assert r.startswith("true"), r
+            jid = f"{name.split('-')[0]}-{n_prev}"
+            ok, _res = js.driver.wait_job(jid, timeout=1800)
+            solo[name] = {"ok": ok, "seconds": round(time.perf_counter() - ts, 3)}
+            n_prev += 1
+        jobs = [(f"{name.split('-')[0]}-{n_prev + i}", app, args) for i, (name, app, args) in enumerate(jobs)]
     t0 = time.perf_counter()
     wall0 = time.time()
     for name, app, args in jobs:
@@ -71,13 +86,13 @@ def main():
     def repartition():
         m = js.et_master
         deadline = time.time() + 120
-        while time.time() < deadline and not (m.has_table("model_table0") and
-                                              m.get_table("model_table0").sm.current_state == "INITIALIZED"):
+        tid = "model_table%d" % n_prev                # the first concurrent job's model table
+        while time.time() < deadline and not (m.has_table(tid) and m.get_table(tid).sm.current_state == "INITIALIZED"):
             time.sleep(0.02)
         time.sleep(a.repartition_after_s)
-        if not m.has_table("model_table0") or a.executors < 2:
+        if not m.has_table(tid) or a.executors < 2:
             return
-        table = m.get_table("model_table0")
+        table = m.get_table(tid)
         info = table.get_partition_info()
         src = max(sorted(info), key=lambda e: len(info[e]))
         dst = min((e for e in sorted(info) if e != src), key=lambda e: len(info[e]))
@@ -114,6 +129,11 @@ def main():
            "value": round(makespan, 3), "unit": "s", "higher_is_better": False, "n_executors": a.executors,
            "backend": js.backend, "scheduler": a.scheduler, "extra_flags": a.extra, "jobs": per_job, "migration": mig,
            "total_mini_batches_per_s": round(sum(j["mini_batches"] or 0 for j in per_job.values()) / makespan, 2)}
+    if solo:
+        slowest = max(v["seconds"] for v in solo.values())
+        out["solo"] = solo
+        out["makespan_over_slowest_solo"] = round(makespan / slowest, 3)
+        out["makespan_over_sum_of_solos"] = round(makespan / sum(v["seconds"] for v in solo.values()), 3)
     print(json.dumps(out), flush=True)
     js.stop(kill=True)
 
