@@ -154,6 +154,8 @@ class ClockSampler:
 def reference_arm(args):
     """The reference is 100% Java 8 / Maven / Apache REEF (no setup.py / pyproject): it cannot be
     pip-installed into baseline/_ref and there is no JDK in the image."""
+    if int(os.environ.get("RANK", "0")) != 0:       # under torchrun every rank runs this: ONE line, from rank 0
+        return 0
     ok = os.path.isdir(os.path.join(ROOT, "baseline", "_ref")) and any(
         n.endswith(".jar") for _, _, fs in os.walk(os.path.join(ROOT, "baseline", "_ref")) for n in fs)
     if not ok or subprocess.run(["which", "java"], capture_output=True).returncode != 0:
