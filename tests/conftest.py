@@ -38,3 +38,8 @@ def _gpu_test_starts_on_device0(request):
         if torch.cuda.is_available():
             torch.cuda.set_device(0)
     yield
+    if "gpu" in request.keywords:
+        # collect the test's cycles (executors, trainers, streams, events) HERE, on the main thread with device 0
+        # current, instead of inside whichever worker thread of the NEXT test happens to trigger the collector
+        import gc
+        gc.collect()
